@@ -1,0 +1,166 @@
+/* slu.h -- C ABI of libslu.so: the B200 (sm_100a) hot path of SemanticLiDARUnc.
+ *
+ * The reference (kav-institute/SemanticLiDARUnc) is pure Python and has no FFI;
+ * each entry point below replaces the numpy / eager-torch code cited beside
+ * it, and is what a reference-side ctypes binding calls.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (a torch
+ *     tensor's data_ptr()); the library allocates nothing persistent and never
+ *     frees caller memory.  h_* pointers are HOST memory read before return.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     entry point synchronises the device, none touches global device state.
+ *   - accumulators (confmat, ece_bins) are ADDED to: the caller zeroes them to
+ *     reset, which keeps the reference's update()/compute()/reset() semantics.
+ *     They are plain int64 so shards combine with one integer all-reduce and
+ *     the N-GPU result is bit-identical to the 1-GPU result.
+ *   - return value: 0 ok; <0 bad argument (SLU_E_*); >0 a cudaError_t.
+ *     slu_last_error() gives the message for the calling thread.
+ *   - image tensors are [.., C, H*W] "planar" exactly as the reference's
+ *     [B,C,H,W] contiguous tensors; HW = H*W.
+ */
+#ifndef SLU_H_
+#define SLU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLU_VERSION 100            /* 0.1.0 */
+
+#define SLU_E_ARG      (-1)        /* null / negative / inconsistent argument        */
+#define SLU_E_RANGE    (-2)        /* size outside what the kernels support           */
+#define SLU_E_ALIGN    (-3)        /* pointer not aligned as documented               */
+#define SLU_E_DEVICE   (-4)        /* not an sm_100 device / no device                */
+
+#define SLU_MAX_CLASSES 32         /* register-resident class axis                    */
+#define SLU_MAX_BINS    64         /* reliability bins                                */
+
+/* what the class axis of `d_in` holds (reference: ECEAggregator mode, src/metrics/ece.py:54-64) */
+#define SLU_IN_LOGITS 0            /* softmax over classes, per sample                */
+#define SLU_IN_PROBS  1            /* already probabilities, per sample               */
+#define SLU_IN_ALPHA  2            /* Dirichlet concentrations (T must be 1)          */
+
+/* how the top-label confidence is formed from the mean distribution p_bar */
+#define SLU_CONF_RAW     0         /* conf = max_c p_bar                              (ece.py:60-61 'logits') */
+#define SLU_CONF_RENORM  1         /* conf = max_c  max(p,0) / max(sum_c max(p,0), eps)  (ece.py:62-63 'probs') */
+/* with SLU_IN_ALPHA the distribution is alpha / (alpha0 + eps) (ece.py:57-58) and conf_mode RAW applies to it */
+
+typedef void* slu_stream_t;
+
+int         slu_version(void);
+const char* slu_last_error(void);
+/* sm count and compute capability of `device`; fails with SLU_E_DEVICE if it is not cc 10.x */
+int         slu_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3+4 fused: per-pixel reduction over T samples x C classes, plus the evaluation
+ * histograms, in ONE pass over d_in.
+ * Replaces: src/models/tester.py:412-471 (softmax, mean_T, argmax, H_norm, MI_norm, then
+ *           IoUEvaluator.update src/models/evaluator.py:39-53 and ECEAggregator.update
+ *           src/metrics/ece.py:66-90 with max_samples=None); T=1 covers the single-pass
+ *           branches src/models/trainer.py:1170-1225 and src/utils/mc_dropout.py:121-133.
+ *
+ *   d_in      [T,B,C,HW] float32
+ *   d_labels  [B,HW] int64, or NULL (then no histogram is touched)
+ *   eps       clamp inside the entropies (reference default 1e-12)
+ *   normalize 1: entropies are divided by log C (the *_norm maps); 0: left in nats
+ *   ignore    label value excluded from the ECE bins when has_ignore != 0
+ *   h_edges   n_bins+1 float32 bin edges (host), [lo,hi) with a closed last bin
+ *   outputs (each may be NULL):
+ *     d_pbar   [B,C,HW] float32   mean distribution
+ *     d_pred   [B,HW]   int64     argmax_c p_bar (first index on ties)
+ *     d_conf   [B,HW]   float32   top-label confidence per conf_mode
+ *     d_hnorm  [B,HW]   float32   -sum p_bar log p_bar / log C   (clamped at eps)
+ *     d_minorm [B,HW]   float32   max(0, (H[p_bar] - mean_t H[p_t]) / log C)
+ *   accumulators (each may be NULL):
+ *     d_confmat  [C*C]      int64  rows = label, cols = pred; labels outside [0,C) dropped
+ *     d_ece_bins [3*n_bins] int64  n | n_correct | sum(conf) in units of 2^-32
+ */
+int slu_reduce_metrics(const float* d_in, const int64_t* d_labels,
+                       int T, int B, int C, int64_t HW,
+                       int in_kind, int conf_mode, float eps, int normalize,
+                       int has_ignore, int64_t ignore,
+                       int n_bins, const float* h_edges,
+                       float* d_pbar, int64_t* d_pred, float* d_conf, float* d_hnorm, float* d_minorm,
+                       int64_t* d_confmat, int64_t* d_ece_bins,
+                       slu_stream_t stream);
+
+/* Same work with every thread loading straight from global memory (no TMA staging): used for
+ * shapes the bulk-copy path cannot take (HW % 4 != 0 or unaligned d_in) and as the A/B
+ * comparison in profiles/.  slu_reduce_metrics() dispatches to it on its own when needed. */
+int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_labels,
+                              int T, int B, int C, int64_t HW,
+                              int in_kind, int conf_mode, float eps, int normalize,
+                              int has_ignore, int64_t ignore,
+                              int n_bins, const float* h_edges,
+                              float* d_pbar, int64_t* d_pred, float* d_conf, float* d_hnorm, float* d_minorm,
+                              int64_t* d_confmat, int64_t* d_ece_bins,
+                              slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 4 standalone: histograms from already-reduced maps (integer inputs).
+ * Replaces: IoUEvaluator.update (src/models/evaluator.py:39-53) and the binning of
+ *           ECEAggregator (src/metrics/ece.py:75-90,131-140).
+ *   d_pred, d_labels [n] int64;  d_conf [n] float32 or NULL (then only the confusion matrix)
+ *   d_confmat [C*C] int64 or NULL; d_ece_bins [3*n_bins] int64 or NULL.
+ *   C may be any value up to 1024 here.
+ */
+int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const float* d_conf,
+                      int64_t n, int C, int has_ignore, int64_t ignore,
+                      int n_bins, const float* h_edges,
+                      int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1: spherical range-image projection with a nearest-range depth test, batched.
+ * Replaces: spherical_projection (src/dataset/utils.py:288-349) + to_deflection_coordinates
+ *           (:61-67) + the KITTI loader glue around it
+ *           (src/dataset/dataloader_semantic_KITTI.py:40-49 label remap, :83 range).
+ *
+ *   d_xyzi      [n_total,4] float32  all scans of the batch, concatenated (16-byte aligned)
+ *   d_raw_label [n_total]   uint32   raw labels (semantic id in the low 16 bits) or NULL
+ *   d_lut       [65536]     int32    raw id -> train id (missing ids < 0), or NULL = identity
+ *   h_offsets   [B+1]       int64    HOST array; scan b owns points [offsets[b], offsets[b+1]); B <= 256
+ *   H, W                    image size;  all angle math is float64 (the loaders feed float64)
+ *   theta_lo/hi             row range; if use_theta_range == 0 the per-scan min/max of theta is used
+ *   farthest_wins           0: nearest point wins (reference default); 1: sort_largest_first=True
+ *   d_work      workspace of slu_project_workspace_bytes(n_total, B, H*W) bytes, 16-byte aligned
+ *   outputs (each may be NULL):
+ *     d_img    [B,6,HW] float32  planes x,y,z,range,intensity,label; 0 where empty
+ *     d_pix    [n_total] int32   pixel (row*W+col) every point projects to
+ *     d_winner [B,HW]   int32    index (within its scan) of the winning point, -1 where empty
+ *     d_theta  [B,2]    float64  (theta_min, theta_max) used per scan
+ *     d_diag   [B,2]    int32    [#points with a raw id missing from the LUT,
+ *                                 #points within 4 ulp of a bin edge (index could differ from numpy's)]
+ */
+int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW);
+int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
+                      const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
+                      int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                      void* d_work,
+                      float* d_img, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                      slu_stream_t stream);
+
+/* Generic form of spherical_projection: pc [N,Cin] float64 (any Cin >= 3), one scan, output in the
+ * reference's [H,W,Cin] float32 layout (src/dataset/utils.py:341-344).  Same workspace rule with B=1. */
+int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
+                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                       void* d_work,
+                       float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                       slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2: label back-projection, pixels -> points (the reference has no code
+ * for it: documentation/dataset.md:109 describes the organised-cloud case only).
+ *   point_label[n] = label_img[scan(n)][pix[n]]
+ *   d_label_img [B,HW] int64;  d_pix [n_total] int32;  h_offsets [B+1] int64 (host);  d_out [n_total] int64
+ */
+int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix, const int64_t* h_offsets,
+                    int64_t n_total, int B, int64_t HW, int64_t* d_out, slu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLU_H_ */

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (needs /root/reference):
+    python oracle/gen_golden.py
+Every array written here is an output of reference code imported from
+/root/reference/src through oracle/_refshim.py; the only restated lines are the
+per-point (row, col) formula, which is asserted to reproduce the reference
+image before it is stored.  The two MC closures that live inside
+Tester.test_epoch (src/models/tester.py:419-451) cannot be imported, so their
+source is extracted from the reference file with `ast` at generation time and
+executed as is.
+"""
+from __future__ import annotations
+
+import ast
+import hashlib
+import json
+import math
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the script's own directory must not shadow the reference's top-level packages (metrics, losses ...)
+sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != os.path.join(ROOT, "oracle")]
+sys.path.insert(0, ROOT)
+
+from oracle import _refshim  # noqa: E402
+
+_refshim.install()
+
+from semanticlidarunc_b200 import synth  # noqa: E402
+from semanticlidarunc_b200.dataset.definitions import build_id_lut  # noqa: E402
+from oracle import projection as oproj  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def extract_closures(path, names):
+    """Compile nested function definitions out of a reference source file, unmodified."""
+    with open(path) as f:
+        src = f.read()
+    tree = ast.parse(src)
+    found = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name in names and node.name not in found:
+            node.decorator_list = []           # @torch.no_grad() only
+            found[node.name] = node
+    mod = ast.Module(body=[found[n] for n in names], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"torch": torch, "math": math}
+    exec(compile(mod, path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+# ---------------------------------------------------------------- projection
+def gen_projection():
+    from dataset.utils import spherical_projection as ref_proj
+
+    cases = {}
+
+    def run(name, xyzi, raw, H, W, theta_range=None, largest_first=False):
+        lut = build_id_lut()
+        sem = lut[(raw & 0xFFFF).astype(np.int64)].astype(np.int64)
+        pc = np.concatenate([xyzi, sem[:, None]], axis=-1)                   # float64, as the loaders
+        pc_id = np.concatenate([pc, np.arange(pc.shape[0])[:, None] + 1.0], axis=-1)
+        img, alpha, (tmin, tmax), (pmin, pmax) = ref_proj(pc_id, H, W, theta_range=theta_range,
+                                                          sort_largest_first=largest_first)
+        winner = img[..., -1].reshape(-1).astype(np.int64) - 1                # -1 = empty
+        row, col, _ = oproj.projection_indices(pc, H, W, theta_range)
+        pix = row * W + col
+        # the restated per-point indices must reproduce the reference image
+        occ = winner >= 0
+        assert (pix[winner[occ]] == np.nonzero(occ)[0]).all(), name
+        assert set(np.unique(pix)) == set(np.nonzero(occ)[0]), name
+        return {"img": img[..., :-1], "winner": winner, "pix": pix, "alpha": alpha,
+                "theta": np.array([tmin, tmax], dtype=np.float64)}
+
+    # small cases, stored in full (inputs included)
+    small = {}
+    xyzi, raw = synth.synth_scan(11, "tiny")
+    small["tiny_auto"] = (xyzi, raw, 16, 256, None, False)
+    small["tiny_range"] = (xyzi, raw, 16, 256, (-np.pi / 8, np.pi / 8), False)   # CUDAL-style clip
+    small["tiny_farthest"] = (xyzi, raw, 16, 256, None, True)
+    # edge cases: points on the +-pi seam, straight up/down, duplicates in a pixel
+    e = xyzi[:400].copy()
+    e[0, :3] = (-5.0, 0.0, 0.1)        # phi = +pi  -> wraps to last column
+    e[1, :3] = (-5.0, -0.0, 0.1)       # phi = -pi
+    e[2, :3] = (0.0, 0.0, 7.0)         # straight up
+    e[3, :3] = (0.0, 0.0, -7.0)        # straight down
+    e[4, :3] = (3.0, 0.0, 0.0)         # phi = 0, theta = 0
+    e[5, :3] = (0.0, 3.0, 0.0)         # phi = pi/2
+    e[6, :3] = e[7, :3] * 0.5          # same direction, nearer -> must win its pixel
+    small["edge"] = (e, raw[:400], 8, 32, None, False)
+    small["ragged_1pt"] = (xyzi[:1].copy(), raw[:1], 4, 8, (-0.5, 0.5), False)
+    out = {}
+    for name, (a, b, H, W, tr, lf) in small.items():
+        res = run(name, a, b, H, W, tr, lf)
+        out[name + "/xyzi"] = a
+        out[name + "/raw"] = b
+        out[name + "/hw"] = np.array([H, W])
+        out[name + "/theta_range"] = np.array(tr if tr is not None else [np.nan, np.nan])
+        out[name + "/largest_first"] = np.array(int(lf))
+        for k, v in res.items():
+            if k != "alpha":
+                out[name + "/" + k] = v
+        out[name + "/alpha_sha"] = np.frombuffer(bytes.fromhex(sha(res["alpha"])), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "projection_small.npz"), **out)
+
+    # full-size cases: digests only (inputs regenerate from the seed)
+    for name, sensor, seed, tr in (("hdl64_seed0", "hdl64", 0, None), ("hdl64_seed1", "hdl64", 1, None),
+                                   ("os1_128_seed0", "os1-128", 0, None),
+                                   ("os1_128_cudal", "os1-128", 2, (-np.pi / 8, np.pi / 8))):
+        xyzi, raw = synth.synth_scan(seed, sensor)
+        H, W = synth.SENSORS[sensor][4:6]
+        res = run(name, xyzi, raw, H, W, tr)
+        cases[name] = {
+            "sensor": sensor, "seed": seed, "H": H, "W": W,
+            "theta_range": None if tr is None else list(tr),
+            "n_points": int(xyzi.shape[0]), "xyzi_sha": sha(xyzi), "raw_sha": sha(raw),
+            "img_sha": sha(res["img"]), "winner_sha": sha(res["winner"]), "pix_sha": sha(res["pix"]),
+            "theta_min": float(res["theta"][0]), "theta_max": float(res["theta"][1]),
+            "occupied": int((res["winner"] >= 0).sum()),
+        }
+    return cases
+
+
+def gen_kitti_loader():
+    """SemanticKitti.__getitem__ (resize off) on a temp .bin/.label pair."""
+    from dataset.dataloader_semantic_KITTI import SemanticKitti
+
+    xyzi, raw = synth.synth_scan(21, "tiny")
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "000000.bin"), os.path.join(d, "000000.label")
+        xyzi.tofile(fb)
+        raw.tofile(fl)
+        ds = SemanticKitti([(fb, fl)], rotate=False, flip=False, projection=(16, 256), resize=False)
+        rng_img, refl, xyz, normals, sem = ds[0]
+    np.savez_compressed(os.path.join(GOLD, "kitti_loader.npz"), xyzi=xyzi, raw=raw, hw=np.array([16, 256]),
+                        range=rng_img.numpy(), reflectivity=refl.numpy(), xyz=xyz.numpy(),
+                        normals=normals.numpy(), semantics=sem.numpy())
+
+
+# ---------------------------------------------------------------- uncertainty
+def gen_mc():
+    pe, mi = extract_closures(os.path.join(_refshim.REF_SRC, "models", "tester.py"),
+                              ["mc_predictive_entropy_norm", "mc_mutual_information_norm"])
+    from utils.mc_dropout import predictive_entropy_mc
+    import torch.nn.functional as F
+
+    out = {}
+    for name, (T, B, C, H, W, scale) in {"mc_small": (5, 2, 20, 4, 64, 3.0),
+                                         "mc_peaked": (3, 1, 20, 2, 64, 25.0),
+                                         "mc_c7": (4, 1, 7, 3, 40, 2.0)}.items():
+        logits, labels = synth.synth_mc_logits(101, T, B, C, H, W, scale=scale)
+        with torch.no_grad():
+            probs = F.softmax(logits, dim=2)                 # tester.py:412
+            p_bar = probs.mean(dim=0)                        # :415
+            preds = p_bar.argmax(dim=1)                      # :417
+            H_norm = pe(probs)
+            MI_norm = mi(probs)
+            H_mc = predictive_entropy_mc(probs)
+        out.update({name + "/logits": logits.numpy(), name + "/labels": labels.numpy(),
+                    name + "/p_bar": p_bar.numpy(), name + "/pred": preds.numpy(),
+                    name + "/H_norm": H_norm.numpy(), name + "/MI_norm": MI_norm.numpy(),
+                    name + "/H_mc": H_mc.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "mc_reduce.npz"), **out)
+
+
+def gen_evidential():
+    import models.probability_helper as ph
+    from metrics.auroc import AUROCAggregator
+
+    out = {}
+    for name, (B, C, H, W, scale) in {"ev_small": (2, 20, 4, 64, 3.0), "ev_strong": (1, 20, 2, 64, 12.0)}.items():
+        o, labels = synth.synth_evidential_logits(202, B, C, H, W, scale=scale)
+        with torch.no_grad():
+            alpha = ph.to_alpha_concentrations_from_shape_and_scale(o[:, :C], o[:, C:C + 1])
+            Hn = ph.get_predictive_entropy_norm(alpha)
+            Hp = ph.get_predictive_entropy(alpha)
+            AU = ph.get_aleatoric_uncertainty(alpha)
+            EU = ph.get_epistemic_uncertainty(alpha)
+            MI = AUROCAggregator(mode="alpha", score="mi_norm")._uncertainty_score(alpha)
+            pred = torch.softmax(o[:, :C], dim=1).argmax(dim=1)            # tester.py:493-495
+        out.update({name + "/outputs": o.numpy(), name + "/labels": labels.numpy(), name + "/alpha": alpha.numpy(),
+                    name + "/H_norm": Hn.numpy(), name + "/H": Hp.numpy(), name + "/AU": AU.numpy(),
+                    name + "/EU": EU.numpy(), name + "/MI_norm": MI.numpy(), name + "/pred": pred.numpy()})
+    np.savez_compressed(os.path.join(GOLD, "evidential.npz"), **out)
+
+
+# ---------------------------------------------------------------- metrics
+def gen_metrics():
+    from models.evaluator import IoUEvaluator
+    from metrics.ece import ECEAggregator
+
+    out = {}
+    g = torch.Generator().manual_seed(303)
+    C = 20
+    preds = torch.randint(-1, C + 1, (3, 8, 64), generator=g)     # includes out-of-range -1 and C
+    targets = torch.randint(-1, C + 1, (3, 8, 64), generator=g)
+    ev = IoUEvaluator(C)
+    ev.update(preds[:2], targets[:2])
+    ev.update(preds[2:], targets[2:])
+    names = {i: str(i) for i in range(C)}
+    miou, per = ev.compute(names, test_mask=[0] + [1] * (C - 1), ignore_gt=[0])
+    miou_all, per_all = ev.compute(names)
+    out.update({"iou/preds": preds.numpy(), "iou/targets": targets.numpy(), "iou/confmat": ev.confmat.numpy(),
+                "iou/miou": np.array(miou), "iou/per_class": np.array([per[str(i)] for i in range(C)]),
+                "iou/miou_all": np.array(miou_all), "iou/per_class_all": np.array([per_all[str(i)] for i in range(C)])})
+
+    for mode in ("alpha", "logits", "probs"):
+        x = torch.randn((2, C, 8, 64), generator=g) * 3.0
+        if mode == "alpha":
+            x = torch.nn.functional.softplus(x) + 1.0
+        elif mode == "probs":
+            x = torch.softmax(x, dim=1)
+        labels = torch.randint(0, C, (2, 8, 64), generator=g)
+        # make about half the predictions correct so acc is not ~1/C
+        with torch.no_grad():
+            am = x.argmax(1)
+            take = torch.rand((2, 8, 64), generator=g) < 0.5
+            labels = torch.where(take, am, labels)
+        agg = ECEAggregator(n_bins=15, mode=mode, ignore_index=0, max_samples=None)
+        agg.update(x[:1], labels[:1])
+        agg.update(x[1:], labels[1:])
+        (ece, mce), stats, _ = agg.compute(save_plot_path=os.path.join(tempfile.gettempdir(), "slu_gold.png"))
+        out.update({f"ece_{mode}/preds": x.numpy(), f"ece_{mode}/labels": labels.numpy(),
+                    f"ece_{mode}/conf": agg._conf.numpy(), f"ece_{mode}/correct": agg._correct.numpy(),
+                    f"ece_{mode}/n": stats["n"].to_numpy(), f"ece_{mode}/acc": stats["acc"].to_numpy(),
+                    f"ece_{mode}/avg_conf": stats["conf"].to_numpy(),
+                    f"ece_{mode}/ece_mce": np.array([ece, mce])})
+    # empty aggregator: 2-tuple with NaNs (ece.py:157-158)
+    r = ECEAggregator(n_bins=15, mode="probs", ignore_index=0).compute(save_plot_path=None)
+    out["ece_empty/len"] = np.array(len(r))
+    np.savez_compressed(os.path.join(GOLD, "metrics.npz"), **out)
+
+
+# ---------------------------------------------------------------- losses
+def gen_losses():
+    from losses.dirichlet_losses import DirichletMSELoss
+    from losses.regularizers import KL_offClasses_to_uniform
+
+    g = torch.Generator().manual_seed(404)
+    B, C, H, W = 2, 20, 4, 32
+    alpha = (torch.nn.functional.softplus(torch.randn((B, C, H, W), generator=g) * 3.0) + 1.0)
+    target = torch.randint(0, C, (B, H, W), generator=g)
+    out = {"alpha": alpha.numpy(), "target": target.numpy()}
+    for name, mod in (("mse", DirichletMSELoss(ignore_index=0)), ("kl", KL_offClasses_to_uniform(ignore_index=0))):
+        a = alpha.clone().requires_grad_(True)
+        loss = mod(a, target)
+        (grad,) = torch.autograd.grad(loss, a)
+        out[name + "/loss"] = loss.detach().numpy()
+        out[name + "/grad"] = grad.numpy()
+    np.savez_compressed(os.path.join(GOLD, "losses.npz"), **out)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(1)
+    manifest = {
+        "generator": "oracle/gen_golden.py",
+        "reference_root": _refshim.REF_ROOT,
+        "versions": {"python": sys.version.split()[0], "numpy": np.__version__, "torch": torch.__version__},
+        "projection_full": gen_projection(),
+    }
+    gen_kitti_loader()
+    gen_mc()
+    gen_evidential()
+    gen_metrics()
+    gen_losses()
+    with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    for fn in sorted(os.listdir(GOLD)):
+        print(fn, os.path.getsize(os.path.join(GOLD, fn)))
+
+
+if __name__ == "__main__":
+    main()

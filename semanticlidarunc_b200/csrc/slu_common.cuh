@@ -1,0 +1,126 @@
+// slu_common.cuh -- shared host/device helpers of libslu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "slu.h"
+
+namespace slu {
+
+// ---- host: error plumbing (thread-local message behind slu_last_error) -------------------
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int sm_count_current_device();
+
+#define SLU_CUDA(call)                                            \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return slu::cuda_fail(e__, #call); \
+    } while (0)
+
+#define SLU_LAUNCH_CHECK(what)                                      \
+    do {                                                            \
+        cudaError_t e__ = cudaGetLastError();                       \
+        if (e__ != cudaSuccess) return slu::cuda_fail(e__, what);   \
+    } while (0)
+
+#ifdef __CUDACC__
+// ---- device: PTX wrappers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, both 16 B aligned.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// streaming 4-byte load: read-only path, do not keep in L1
+__device__ __forceinline__ float ldg_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// ---- device: warp-aggregated shared-memory histogram updates -------------------------------
+// One shared atomic per DISTINCT key in the warp instead of one per lane.
+__device__ __forceinline__ void warp_hist_add(unsigned* hist, int key, bool active) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(act, key);
+    if ((threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(&hist[key], (unsigned)__popc(peers));
+}
+
+// Reliability bins: n, n_correct (u32 per CTA) and sum(conf) as 2^-32 fixed point (u64).
+// Loops over the distinct bins present in the warp; all 32 lanes must call it.
+__device__ __forceinline__ void warp_bins_add(unsigned* bin_n, unsigned* bin_c, unsigned long long* bin_s,
+                                              int bin, bool correct, float conf, bool active) {
+    const unsigned lane = threadIdx.x & 31;
+    // conf in [0,1]: conf * 2^32 is exact for conf >= 2^-9 and fits 33 bits
+    const unsigned long long fx = active ? __float2ull_rn(conf * 4294967296.0f) : 0ull;
+    const unsigned fx_lo = (unsigned)(fx & 0xffffu), fx_hi = (unsigned)(fx >> 16);
+    unsigned todo = __ballot_sync(0xffffffffu, active);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int k = __shfl_sync(0xffffffffu, bin, leader);
+        const bool mine = active && (bin == k);
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        const unsigned ok = __ballot_sync(0xffffffffu, mine && correct);
+        const unsigned lo = __reduce_add_sync(0xffffffffu, mine ? fx_lo : 0u);
+        const unsigned hi = __reduce_add_sync(0xffffffffu, mine ? fx_hi : 0u);
+        if (lane == (unsigned)leader) {
+            atomicAdd(&bin_n[k], (unsigned)__popc(grp));
+            if (ok) atomicAdd(&bin_c[k], (unsigned)__popc(ok));
+            atomicAdd(&bin_s[k], ((unsigned long long)hi << 16) + lo);
+        }
+        todo &= ~grp;
+    }
+}
+
+// Bin of a confidence under np.histogram's rule: edges[k] <= v < edges[k+1], last bin closed.
+// Returns -1 when v is NaN or outside [edges[0], edges[n_bins]].
+__device__ __forceinline__ int find_bin(const float* edges, int n_bins, float v) {
+    if (!(v >= edges[0]) || !(v <= edges[n_bins])) return -1;
+    int k = (int)(v * (float)n_bins);
+    k = k < 0 ? 0 : (k > n_bins - 1 ? n_bins - 1 : k);
+    while (k > 0 && v < edges[k]) --k;
+    while (k < n_bins - 1 && v >= edges[k + 1]) ++k;
+    return k;
+}
+#endif  // __CUDACC__
+
+}  // namespace slu

@@ -1,0 +1,138 @@
+// slu_hist.cu -- stage 4 standalone: confusion matrix + reliability bins from reduced maps.
+//
+// Replaces (reference file:line): IoUEvaluator.update src/models/evaluator.py:39-53
+// (bincount(t*C+p) on the CPU after a D2H copy of preds/labels) and the binning half of
+// ECEAggregator (src/metrics/ece.py:75-90 keeps every valid pixel on the host, :131-140 sorts them
+// three times at compute()).  Here the state is the histogram itself: C*C + 3*n_bins int64.
+//
+// HBM-bound: 8 (pred) + 8 (label) + 4 (conf) = 20 B/pixel read, nothing written but the counts.
+// Each thread loads 4 independent elements before touching shared memory; per-CTA histograms in
+// shared memory take one atomic per DISTINCT key per warp (__match_any_sync), which is what makes
+// spatially coherent label maps cheap; one global atomic per non-zero cell per CTA at the end.
+#include "slu_common.cuh"
+
+namespace slu {
+
+constexpr int HIST_THREADS = 256;
+constexpr int HIST_UNROLL = 4;
+constexpr int HIST_SMEM_CELLS = 64 * 64;     // confusion matrices up to C=64 live in shared memory
+
+struct HistParams {
+    const long long* pred;
+    const long long* labels;
+    const float* conf;
+    long long n;
+    int C;
+    int has_ignore;
+    long long ignore;
+    int n_bins;
+    float edges[SLU_MAX_BINS + 1];
+    unsigned long long* confmat;
+    unsigned long long* bins;
+};
+
+template <bool SMEM_CM>
+__global__ void __launch_bounds__(HIST_THREADS) confusion_ece_kernel(const __grid_constant__ HistParams p) {
+    __shared__ unsigned cm[SMEM_CM ? HIST_SMEM_CELLS : 1];
+    __shared__ unsigned bin_n[SLU_MAX_BINS], bin_c[SLU_MAX_BINS];
+    __shared__ unsigned long long bin_s[SLU_MAX_BINS];
+    __shared__ float edges[SLU_MAX_BINS + 1];
+    const int tid = threadIdx.x;
+    const int cells = p.C * p.C;
+    if (SMEM_CM)
+        for (int i = tid; i < cells; i += HIST_THREADS) cm[i] = 0;
+    for (int i = tid; i < SLU_MAX_BINS; i += HIST_THREADS) { bin_n[i] = 0; bin_c[i] = 0; bin_s[i] = 0ull; }
+    for (int i = tid; i <= p.n_bins; i += HIST_THREADS) edges[i] = p.edges[i];
+    __syncthreads();
+
+    const long long chunk = (long long)HIST_THREADS * HIST_UNROLL;
+    // whole warps stay in the loop together: the warp-aggregated updates need all 32 lanes
+    for (long long base = (long long)blockIdx.x * chunk; base < p.n; base += (long long)gridDim.x * chunk) {
+        long long pr[HIST_UNROLL], lb[HIST_UNROLL];
+        float cf[HIST_UNROLL];
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; ++u) {
+            const long long i = base + (long long)u * HIST_THREADS + tid;
+            const bool in = i < p.n;
+            pr[u] = in ? __ldg(p.pred + i) : -1;
+            lb[u] = in ? __ldg(p.labels + i) : -1;
+            cf[u] = (in && p.conf) ? __ldg(p.conf + i) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < HIST_UNROLL; ++u) {
+            const bool in = base + (long long)u * HIST_THREADS + tid < p.n;
+            if (p.confmat) {
+                const bool ok = in && lb[u] >= 0 && lb[u] < p.C && pr[u] >= 0 && pr[u] < p.C;   // evaluator.py:49
+                const int key = ok ? (int)lb[u] * p.C + (int)pr[u] : 0;
+                if (SMEM_CM) {
+                    warp_hist_add(cm, key, ok);
+                } else {
+                    const unsigned act = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const unsigned peers = __match_any_sync(act, key);
+                        if ((tid & 31) == (__ffs(peers) - 1)) atomicAdd(&p.confmat[key], (unsigned long long)__popc(peers));
+                    }
+                }
+            }
+            if (p.bins) {
+                const float c = fminf(fmaxf(cf[u], 0.f), 1.f);
+                const int bin = (cf[u] == cf[u]) ? find_bin(edges, p.n_bins, c) : -1;
+                const bool ok = in && bin >= 0 && !(p.has_ignore && lb[u] == p.ignore);
+                warp_bins_add(bin_n, bin_c, bin_s, bin, pr[u] == lb[u], c, ok);
+            }
+        }
+    }
+    __syncthreads();
+    if (SMEM_CM && p.confmat)
+        for (int i = tid; i < cells; i += HIST_THREADS)
+            if (cm[i]) atomicAdd(&p.confmat[i], (unsigned long long)cm[i]);
+    if (p.bins)
+        for (int i = tid; i < p.n_bins; i += HIST_THREADS) {
+            if (bin_n[i]) atomicAdd(&p.bins[i], (unsigned long long)bin_n[i]);
+            if (bin_c[i]) atomicAdd(&p.bins[p.n_bins + i], (unsigned long long)bin_c[i]);
+            if (bin_s[i]) atomicAdd(&p.bins[2 * p.n_bins + i], bin_s[i]);
+        }
+}
+
+}  // namespace slu
+
+extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const float* d_conf,
+                                 int64_t n, int C, int has_ignore, int64_t ignore,
+                                 int n_bins, const float* h_edges,
+                                 int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
+    using namespace slu;
+    if (n < 0) return fail(SLU_E_ARG, "n=%lld < 0", (long long)n);
+    if (n == 0) return 0;
+    if (!d_pred || !d_labels) return fail(SLU_E_ARG, "d_pred / d_labels is NULL");
+    if (C < 1 || C > 1024) return fail(SLU_E_RANGE, "C=%d outside [1,1024]", C);
+    if (d_ece_bins) {
+        if (!d_conf) return fail(SLU_E_ARG, "reliability bins requested without d_conf");
+        if (n_bins < 1 || n_bins > SLU_MAX_BINS) return fail(SLU_E_RANGE, "n_bins=%d outside [1,%d]", n_bins, SLU_MAX_BINS);
+        if (!h_edges) return fail(SLU_E_ARG, "h_edges is NULL");
+        for (int i = 0; i < n_bins; ++i)
+            if (!(h_edges[i] < h_edges[i + 1])) return fail(SLU_E_ARG, "bin edges must increase strictly");
+    }
+    if (!d_confmat && !d_ece_bins) return 0;
+    HistParams p{};
+    p.pred = reinterpret_cast<const long long*>(d_pred);
+    p.labels = reinterpret_cast<const long long*>(d_labels);
+    p.conf = d_conf;
+    p.n = n; p.C = C; p.has_ignore = has_ignore; p.ignore = ignore;
+    p.n_bins = d_ece_bins ? n_bins : 0;
+    for (int i = 0; i <= p.n_bins && d_ece_bins; ++i) p.edges[i] = h_edges[i];
+    p.confmat = reinterpret_cast<unsigned long long*>(d_confmat);
+    p.bins = reinterpret_cast<unsigned long long*>(d_ece_bins);
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long chunk = (long long)HIST_THREADS * HIST_UNROLL;
+    const long long want = (n + chunk - 1) / chunk;
+    const long long cap = 8LL * sms;                       // 8 resident CTAs of 256 threads per SM
+    const int grid = (int)(want < cap ? want : cap);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (C * C <= HIST_SMEM_CELLS)
+        confusion_ece_kernel<true><<<grid, HIST_THREADS, 0, st>>>(p);
+    else
+        confusion_ece_kernel<false><<<grid, HIST_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("confusion_ece_kernel");
+    return 0;
+}

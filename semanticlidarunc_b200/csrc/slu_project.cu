@@ -1,0 +1,457 @@
+// slu_project.cu -- stage 1 (spherical range-image projection with a depth test) and stage 2
+// (label back-projection).
+//
+// Replaces (reference file:line): spherical_projection src/dataset/utils.py:288-349,
+// to_deflection_coordinates :61-67, and the KITTI loader glue around them
+// (src/dataset/dataloader_semantic_KITTI.py:40-49 label remap + float64 concat, :83 fp32 range).
+// The reference sorts the cloud far->near (argsort + gather), digitizes against two linspace edge
+// arrays and lets a fancy-index scatter keep the last write; here every point is handled in place:
+//
+//   K0 init      key[b,px] = ~0, winner[b,px] = INT_MAX, theta min/max cells, diagnostics
+//   K1 angles    per point (fp64, same operation order as numpy, no FMA contraction):
+//                r, phi, theta -> column index from the fixed azimuth edges, range key, and a
+//                block-reduced theta min/max per scan (ordered-integer atomicMin/Max)
+//   K2 rows      per point: row index from the scan's theta edges, pix = row*W+col,
+//                atomicMin(key[b,pix], range bits)                     -- 64-bit, exact fp64 order
+//   K3 ties      per point: if my range bits == key[b,pix]: atomicMin(winner[b,pix], my index)
+//                -- deterministic "lowest index" among exactly equal ranges
+//   K4 resolve   per pixel: gather the winner, write the channel planes (0 where empty)
+//
+// The depth test compares the FULL float64 range (a positive double's bit pattern is monotone),
+// so it reproduces the reference's sort order exactly; packing range and index into one 64-bit
+// word would have to truncate the range to ~44 bits and would create ties the reference does not
+// have.  A scan (<= 4 MB) and its image stay in the 126 MB L2, so only K1's read of the points and
+// K4's write of the image are HBM traffic: 20 B/point + 24 B/pixel.
+//
+// Bin edges are numpy's linspace restated bit for bit: step = (stop-start)/(num-1),
+// edge(i) = fl(fl(i*step) + start), edge(num-1) = stop.  cnt = #{edges <= v} is found by a guess
+// from the step and an exact fix-up against those edges, then row = (H-1-cnt) mod H (the
+// reference's digitize(...)-1 with negative indices wrapping).
+#include <math.h>
+#include "slu_common.cuh"
+
+namespace slu {
+
+constexpr int PT_THREADS = 256;
+constexpr int MAX_SCANS = 256;
+constexpr double HALF_PI = 1.5707963267948966;   // np.pi / 2
+constexpr double PI = 3.141592653589793;         // np.pi
+
+struct Edges {            // numpy.linspace(start, stop, num) without materialising it
+    double start, stop, step, delta;
+    int num;
+};
+
+__host__ __device__ inline Edges make_edges(double start, double stop, int num) {
+    Edges e;
+    e.start = start; e.stop = stop; e.num = num;
+    e.delta = stop - start;
+    e.step = num > 1 ? e.delta / (double)(num - 1) : 0.0;
+    return e;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ double edge_at(const Edges& e, int i) {
+    if (i == e.num - 1 && e.num > 1) return e.stop;
+    if (e.num == 1) return e.start;
+    if (e.step != 0.0) return __dadd_rn(__dmul_rn((double)i, e.step), e.start);
+    // numpy's denormal/zero-step branch: y = (i / div) * delta + start
+    return __dadd_rn(__dmul_rn(__ddiv_rn((double)i, (double)(e.num - 1)), e.delta), e.start);
+}
+
+// #{i : edge(i) <= v}; NaN counts as beyond every edge (numpy sorts NaN last).  `near` reports
+// whether v lies within 4 ulp of an edge, where a 1-2 ulp difference between CUDA's and numpy's
+// atan2 could move the point to the neighbouring bin.
+__device__ __forceinline__ int count_le(const Edges& e, double v, bool& near) {
+    near = false;
+    if (v != v) return e.num;
+    int i;                                          // candidate: last edge <= v
+    if (e.step > 0.0) {
+        const double g = floor((v - e.start) / e.step);
+        i = g < -1.0 ? -1 : (g > (double)(e.num - 1) ? e.num - 1 : (int)g);
+    } else {
+        i = -1;
+    }
+    while (i >= 0 && edge_at(e, i) > v) --i;
+    while (i + 1 < e.num && edge_at(e, i + 1) <= v) ++i;
+    const double tol = 8.9e-16 * fmax(fabs(v), 2.3e-308);
+    if (i >= 0 && fabs(v - edge_at(e, i)) <= tol) near = true;
+    if (i + 1 < e.num && fabs(edge_at(e, i + 1) - v) <= tol) near = true;
+    return i + 1;
+}
+
+__device__ __forceinline__ unsigned long long order_bits(double d) {     // monotone double -> u64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unorder_bits(unsigned long long u) {
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+#endif
+
+struct ProjParams {
+    // input, one of the two forms
+    const float4* xyzi;            // [n_total] x,y,z,intensity
+    const unsigned* raw_label;     // [n_total] or NULL
+    const int* lut;                // [65536] or NULL
+    const double* pc;              // generic form: [N,Cin] float64
+    int cin;
+    long long offsets[MAX_SCANS + 1];
+    int B, H, W;
+    long long HW;
+    int use_range;
+    double theta_lo, theta_hi;
+    int farthest;
+    // workspace
+    double* theta;                 // [n_total]
+    unsigned long long* rkey;      // [n_total]
+    int* col;                      // [n_total]
+    unsigned long long* key;       // [B*HW]
+    unsigned long long* tminmax;   // [B*2] ordered bits: min | max
+    // outputs
+    int* pix;                      // [n_total]
+    int* winner;                   // [B*HW]
+    float* img;                    // [B,6,HW] planes, or [H,W,Cin] generic
+    double* theta_out;             // [B,2]
+    int* diag;                     // [B,2]
+};
+
+__global__ void __launch_bounds__(PT_THREADS) proj_init_kernel(const __grid_constant__ ProjParams p) {
+    const long long total = (long long)p.B * p.HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        p.key[i] = ~0ull;
+        p.winner[i] = 0x7fffffff;
+    }
+    if (blockIdx.x == 0) {
+        for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+            p.tminmax[2 * b] = ~0ull;
+            p.tminmax[2 * b + 1] = 0ull;
+            p.diag[2 * b] = 0;
+            p.diag[2 * b + 1] = 0;
+        }
+    }
+}
+
+template <bool GENERIC>
+__global__ void __launch_bounds__(PT_THREADS) proj_angles_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    const Edges ew = make_edges(-PI, PI, p.W);
+    double tmin = INFINITY, tmax = -INFINITY;
+    int missing = 0, near_cnt = 0;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        double x, y, z;
+        if (GENERIC) {
+            const double* q = p.pc + n * p.cin;
+            x = q[0]; y = q[1]; z = q[2];
+        } else {
+            const float4 v = __ldg(p.xyzi + n);
+            x = (double)v.x; y = (double)v.y; z = (double)v.z;
+            if (p.raw_label && p.lut && __ldg(p.lut + (__ldg(p.raw_label + n) & 0xffffu)) < 0) ++missing;
+        }
+        // r = sqrt(x**2 + y**2 + z**2), p = sqrt(x**2 + y**2)   (utils.py:299, :63), each op rounded
+        const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
+        const double sxy = __dadd_rn(xx, yy);
+        const double r = __dsqrt_rn(__dadd_rn(sxy, zz));
+        const double rho = __dsqrt_rn(sxy);
+        const double phi = atan2(y, x);                                     // :64
+        const double theta = __dadd_rn(-atan2(rho, z), HALF_PI);            // :66
+        bool near;
+        const int cnt_w = count_le(ew, phi, near);
+        if (near) ++near_cnt;
+        int c = (p.W - 1 - cnt_w) % p.W;
+        if (c < 0) c += p.W;
+        p.col[n] = c;
+        p.theta[n] = theta;
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
+        p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
+        if (theta == theta) { tmin = fmin(tmin, theta); tmax = fmax(tmax, theta); }
+    }
+    // block reduction of theta min/max and the diagnostics
+    __shared__ double s_min[PT_THREADS / 32], s_max[PT_THREADS / 32];
+    __shared__ int s_miss[PT_THREADS / 32], s_near[PT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        missing += __shfl_xor_sync(0xffffffffu, missing, o);
+        near_cnt += __shfl_xor_sync(0xffffffffu, near_cnt, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_min[w] = tmin; s_max[w] = tmax; s_miss[w] = missing; s_near[w] = near_cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < PT_THREADS / 32; ++i) {
+            tmin = fmin(tmin, s_min[i]); tmax = fmax(tmax, s_max[i]);
+            missing += s_miss[i]; near_cnt += s_near[i];
+        }
+        if (tmin <= tmax) {
+            atomicMin(&p.tminmax[2 * b], order_bits(tmin));
+            atomicMax(&p.tminmax[2 * b + 1], order_bits(tmax));
+        }
+        if (missing) atomicAdd(&p.diag[2 * b], missing);
+        if (near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
+    }
+}
+
+__device__ __forceinline__ void scan_theta_range(const ProjParams& p, int b, double& lo, double& hi) {
+    if (p.use_range) { lo = p.theta_lo; hi = p.theta_hi; return; }
+    const unsigned long long ulo = p.tminmax[2 * b], uhi = p.tminmax[2 * b + 1];
+    if (ulo == ~0ull) { lo = 0.0; hi = 0.0; return; }          // empty scan
+    lo = unorder_bits(ulo);
+    hi = unorder_bits(uhi);
+}
+
+__global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    double lo, hi;
+    scan_theta_range(p, b, lo, hi);
+    const Edges eh = make_edges(lo, hi, p.H);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.theta_out) { p.theta_out[2 * b] = lo; p.theta_out[2 * b + 1] = hi; }
+    int near_cnt = 0;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        bool near;
+        const int cnt_h = count_le(eh, p.theta[n], near);
+        // the scan's own extreme points sit exactly ON the first/last edge by construction
+        if (near && !p.use_range) near = !(p.theta[n] == lo || p.theta[n] == hi);
+        if (near) ++near_cnt;
+        int r = (p.H - 1 - cnt_h) % p.H;
+        if (r < 0) r += p.H;
+        const int px = r * p.W + p.col[n];
+        p.pix[n] = px;
+        atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
+    }
+    near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
+    if ((threadIdx.x & 31) == 0 && near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
+}
+
+__global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        const long long cell = (long long)b * p.HW + p.pix[n];
+        if (p.rkey[n] == p.key[cell]) atomicMin(&p.winner[cell], (int)(n - n0));
+    }
+}
+
+// planes: 0 x, 1 y, 2 z, 3 range (fp32 norm of the fp32 xyz, dataloader_semantic_KITTI.py:83),
+//         4 intensity, 5 label (train id as float, as the reference's float32 image carries it)
+__global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b];
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < p.HW; px += (long long)gridDim.x * blockDim.x) {
+        const long long cell = (long long)b * p.HW + px;
+        int w = p.winner[cell];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lab = 0.f, rng = 0.f;
+        if (w == 0x7fffffff) {
+            w = -1;
+        } else {
+            v = __ldg(p.xyzi + n0 + w);
+            if (p.raw_label) {
+                const unsigned raw = __ldg(p.raw_label + n0 + w) & 0xffffu;
+                lab = (float)(p.lut ? __ldg(p.lut + raw) : (int)raw);
+            }
+            rng = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+        }
+        p.winner[cell] = w;
+        if (p.img) {
+            float* o = p.img + (long long)b * 6 * p.HW + px;
+            o[0] = v.x; o[p.HW] = v.y; o[2 * p.HW] = v.z; o[3 * p.HW] = rng; o[4 * p.HW] = v.w; o[5 * p.HW] = lab;
+        }
+    }
+}
+
+// generic form: [H,W,Cin] float32 = float(pc[winner]) per channel (utils.py:341-344)
+__global__ void __launch_bounds__(PT_THREADS) proj_resolve_hwc_kernel(const __grid_constant__ ProjParams p) {
+    const long long total = p.HW * p.cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long px = i / p.cin;
+        const int c = (int)(i - px * p.cin);
+        const int w = p.winner[px];
+        if (p.img) p.img[i] = (w == 0x7fffffff || w < 0) ? 0.f : (float)p.pc[(long long)w * p.cin + c];
+    }
+}
+__global__ void __launch_bounds__(PT_THREADS) proj_fix_winner_kernel(const __grid_constant__ ProjParams p) {
+    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < p.HW; px += (long long)gridDim.x * blockDim.x)
+        if (p.winner[px] == 0x7fffffff) p.winner[px] = -1;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) backproject_kernel(const long long* __restrict__ label_img,
+                                                                 const int* __restrict__ pix,
+                                                                 const __grid_constant__ ProjParams p,
+                                                                 long long* __restrict__ out) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x)
+        out[n] = __ldg(label_img + (long long)b * p.HW + __ldg(pix + n));
+}
+
+// ---- host ------------------------------------------------------------------------------------------
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, total;
+};
+static Workspace carve(int64_t n_total, int B, int64_t HW) {
+    Workspace w;
+    int64_t o = 0;
+    w.theta = o;   o = align_up(o + n_total * 8, 256);
+    w.rkey = o;    o = align_up(o + n_total * 8, 256);
+    w.key = o;     o = align_up(o + (int64_t)B * HW * 8, 256);
+    w.tminmax = o; o = align_up(o + (int64_t)B * 16, 256);
+    w.col = o;     o = align_up(o + n_total * 4, 256);
+    w.pix = o;     o = align_up(o + n_total * 4, 256);
+    w.winner = o;  o = align_up(o + (int64_t)B * HW * 4, 256);
+    w.diag = o;    o = align_up(o + (int64_t)B * 8, 256);
+    w.total = o;
+    return w;
+}
+
+static int point_grid_x(const long long* offsets, int B, int sms) {
+    long long max_n = 1;
+    for (int b = 0; b < B; ++b) max_n = offsets[b + 1] - offsets[b] > max_n ? offsets[b + 1] - offsets[b] : max_n;
+    long long gx = (max_n + PT_THREADS - 1) / PT_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;           // ~8 resident CTAs per SM over the batch
+    if (gx > cap) gx = cap;
+    return (int)(gx < 1 ? 1 : gx);
+}
+
+static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t* d_pix, int32_t* d_winner,
+                          int32_t* d_diag, bool generic, cudaStream_t st) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    if ((reinterpret_cast<uintptr_t>(d_work) & 15) != 0) return fail(SLU_E_ALIGN, "d_work not 16-byte aligned");
+    const Workspace w = carve(n_total, p.B, p.HW);
+    char* base = static_cast<char*>(d_work);
+    p.theta = reinterpret_cast<double*>(base + w.theta);
+    p.rkey = reinterpret_cast<unsigned long long*>(base + w.rkey);
+    p.col = reinterpret_cast<int*>(base + w.col);
+    p.key = reinterpret_cast<unsigned long long*>(base + w.key);
+    p.tminmax = reinterpret_cast<unsigned long long*>(base + w.tminmax);
+    p.pix = d_pix ? d_pix : reinterpret_cast<int*>(base + w.pix);
+    p.winner = d_winner ? d_winner : reinterpret_cast<int*>(base + w.winner);
+    p.diag = d_diag ? d_diag : reinterpret_cast<int*>(base + w.diag);
+
+    const long long cells = (long long)p.B * p.HW;
+    const int gi = (int)((cells + PT_THREADS - 1) / PT_THREADS < 8LL * sms ? (cells + PT_THREADS - 1) / PT_THREADS : 8LL * sms);
+    proj_init_kernel<<<gi < 1 ? 1 : gi, PT_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("proj_init_kernel");
+    const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
+    if (n_total > 0) {
+        if (generic) proj_angles_kernel<true><<<gp, PT_THREADS, 0, st>>>(p);
+        else proj_angles_kernel<false><<<gp, PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj_angles_kernel");
+    }
+    proj_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);           // also writes theta_out for empty scans
+    SLU_LAUNCH_CHECK("proj_rows_kernel");
+    if (n_total > 0) {
+        proj_ties_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj_ties_kernel");
+    }
+    return 0;
+}
+
+}  // namespace slu
+
+extern "C" int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW) {
+    if (n_total < 0 || B < 1 || HW < 1) return slu::fail(SLU_E_ARG, "bad workspace query");
+    return slu::carve(n_total, B, HW).total;
+}
+
+extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
+                                 const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
+                                 int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                                 void* d_work,
+                                 float* d_img, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                                 slu_stream_t stream) {
+    using namespace slu;
+    if (B < 1 || B > MAX_SCANS) return fail(SLU_E_RANGE, "B=%d outside [1,%d]", B, MAX_SCANS);
+    if (H < 1 || W < 1 || (long long)H * W > 0x7fffffffLL) return fail(SLU_E_RANGE, "image %dx%d unsupported", H, W);
+    if (!h_offsets || !d_work) return fail(SLU_E_ARG, "h_offsets / d_work is NULL");
+    if (n_total < 0 || h_offsets[0] != 0 || h_offsets[B] != n_total) return fail(SLU_E_ARG, "offsets do not span [0,n_total]");
+    for (int b = 0; b < B; ++b) {
+        if (h_offsets[b + 1] < h_offsets[b]) return fail(SLU_E_ARG, "offsets must be non-decreasing");
+        if (h_offsets[b + 1] - h_offsets[b] > 0x7ffffff0LL) return fail(SLU_E_RANGE, "scan %d has too many points", b);
+    }
+    if (n_total > 0 && !d_xyzi) return fail(SLU_E_ARG, "d_xyzi is NULL");
+    if ((reinterpret_cast<uintptr_t>(d_xyzi) & 15) != 0) return fail(SLU_E_ALIGN, "d_xyzi not 16-byte aligned");
+    if (use_theta_range && !(theta_lo == theta_lo && theta_hi == theta_hi)) return fail(SLU_E_ARG, "theta range is NaN");
+    ProjParams p{};
+    p.xyzi = reinterpret_cast<const float4*>(d_xyzi);
+    p.raw_label = d_raw_label;
+    p.lut = d_lut;
+    for (int b = 0; b <= B; ++b) p.offsets[b] = h_offsets[b];
+    p.B = B; p.H = H; p.W = W; p.HW = (long long)H * W;
+    p.use_range = use_theta_range; p.theta_lo = theta_lo; p.theta_hi = theta_hi;
+    p.farthest = farthest_wins;
+    p.img = d_img; p.theta_out = d_theta;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = project_common(p, n_total, d_work, d_pix, d_winner, d_diag, false, st);
+    if (rc) return rc;
+    const int sms = sm_count_current_device();
+    long long gx = (p.HW + PT_THREADS - 1) / PT_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;
+    if (gx > cap) gx = cap;
+    proj_resolve_planes_kernel<<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("proj_resolve_planes_kernel");
+    return 0;
+}
+
+extern "C" int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
+                                  int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                                  void* d_work,
+                                  float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                                  slu_stream_t stream) {
+    using namespace slu;
+    if (N < 0 || N > 0x7ffffff0LL) return fail(SLU_E_RANGE, "N=%lld unsupported", (long long)N);
+    if (Cin < 3) return fail(SLU_E_ARG, "Cin=%d < 3", Cin);
+    if (H < 1 || W < 1 || (long long)H * W > 0x7fffffffLL) return fail(SLU_E_RANGE, "image %dx%d unsupported", H, W);
+    if (!d_work) return fail(SLU_E_ARG, "d_work is NULL");
+    if (N > 0 && !d_pc) return fail(SLU_E_ARG, "d_pc is NULL");
+    if (use_theta_range && !(theta_lo == theta_lo && theta_hi == theta_hi)) return fail(SLU_E_ARG, "theta range is NaN");
+    ProjParams p{};
+    p.pc = d_pc; p.cin = Cin;
+    p.offsets[0] = 0; p.offsets[1] = N;
+    p.B = 1; p.H = H; p.W = W; p.HW = (long long)H * W;
+    p.use_range = use_theta_range; p.theta_lo = theta_lo; p.theta_hi = theta_hi;
+    p.farthest = farthest_wins;
+    p.img = d_img_hwc; p.theta_out = d_theta;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = project_common(p, N, d_work, d_pix, d_winner, d_diag, true, st);
+    if (rc) return rc;
+    const int sms = sm_count_current_device();
+    if (d_img_hwc) {
+        long long gx = (p.HW * Cin + PT_THREADS - 1) / PT_THREADS;
+        if (gx > 8LL * sms) gx = 8LL * sms;
+        proj_resolve_hwc_kernel<<<(unsigned)gx, PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj_resolve_hwc_kernel");
+    }
+    long long gx = (p.HW + PT_THREADS - 1) / PT_THREADS;
+    if (gx > 8LL * sms) gx = 8LL * sms;
+    proj_fix_winner_kernel<<<(unsigned)gx, PT_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("proj_fix_winner_kernel");
+    return 0;
+}
+
+extern "C" int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix, const int64_t* h_offsets,
+                               int64_t n_total, int B, int64_t HW, int64_t* d_out, slu_stream_t stream) {
+    using namespace slu;
+    if (B < 1 || B > MAX_SCANS) return fail(SLU_E_RANGE, "B=%d outside [1,%d]", B, MAX_SCANS);
+    if (!h_offsets || h_offsets[0] != 0 || h_offsets[B] != n_total || n_total < 0) return fail(SLU_E_ARG, "offsets do not span [0,n_total]");
+    if (n_total == 0) return 0;
+    if (!d_label_img || !d_pix || !d_out) return fail(SLU_E_ARG, "NULL pointer");
+    if (HW < 1) return fail(SLU_E_ARG, "HW < 1");
+    ProjParams p{};
+    for (int b = 0; b <= B; ++b) p.offsets[b] = h_offsets[b];
+    p.B = B; p.HW = HW;
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const dim3 g(point_grid_x(p.offsets, B, sms), B);
+    backproject_kernel<<<g, PT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(d_label_img), d_pix, p, reinterpret_cast<long long*>(d_out));
+    SLU_LAUNCH_CHECK("backproject_kernel");
+    return 0;
+}

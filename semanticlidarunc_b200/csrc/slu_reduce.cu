@@ -1,0 +1,417 @@
+// slu_reduce.cu -- stage 3+4: fused per-pixel reduction over T samples x C classes + evaluation
+// histograms, one pass over HBM.
+//
+// Replaces (reference file:line): src/models/tester.py:412-471 (softmax, mean over T, argmax,
+// predictive entropy, mutual information, IoUEvaluator.update, ECEAggregator.update),
+// src/models/trainer.py:1170-1225 (T=1), src/utils/mc_dropout.py:121-133, src/metrics/ece.py:54-90,
+// src/models/evaluator.py:39-53.
+//
+// Data layout.  d_in is [T,B,C,HW] fp32: for fixed (t,b,c) the HW pixels are contiguous, the two
+// reduced axes (T, C) are the strided ones.  A tile is TILE consecutive pixels of one scan b; a
+// tile's whole reduction (T*C values per pixel) happens in the registers of one thread per pixel, so
+// every input byte is read from HBM exactly once and nothing but the 24 B/pixel of results is
+// written.  HBM-bound: 4*T*C + 8 (label) bytes in, 24 bytes out per pixel; ~0.3 flop/B, no tensor
+// cores (there is no contraction here).
+//
+// Staged kernel (default).  One producer warp streams [C x TILE] fp32 slabs (C bulk async copies
+// of TILE*4 B, TMA engine, mbarrier complete_tx) through a STAGES-deep shared-memory ring, running
+// ahead of the 8 consumer warps across (t, tile) boundaries; consumers copy their pixel's C values
+// to registers, release the slot at once, and do the math.  CTAs are persistent (grid = resident
+// CTAs), tiles are strided over CTAs.
+//
+// Per (pixel, t) with logits x_c (fast path, 7 issue slots per value):
+//   m = max_c x_c;  a_c = x_c*log2e - m*log2e;  e_c = 2^a_c;  S = sum e_c;  A = sum e_c*a_c
+//   p_c = e_c / S;  H_t = ln S - ln2 * A / S   ( = -sum p_c ln p_c, no per-value log )
+// The eps clamp of the reference (p.clamp_min(1e-12) inside H_t) changes H_t by at most
+// C*eps*|ln eps| = 5.5e-10 for eps = 1e-12, below fp32 resolution of the result; it is applied
+// literally (per-value log) when eps is large enough to matter or when the fast path produced a
+// non-finite A (-inf logits).  The clamp on p_bar is always applied literally.
+#include <math.h>
+#include "slu_common.cuh"
+
+namespace slu {
+
+constexpr int TILE = 256;               // pixels per tile == consumer threads per CTA
+constexpr int STAGES = 4;               // ring depth (slabs of C*TILE*4 bytes)
+constexpr int NCONS_WARPS = TILE / 32;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct ReduceParams {
+    const float* in;
+    const long long* labels;
+    int T, B, C;
+    long long HW;
+    int conf_mode;
+    float eps;
+    int has_ignore;
+    long long ignore;
+    int n_bins;
+    float edges[SLU_MAX_BINS + 1];
+    float* pbar;
+    long long* pred;
+    float* conf;
+    float* hnorm;
+    float* minorm;
+    unsigned long long* confmat;
+    unsigned long long* bins;
+    int tiles_per_scan;
+    long long n_tiles;
+    float logC;
+    int literal_clamp;   // apply the eps clamp per value inside H_t
+    int need_ht;         // mutual information requested (per-sample entropies needed)
+};
+
+// Per-CTA histogram scratch in static shared memory.
+struct HistSmem {
+    unsigned confmat[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
+    unsigned bin_n[SLU_MAX_BINS];
+    unsigned bin_c[SLU_MAX_BINS];
+    unsigned long long bin_s[SLU_MAX_BINS];
+    float edges[SLU_MAX_BINS + 1];
+};
+
+// ---- per (pixel, t) step: turns x[] into p_t (scaled by `inv`) and returns H_t -------------------
+template <int CP, int KIND>
+__device__ __forceinline__ void sample_step(float (&x)[CP], float (&pbar)[CP], float& EH, const ReduceParams& p) {
+    if (KIND == SLU_IN_LOGITS) {
+        float m = x[0];
+#pragma unroll
+        for (int c = 1; c < CP; ++c) m = fmaxf(m, x[c]);
+        const float m2 = m * LOG2E;
+        float S = 0.f, A = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            const float a = fmaf(x[c], LOG2E, -m2);
+            const float e = ex2_approx(a);
+            x[c] = e;
+            S += e;
+            A = fmaf(e, a, A);
+        }
+        const float inv = __frcp_rn(S);
+        if (p.need_ht) {
+            float Ht = fmaf(-LN2 * A, inv, logf(S));
+            if (p.literal_clamp || !(fabsf(Ht) <= 3.0e38f)) {
+                Ht = 0.f;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (c < p.C) {
+                        const float pc = fmaxf(x[c] * inv, p.eps);
+                        Ht = fmaf(-pc, logf(pc), Ht);
+                    }
+                }
+            }
+            EH += Ht;
+        }
+#pragma unroll
+        for (int c = 0; c < CP; ++c) pbar[c] = fmaf(x[c], inv, pbar[c]);
+    } else {
+        if (KIND == SLU_IN_ALPHA) {       // p = alpha / (alpha0 + eps)   (src/metrics/ece.py:57-58)
+            float a0 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) a0 += x[c];
+            const float d = a0 + p.eps;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) x[c] = __fdiv_rn(x[c], d);
+        }
+        if (p.need_ht) {
+            float Ht = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (c < p.C) {
+                    const float pc = fmaxf(x[c], p.eps);
+                    Ht = fmaf(-pc, logf(pc), Ht);
+                }
+            }
+            EH += Ht;
+        }
+#pragma unroll
+        for (int c = 0; c < CP; ++c) pbar[c] += x[c];
+    }
+}
+
+// ---- per pixel epilogue: mean, argmax, entropies, confidence, outputs, histograms ------------------
+template <int CP>
+__device__ __forceinline__ void pixel_epilogue(float (&pbar)[CP], float EH, bool live, int b, long long px,
+                                               const ReduceParams& p, HistSmem& hs) {
+    const float Tf = (float)p.T;
+    float pmax = 0.f, Hb = 0.f, sump = 0.f;
+    int arg = 0;
+    bool first = true;
+    const long long obase = (long long)b * p.C * p.HW + px;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+        if (c < p.C) {
+            const float pb = __fdiv_rn(pbar[c], Tf);
+            if (p.pbar && live) p.pbar[obase + (long long)c * p.HW] = pb;
+            // torch.argmax: first maximal index, NaN counts as maximal
+            if (first || pb > pmax || (pb != pb && pmax == pmax)) { pmax = pb; arg = c; first = false; }
+            const float pc = fmaxf(pb, p.eps);
+            Hb = fmaf(-pc, logf(pc), Hb);
+            sump += fmaxf(pb, 0.f);
+        }
+    }
+    float conf = pmax;
+    if (p.conf_mode == SLU_CONF_RENORM) conf = __fdiv_rn(fmaxf(pmax, 0.f), fmaxf(sump, p.eps));
+    const long long o = (long long)b * p.HW + px;
+    if (live) {
+        if (p.pred) p.pred[o] = arg;
+        if (p.conf) p.conf[o] = conf;
+        if (p.hnorm) p.hnorm[o] = __fdiv_rn(Hb, p.logC);
+        // T == 1: H[p_bar] and H[p_1] are the same number in the reference, so MI is exactly 0
+        if (p.minorm) p.minorm[o] = p.need_ht ? fmaxf(__fdiv_rn(Hb - __fdiv_rn(EH, Tf), p.logC), 0.f) : 0.f;
+    }
+    if (p.labels) {   // warp-uniform
+        const long long lab = live ? p.labels[o] : -1;
+        if (p.confmat) {
+            const bool ok = live && lab >= 0 && lab < p.C;
+            warp_hist_add(hs.confmat, ok ? (int)lab * p.C + arg : 0, ok);
+        }
+        if (p.bins) {
+            const float cf = fminf(fmaxf(conf, 0.f), 1.f);                 // ece.py:83 clamp_(0,1)
+            const int bin = (conf == conf) ? find_bin(hs.edges, p.n_bins, cf) : -1;   // NaN stays out of every bin
+            const bool ok = live && bin >= 0 && !(p.has_ignore && lab == p.ignore);
+            warp_bins_add(hs.bin_n, hs.bin_c, hs.bin_s, bin, (long long)arg == lab, cf, ok);
+        }
+    }
+}
+
+__device__ __forceinline__ void hist_init(HistSmem& hs, const ReduceParams& p, int tid, int nthreads) {
+    for (int i = tid; i < p.C * p.C; i += nthreads) hs.confmat[i] = 0;
+    for (int i = tid; i < SLU_MAX_BINS; i += nthreads) { hs.bin_n[i] = 0; hs.bin_c[i] = 0; hs.bin_s[i] = 0ull; }
+    for (int i = tid; i <= p.n_bins; i += nthreads) hs.edges[i] = p.edges[i];
+}
+__device__ __forceinline__ void hist_flush(HistSmem& hs, const ReduceParams& p, int tid, int nthreads) {
+    if (p.confmat)
+        for (int i = tid; i < p.C * p.C; i += nthreads)
+            if (hs.confmat[i]) atomicAdd(&p.confmat[i], (unsigned long long)hs.confmat[i]);
+    if (p.bins)
+        for (int i = tid; i < p.n_bins; i += nthreads) {
+            if (hs.bin_n[i]) atomicAdd(&p.bins[i], (unsigned long long)hs.bin_n[i]);
+            if (hs.bin_c[i]) atomicAdd(&p.bins[p.n_bins + i], (unsigned long long)hs.bin_c[i]);
+            if (hs.bin_s[i]) atomicAdd(&p.bins[2 * p.n_bins + i], hs.bin_s[i]);
+        }
+}
+
+// =====================================================================================================
+// Staged kernel: 8 consumer warps + 1 producer warp, STAGES-deep ring of [C x TILE] slabs.
+// =====================================================================================================
+template <int CP, int KIND>
+__global__ void __launch_bounds__(TILE + 32, 2) reduce_staged_kernel(const __grid_constant__ ReduceParams p) {
+    extern __shared__ __align__(128) float ring[];          // STAGES * C * TILE floats
+    __shared__ __align__(8) unsigned long long bars[2 * STAGES];   // full[0..S) | empty[0..S)
+    __shared__ HistSmem hs;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    const int slab = p.C * TILE;                             // floats per stage
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar0 + 8 * s, 1);                      // full: one arrive (+tx bytes) by the producer
+            mbar_init(bar0 + 8 * (STAGES + s), NCONS_WARPS); // empty: one arrive per consumer warp
+        }
+        fence_mbar_init();
+    }
+    hist_init(hs, p, tid, blockDim.x);
+    __syncthreads();
+
+    if (warp == NCONS_WARPS) {
+        // ------------------------------- producer warp -------------------------------------------
+        const uint64_t pol = policy_evict_first();           // input is read once: do not keep it in L2
+        unsigned k = 0;
+        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int b = (int)(tile / p.tiles_per_scan);
+            const long long px0 = (tile % p.tiles_per_scan) * TILE;
+            const int npx = (int)min((long long)TILE, p.HW - px0);
+            const uint32_t row_bytes = (uint32_t)npx * 4u;
+            for (int t = 0; t < p.T; ++t, ++k) {
+                const int s = k % STAGES;
+                const uint32_t ph = (k / STAGES) & 1u;
+                const uint32_t full = bar0 + 8 * s, empty = bar0 + 8 * (STAGES + s);
+                if (lane == 0) {
+                    mbar_wait(empty, ph ^ 1u);               // slot drained by all consumer warps
+                    mbar_arrive_expect_tx(full, row_bytes * (uint32_t)p.C);
+                }
+                __syncwarp();
+                const float* src = p.in + (((long long)t * p.B + b) * p.C) * p.HW + px0;
+                const uint32_t dst = smem_u32(ring + (size_t)s * slab);
+                for (int c = lane; c < p.C; c += 32)
+                    bulk_g2s(dst + (uint32_t)c * TILE * 4u, src + (long long)c * p.HW, row_bytes, full, pol);
+            }
+        }
+    } else {
+        // ------------------------------- consumer warps ------------------------------------------
+        unsigned k = 0;
+        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int b = (int)(tile / p.tiles_per_scan);
+            const long long px0 = (tile % p.tiles_per_scan) * TILE;
+            const bool live = px0 + tid < p.HW;
+            float pbar[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) pbar[c] = 0.f;
+            float EH = 0.f;
+            for (int t = 0; t < p.T; ++t, ++k) {
+                const int s = k % STAGES;
+                const uint32_t ph = (k / STAGES) & 1u;
+                mbar_wait(bar0 + 8 * s, ph);
+                const float* st = ring + (size_t)s * slab + tid;
+                float x[CP];
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+                    x[c] = (c < p.C) ? st[c * TILE] : (KIND == SLU_IN_LOGITS ? -1.0e30f : 0.f);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + s));   // values are in registers: free the slot
+                sample_step<CP, KIND>(x, pbar, EH, p);
+            }
+            pixel_epilogue<CP>(pbar, EH, live, b, px0 + tid, p, hs);
+        }
+    }
+    __syncthreads();
+    hist_flush(hs, p, tid, blockDim.x);
+}
+
+// =====================================================================================================
+// Direct kernel: every thread loads its pixel's values straight from global memory, the next
+// sample's C values are prefetched into registers while the current one is reduced.
+// =====================================================================================================
+template <int CP, int KIND>
+__global__ void __launch_bounds__(TILE, 2) reduce_direct_kernel(const __grid_constant__ ReduceParams p) {
+    __shared__ HistSmem hs;
+    const int tid = threadIdx.x;
+    hist_init(hs, p, tid, blockDim.x);
+    __syncthreads();
+    const float pad = (KIND == SLU_IN_LOGITS) ? -1.0e30f : 0.f;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_per_scan);
+        const long long px = (tile % p.tiles_per_scan) * TILE + tid;
+        const bool live = px < p.HW;
+        const long long pxs = live ? px : p.HW - 1;          // clamp so dead lanes load valid memory
+        const long long tstride = (long long)p.B * p.C * p.HW;
+        const float* base = p.in + ((long long)b * p.C) * p.HW + pxs;
+        float pbar[CP], x[CP], xn[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { pbar[c] = 0.f; xn[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : pad; }
+        float EH = 0.f;
+        for (int t = 0; t < p.T; ++t) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) x[c] = xn[c];
+            if (t + 1 < p.T) {
+                const float* nb = base + (long long)(t + 1) * tstride;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) xn[c] = (c < p.C) ? ldg_stream(nb + (long long)c * p.HW) : pad;
+            }
+            sample_step<CP, KIND>(x, pbar, EH, p);
+        }
+        pixel_epilogue<CP>(pbar, EH, live, b, px, p, hs);
+    }
+    __syncthreads();
+    hist_flush(hs, p, tid, blockDim.x);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+template <int CP, int KIND>
+static int launch(const ReduceParams& p, bool staged, cudaStream_t stream) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long max_ctas = 2LL * sms;
+    const int grid = (int)(p.n_tiles < max_ctas ? p.n_tiles : max_ctas);
+    if (staged) {
+        const size_t dyn = (size_t)STAGES * p.C * TILE * sizeof(float);
+        SLU_CUDA(cudaFuncSetAttribute(reduce_staged_kernel<CP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        reduce_staged_kernel<CP, KIND><<<grid, TILE + 32, dyn, stream>>>(p);
+        SLU_LAUNCH_CHECK("reduce_staged_kernel");
+    } else {
+        reduce_direct_kernel<CP, KIND><<<grid, TILE, 0, stream>>>(p);
+        SLU_LAUNCH_CHECK("reduce_direct_kernel");
+    }
+    return 0;
+}
+
+template <int KIND>
+static int dispatch_cp(const ReduceParams& p, bool staged, cudaStream_t stream) {
+    const int cp = (p.C + 3) / 4 * 4;
+    switch (cp) {
+        case 4: return launch<4, KIND>(p, staged, stream);
+        case 8: return launch<8, KIND>(p, staged, stream);
+        case 12: return launch<12, KIND>(p, staged, stream);
+        case 16: return launch<16, KIND>(p, staged, stream);
+        case 20: return launch<20, KIND>(p, staged, stream);
+        case 24: return launch<24, KIND>(p, staged, stream);
+        case 28: return launch<28, KIND>(p, staged, stream);
+        case 32: return launch<32, KIND>(p, staged, stream);
+    }
+    return fail(SLU_E_RANGE, "C=%d outside [2,%d]", p.C, SLU_MAX_CLASSES);
+}
+
+static int reduce_entry(const float* d_in, const int64_t* d_labels, int T, int B, int C, int64_t HW,
+                        int in_kind, int conf_mode, float eps, int normalize, int has_ignore, int64_t ignore,
+                        int n_bins, const float* h_edges,
+                        float* d_pbar, int64_t* d_pred, float* d_conf, float* d_hnorm, float* d_minorm,
+                        int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream, bool allow_staged) {
+    if (!d_in) return fail(SLU_E_ARG, "d_in is NULL");
+    if (T < 1 || B < 1 || HW < 1) return fail(SLU_E_ARG, "T=%d B=%d HW=%lld must be >= 1", T, B, (long long)HW);
+    if (C < 2 || C > SLU_MAX_CLASSES) return fail(SLU_E_RANGE, "C=%d outside [2,%d]", C, SLU_MAX_CLASSES);
+    if (in_kind < SLU_IN_LOGITS || in_kind > SLU_IN_ALPHA) return fail(SLU_E_ARG, "in_kind=%d", in_kind);
+    if (in_kind == SLU_IN_ALPHA && T != 1) return fail(SLU_E_ARG, "SLU_IN_ALPHA needs T=1, got %d", T);
+    if (conf_mode != SLU_CONF_RAW && conf_mode != SLU_CONF_RENORM) return fail(SLU_E_ARG, "conf_mode=%d", conf_mode);
+    if (!(eps >= 0.f)) return fail(SLU_E_ARG, "eps must be >= 0");
+    if ((d_confmat || d_ece_bins) && !d_labels) return fail(SLU_E_ARG, "histograms requested without labels");
+    if (d_ece_bins) {
+        if (n_bins < 1 || n_bins > SLU_MAX_BINS) return fail(SLU_E_RANGE, "n_bins=%d outside [1,%d]", n_bins, SLU_MAX_BINS);
+        if (!h_edges) return fail(SLU_E_ARG, "h_edges is NULL");
+        for (int i = 0; i < n_bins; ++i)
+            if (!(h_edges[i] < h_edges[i + 1])) return fail(SLU_E_ARG, "bin edges must increase strictly");
+    }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 3) != 0) return fail(SLU_E_ALIGN, "d_in not 4-byte aligned");
+
+    ReduceParams p{};
+    p.in = d_in;
+    p.labels = reinterpret_cast<const long long*>(d_labels);
+    p.T = T; p.B = B; p.C = C; p.HW = HW;
+    p.conf_mode = conf_mode;
+    p.eps = eps;
+    p.has_ignore = has_ignore; p.ignore = ignore;
+    p.n_bins = d_ece_bins ? n_bins : 0;
+    for (int i = 0; i <= p.n_bins && d_ece_bins; ++i) p.edges[i] = h_edges[i];
+    p.pbar = d_pbar; p.pred = reinterpret_cast<long long*>(d_pred);
+    p.conf = d_conf; p.hnorm = d_hnorm; p.minorm = d_minorm;
+    p.confmat = reinterpret_cast<unsigned long long*>(d_confmat);
+    p.bins = reinterpret_cast<unsigned long long*>(d_ece_bins);
+    p.tiles_per_scan = (int)((HW + TILE - 1) / TILE);
+    p.n_tiles = (long long)p.tiles_per_scan * B;
+    p.logC = normalize ? (float)log((double)C) : 1.0f;    // x / 1.0f is exact: entropies stay in nats
+    // the clamp matters once C*eps*|ln eps| reaches fp32 resolution of an O(1) entropy
+    p.literal_clamp = (eps > 0.f && (double)C * eps * fabs(log((double)eps)) > 1e-8) ? 1 : 0;
+    p.need_ht = (d_minorm != nullptr && T > 1) ? 1 : 0;
+
+    const bool staged = allow_staged && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (in_kind) {
+        case SLU_IN_LOGITS: return dispatch_cp<SLU_IN_LOGITS>(p, staged, st);
+        case SLU_IN_PROBS: return dispatch_cp<SLU_IN_PROBS>(p, staged, st);
+        default: return dispatch_cp<SLU_IN_ALPHA>(p, staged, st);
+    }
+}
+
+}  // namespace slu
+
+extern "C" int slu_reduce_metrics(const float* d_in, const int64_t* d_labels, int T, int B, int C, int64_t HW,
+                                  int in_kind, int conf_mode, float eps, int normalize, int has_ignore, int64_t ignore,
+                                  int n_bins, const float* h_edges,
+                                  float* d_pbar, int64_t* d_pred, float* d_conf, float* d_hnorm, float* d_minorm,
+                                  int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
+    return slu::reduce_entry(d_in, d_labels, T, B, C, HW, in_kind, conf_mode, eps, normalize, has_ignore, ignore, n_bins, h_edges,
+                             d_pbar, d_pred, d_conf, d_hnorm, d_minorm, d_confmat, d_ece_bins, stream, true);
+}
+
+extern "C" int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_labels, int T, int B, int C, int64_t HW,
+                                         int in_kind, int conf_mode, float eps, int normalize, int has_ignore, int64_t ignore,
+                                         int n_bins, const float* h_edges,
+                                         float* d_pbar, int64_t* d_pred, float* d_conf, float* d_hnorm, float* d_minorm,
+                                         int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
+    return slu::reduce_entry(d_in, d_labels, T, B, C, HW, in_kind, conf_mode, eps, normalize, has_ignore, ignore, n_bins, h_edges,
+                             d_pbar, d_pred, d_conf, d_hnorm, d_minorm, d_confmat, d_ece_bins, stream, false);
+}

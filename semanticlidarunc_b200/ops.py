@@ -1,0 +1,230 @@
+"""Functional wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+These are the device-resident entry points (no host copies, no synchronisation); the modules that
+mirror the reference's Python interfaces (dataset/, metrics/, models/, utils/) are built on them.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CONF_RAW, CONF_RENORM, IN_ALPHA, IN_LOGITS, IN_PROBS  # noqa: F401  (re-exported)
+
+KINDS = {"logits": IN_LOGITS, "probs": IN_PROBS, "alpha": IN_ALPHA}
+
+
+def uniform_edges(n_bins: int) -> np.ndarray:
+    """float32 edges of the reference's uniform binning (src/metrics/ece.py:116,128)."""
+    e = np.linspace(0.0, 1.0, n_bins + 1, dtype=np.float32)
+    e[0], e[-1] = 0.0, 1.0
+    return e
+
+
+def new_confmat(num_classes: int, device) -> torch.Tensor:
+    return torch.zeros((num_classes, num_classes), dtype=torch.int64, device=device)
+
+
+def new_ece_bins(n_bins: int, device) -> torch.Tensor:
+    """[3, n_bins] int64: n | n_correct | sum(conf) in units of 2^-32."""
+    return torch.zeros((3, n_bins), dtype=torch.int64, device=device)
+
+
+def reduce_metrics(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, kind: str = "logits",
+                   conf_mode: int = CONF_RAW, eps: float = 1e-12, ignore_index: Optional[int] = None,
+                   edges: Optional[Sequence[float]] = None,
+                   confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None,
+                   want: Sequence[str] = ("pred", "conf", "H_norm", "MI_norm"), normalize: bool = True,
+                   direct: bool = False) -> dict:
+    """Fused stage 3+4 (slu_reduce_metrics).
+
+    x: [T,B,C,H,W] or [B,C,H,W] (T=1) float32 CUDA.  labels: [B,H,W] int64 CUDA or None.
+    `want` selects the per-pixel outputs to materialise ("p_bar", "pred", "conf", "H_norm", "MI_norm").
+    confmat [C,C] / ece_bins [3,n_bins] int64 are accumulated in place when given.
+    """
+    _lib.require_cuda()
+    if x.dim() == 4:
+        x = x.unsqueeze(0)
+    if x.dim() != 5:
+        raise ValueError("x must be [T,B,C,H,W] or [B,C,H,W]")
+    x = _lib.as_buffer(x, torch.float32, "x")
+    T, B, Cc, H, W = x.shape
+    HW = H * W
+    dev = x.device
+    if labels is not None:
+        if labels.dim() == 4 and labels.size(1) == 1:
+            labels = labels[:, 0]
+        if tuple(labels.shape) != (B, H, W):
+            raise ValueError(f"labels shape {tuple(labels.shape)} != {(B, H, W)}")
+        labels = _lib.as_buffer(labels, torch.int64, "labels")
+    out = {}
+    def mk(name, shape, dtype):
+        if name in want:
+            out[name] = torch.empty(shape, dtype=dtype, device=dev)
+            return out[name]
+        return None
+    pbar = mk("p_bar", (B, Cc, H, W), torch.float32)
+    pred = mk("pred", (B, H, W), torch.int64)
+    conf = mk("conf", (B, H, W), torch.float32)
+    hn = mk("H_norm", (B, H, W), torch.float32)
+    mi = mk("MI_norm", (B, H, W), torch.float32)
+    n_bins, h_edges = 0, None
+    if ece_bins is not None:
+        if ece_bins.dtype != torch.int64 or not ece_bins.is_contiguous() or ece_bins.dim() != 2 or ece_bins.size(0) != 3:
+            raise ValueError("ece_bins must be a contiguous [3,n_bins] int64 tensor")
+        n_bins = ece_bins.size(1)
+        e = uniform_edges(n_bins) if edges is None else np.asarray(edges, dtype=np.float32)
+        if e.shape[0] != n_bins + 1:
+            raise ValueError("edges must have n_bins+1 entries")
+        h_edges = _lib.edges_array(e)
+    if confmat is not None and (confmat.dtype != torch.int64 or not confmat.is_contiguous() or tuple(confmat.shape) != (Cc, Cc)):
+        raise ValueError(f"confmat must be a contiguous [{Cc},{Cc}] int64 tensor")
+    fn = _lib.lib().slu_reduce_metrics_direct if direct else _lib.lib().slu_reduce_metrics
+    rc = fn(_lib.ptr(x), _lib.ptr(labels), T, B, Cc, HW, KINDS[kind], conf_mode, float(eps), int(normalize),
+            0 if ignore_index is None else 1, 0 if ignore_index is None else int(ignore_index),
+            n_bins, h_edges,
+            _lib.ptr(pbar), _lib.ptr(pred), _lib.ptr(conf), _lib.ptr(hn), _lib.ptr(mi),
+            _lib.ptr(confmat), _lib.ptr(ece_bins), _lib.stream_ptr())
+    _lib.check(rc, "slu_reduce_metrics")
+    return out
+
+
+def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None, *,
+                  num_classes: int, ignore_index: Optional[int] = None, edges=None,
+                  confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None) -> None:
+    """Standalone stage 4 (slu_confusion_ece) on flat int64 pred/labels (+ float32 conf)."""
+    _lib.require_cuda()
+    pred = _lib.as_buffer(pred, torch.int64, "pred").reshape(-1)
+    labels = _lib.as_buffer(labels, torch.int64, "labels").reshape(-1)
+    if pred.numel() != labels.numel():
+        raise ValueError("pred and labels differ in size")
+    if conf is not None:
+        conf = _lib.as_buffer(conf, torch.float32, "conf").reshape(-1)
+        if conf.numel() != pred.numel():
+            raise ValueError("conf and pred differ in size")
+    n_bins, h_edges = 0, None
+    if ece_bins is not None:
+        n_bins = ece_bins.size(1)
+        e = uniform_edges(n_bins) if edges is None else np.asarray(edges, dtype=np.float32)
+        h_edges = _lib.edges_array(e)
+    rc = _lib.lib().slu_confusion_ece(_lib.ptr(pred), _lib.ptr(labels), _lib.ptr(conf), pred.numel(), int(num_classes),
+                                      0 if ignore_index is None else 1, 0 if ignore_index is None else int(ignore_index),
+                                      n_bins, h_edges, _lib.ptr(confmat), _lib.ptr(ece_bins), _lib.stream_ptr())
+    _lib.check(rc, "slu_confusion_ece")
+
+
+def _offsets_array(offsets):
+    off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
+    return off, off.ctypes.data_as(_lib.C.c_void_p)
+
+
+def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets, H: int, W: int, *,
+                  lut: Optional[torch.Tensor] = None, theta_range=None, farthest_wins: bool = False,
+                  want_img: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
+    """Batched stage 1 (slu_project_batch).
+
+    xyzi [n_total,4] float32 CUDA (scans concatenated), raw_label [n_total] uint32-as-int32 CUDA or None,
+    offsets: host sequence of B+1 point offsets.  Returns img [B,6,H,W] (x,y,z,range,intensity,label),
+    pix [n_total] int32, winner [B,H,W] int32, theta [B,2] float64, diag [B,2] int32.
+    """
+    _lib.require_cuda()
+    xyzi = _lib.as_buffer(xyzi, torch.float32, "xyzi")
+    if xyzi.dim() != 2 or xyzi.size(1) != 4:
+        raise ValueError("xyzi must be [n_total,4]")
+    off, off_p = _offsets_array(offsets)
+    B = off.shape[0] - 1
+    n_total = xyzi.size(0)
+    dev = xyzi.device
+    if raw_label is not None:
+        if raw_label.dtype not in (torch.int32, torch.uint32):
+            raise ValueError("raw_label must be int32/uint32 (the .label file's uint32 words)")
+        raw_label = raw_label.contiguous()
+        if raw_label.numel() != n_total:
+            raise ValueError("raw_label and xyzi differ in length")
+    if lut is not None:
+        lut = _lib.as_buffer(lut, torch.int32, "lut")
+        if lut.numel() != 65536:
+            raise ValueError("lut must have 65536 entries")
+    HW = H * W
+    need = _lib.lib().slu_project_workspace_bytes(n_total, B, HW)
+    if need < 0:
+        _lib.check(int(need), "slu_project_workspace_bytes")
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    img = torch.empty((B, 6, H, W), dtype=torch.float32, device=dev) if want_img else None
+    pix = torch.empty((n_total,), dtype=torch.int32, device=dev)
+    winner = torch.empty((B, H, W), dtype=torch.int32, device=dev)
+    theta = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    diag = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    use_range = theta_range is not None
+    lo, hi = (float(theta_range[0]), float(theta_range[1])) if use_range else (0.0, 0.0)
+    rc = _lib.lib().slu_project_batch(_lib.ptr(xyzi), _lib.ptr(raw_label), _lib.ptr(lut), off_p, n_total, B, H, W,
+                                      int(use_range), lo, hi, int(farthest_wins), _lib.ptr(workspace),
+                                      _lib.ptr(img), _lib.ptr(pix), _lib.ptr(winner), _lib.ptr(theta), _lib.ptr(diag),
+                                      _lib.stream_ptr())
+    _lib.check(rc, "slu_project_batch")
+    return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
+
+
+def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthest_wins: bool = False,
+                   want_img: bool = True) -> dict:
+    """Generic stage 1 (slu_project_points): pc [N,Cin] float64 CUDA -> img [H,W,Cin] float32."""
+    _lib.require_cuda()
+    pc = _lib.as_buffer(pc, torch.float64, "pc")
+    if pc.dim() != 2 or pc.size(1) < 3:
+        raise ValueError("pc must be [N,Cin] with Cin >= 3")
+    N, Cin = pc.shape
+    dev = pc.device
+    need = _lib.lib().slu_project_workspace_bytes(N, 1, H * W)
+    workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    img = torch.empty((H, W, Cin), dtype=torch.float32, device=dev) if want_img else None
+    pix = torch.empty((N,), dtype=torch.int32, device=dev)
+    winner = torch.empty((H, W), dtype=torch.int32, device=dev)
+    theta = torch.empty((1, 2), dtype=torch.float64, device=dev)
+    diag = torch.empty((1, 2), dtype=torch.int32, device=dev)
+    use_range = theta_range is not None
+    lo, hi = (float(theta_range[0]), float(theta_range[1])) if use_range else (0.0, 0.0)
+    rc = _lib.lib().slu_project_points(_lib.ptr(pc), N, Cin, H, W, int(use_range), lo, hi, int(farthest_wins),
+                                       _lib.ptr(workspace), _lib.ptr(img), _lib.ptr(pix), _lib.ptr(winner),
+                                       _lib.ptr(theta), _lib.ptr(diag), _lib.stream_ptr())
+    _lib.check(rc, "slu_project_points")
+    return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag}
+
+
+def backproject(label_img: torch.Tensor, pix: torch.Tensor, offsets) -> torch.Tensor:
+    """Stage 2 (slu_backproject): label_img [B,H,W] int64, pix [n_total] int32 -> [n_total] int64."""
+    _lib.require_cuda()
+    if label_img.dim() == 2:
+        label_img = label_img.unsqueeze(0)
+    label_img = _lib.as_buffer(label_img, torch.int64, "label_img")
+    pix = _lib.as_buffer(pix, torch.int32, "pix")
+    off, off_p = _offsets_array(offsets)
+    B = off.shape[0] - 1
+    if label_img.size(0) != B:
+        raise ValueError("label_img batch size does not match offsets")
+    out = torch.empty((pix.numel(),), dtype=torch.int64, device=pix.device)
+    rc = _lib.lib().slu_backproject(_lib.ptr(label_img), _lib.ptr(pix), off_p, pix.numel(), B,
+                                    label_img.size(1) * label_img.size(2), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "slu_backproject")
+    return out
+
+
+def ece_from_bins(ece_bins: torch.Tensor):
+    """(ece, mce, n, acc, avg_conf) from the [3,n_bins] int64 state, following src/metrics/ece.py:139-168."""
+    b = ece_bins.detach().cpu().numpy()
+    n = b[0].astype(np.float64)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        acc = np.where(n > 0, b[1].astype(np.float64) / n, np.nan)
+        avg = np.where(n > 0, (b[2].astype(np.float64) / 4294967296.0) / n, np.nan)
+    if n.sum() == 0:
+        return float("nan"), float("nan"), b[0], acc, avg
+    gap = np.abs(np.nan_to_num(acc, nan=0.0) - np.nan_to_num(avg, nan=0.0))
+    ece = float(np.sum((n / max(1.0, n.sum())) * gap))
+    mce = float(np.max(gap[n > 0]))
+    return ece, mce, b[0], acc, avg
+
+
+LOG = math.log

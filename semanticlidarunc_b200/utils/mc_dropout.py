@@ -1,0 +1,48 @@
+"""MC-dropout reductions with the reference's names (src/utils/mc_dropout.py:121-133 and the
+closures of src/models/tester.py:419-451), computed by the fused kernel.
+
+`mc_forward` / dropout toggling stay the reference's PyTorch code (the backbone only supplies the
+logits, BASELINE.json north_star) and are not re-implemented here.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+
+
+@torch.no_grad()
+def predictive_entropy_mc(mc_probs: torch.Tensor, eps: float = 1e-12, normalize: bool = True):
+    """mc_probs [T,B,C,H,W] probabilities -> entropy of the mean [B,H,W] (optionally / log C)."""
+    return ops.reduce_metrics(mc_probs, kind="probs", eps=eps, want=("H_norm",), normalize=normalize)["H_norm"]
+
+
+@torch.no_grad()
+def mc_predictive_entropy_norm(probs: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """tester.py:419-425 on probabilities [T,B,C,H,W]."""
+    return ops.reduce_metrics(probs, kind="probs", eps=eps, want=("H_norm",))["H_norm"]
+
+
+@torch.no_grad()
+def mc_mutual_information_norm(probs: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """tester.py:427-451 on probabilities [T,B,C,H,W]."""
+    return ops.reduce_metrics(probs, kind="probs", eps=eps, want=("MI_norm",))["MI_norm"]
+
+
+@torch.no_grad()
+def mc_reduce_from_logits(mc_logits: torch.Tensor, labels: torch.Tensor | None = None, *, eps: float = 1e-12,
+                          ignore_index=None, iou_evaluator=None, ece_eval=None,
+                          want=("pred", "conf", "H_norm", "MI_norm")) -> dict:
+    """The whole MC block of Tester.test_epoch (tester.py:412-471) in one pass over the logits.
+
+    mc_logits [T,B,C,H,W] straight from `mc_forward`; returns pred / conf / H_norm / MI_norm (and
+    p_bar if asked) and, when given, updates `iou_evaluator` (models.evaluator.IoUEvaluator) and
+    `ece_eval` (metrics.ece.ECEAggregator, mode 'probs' semantics) in the same kernel.
+    """
+    confmat = iou_evaluator._accumulator(mc_logits.device) if iou_evaluator is not None else None
+    bins = ece_eval._accumulator(mc_logits.device) if ece_eval is not None else None
+    edges = ece_eval._edges if ece_eval is not None else None
+    if ece_eval is not None and ignore_index is None:
+        ignore_index = ece_eval.ignore_index
+    return ops.reduce_metrics(mc_logits, labels, kind="logits", conf_mode=ops.CONF_RENORM, eps=eps,
+                              ignore_index=ignore_index, edges=edges, confmat=confmat, ece_bins=bins, want=want)

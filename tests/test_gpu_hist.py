@@ -1,0 +1,88 @@
+"""Standalone confusion / reliability histograms (slu_confusion_ece) and the IoUEvaluator /
+ECEAggregator classes: integer counts bit-exact against the reference's golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from semanticlidarunc_b200 import ops
+from semanticlidarunc_b200.metrics.ece import ECEAggregator
+from semanticlidarunc_b200.models.evaluator import IoUEvaluator
+
+pytestmark = pytest.mark.gpu
+
+
+def test_iou_evaluator_vs_reference_golden(cuda, golden):
+    g = golden("metrics.npz")
+    preds, targets = torch.from_numpy(g["iou/preds"]), torch.from_numpy(g["iou/targets"])
+    C = 20
+    ev = IoUEvaluator(C)
+    ev.update(preds[:2], targets[:2])            # CPU tensors in, as the reference's callers may pass
+    ev.update(preds[2:].to(cuda), targets[2:].to(cuda))
+    assert ev.confmat.device.type == "cpu" and ev.confmat.dtype == torch.long
+    assert np.array_equal(ev.confmat.numpy(), g["iou/confmat"])
+    names = {i: str(i) for i in range(C)}
+    miou, per = ev.compute(names, test_mask=[0] + [1] * (C - 1), ignore_gt=[0])
+    assert miou == float(g["iou/miou"])
+    assert np.array_equal(np.array([per[str(i)] for i in range(C)]), g["iou/per_class"], equal_nan=True)
+    miou_all, per_all = ev.compute(names)
+    assert miou_all == float(g["iou/miou_all"])
+    ev.reset()
+    assert int(ev.confmat.sum()) == 0
+
+
+@pytest.mark.parametrize("mode", ["alpha", "logits", "probs"])
+def test_ece_aggregator_vs_reference_golden(cuda, golden, mode):
+    g = golden("metrics.npz")
+    x, lab = torch.from_numpy(g[f"ece_{mode}/preds"]), torch.from_numpy(g[f"ece_{mode}/labels"])
+    agg = ECEAggregator(n_bins=15, mode=mode, ignore_index=0, max_samples=None)
+    agg.update(x[:1], lab[:1])
+    agg.update(x[1:].to(cuda), lab[1:].to(cuda))
+    (ece, mce), stats, fig = agg.compute(save_plot_path=None)
+    # exact integer state vs the reference's stored samples
+    n, nc, cs = om.ece_bin_counts(g[f"ece_{mode}/conf"], g[f"ece_{mode}/correct"], 15)
+    assert np.array_equal(stats["n"].to_numpy(), g[f"ece_{mode}/n"])
+    assert np.array_equal(agg._bins[0].cpu().numpy(), n) and np.array_equal(agg._bins[1].cpu().numpy(), nc)
+    assert agg._seen == int(n.sum())
+    # ECE / MCE within 1e-5 relative of the reference's own numbers
+    ece_ref, mce_ref = g[f"ece_{mode}/ece_mce"]
+    assert abs(ece - ece_ref) <= 1e-5 * abs(ece_ref) + 1e-9
+    assert abs(mce - mce_ref) <= 1e-5 * abs(mce_ref) + 1e-9
+    assert np.allclose(stats["acc"].to_numpy(), g[f"ece_{mode}/acc"], rtol=1e-6, equal_nan=True)
+    assert np.allclose(stats["conf"].to_numpy(), g[f"ece_{mode}/avg_conf"], rtol=1e-5, equal_nan=True)
+
+
+def test_ece_empty_returns_two_tuple(cuda):
+    r = ECEAggregator(n_bins=15, mode="probs", ignore_index=0).compute()
+    assert len(r) == 2 and np.isnan(r[0][0])
+
+
+@pytest.mark.parametrize("C,n", [(20, 1_000_003), (3, 257), (100, 50_000)])
+def test_standalone_histograms_vs_oracle(cuda, C, n):
+    g = torch.Generator().manual_seed(C + n)
+    pred = torch.randint(-1, C + 1, (n,), generator=g)
+    lab = torch.randint(-1, C + 1, (n,), generator=g)
+    conf = torch.rand((n,), generator=g)
+    conf[:5] = torch.tensor([0.0, 1.0, 1.0 / 15, float(np.float32(14 / 15)), 0.5])   # on-edge values
+    confmat = torch.zeros((C, C), dtype=torch.int64, device=cuda)
+    bins = ops.new_ece_bins(15, cuda)
+    ops.confusion_ece(pred.to(cuda), lab.to(cuda), conf.to(cuda), num_classes=C, ignore_index=0, confmat=confmat, ece_bins=bins)
+    assert torch.equal(confmat.cpu(), om.confusion_counts(pred, lab, C))
+    valid = lab != 0
+    nn, nc, cs = om.ece_bin_counts(conf[valid].numpy(), (pred[valid] == lab[valid]).numpy(), 15)
+    assert np.array_equal(bins[0].cpu().numpy(), nn) and np.array_equal(bins[1].cpu().numpy(), nc)
+    assert np.allclose(bins[2].cpu().numpy() / 2.0 ** 32, cs, rtol=1e-9, atol=1e-6)
+    # np.histogram itself (the reference's binning) agrees on the counts
+    assert np.array_equal(np.histogram(conf[valid].numpy(), bins=om.ece_edges(15))[0], nn)
+
+
+def test_coherent_labels_same_counts(cuda):
+    """Warp-aggregated path with long runs of equal keys (what real label maps look like)."""
+    from semanticlidarunc_b200 import synth
+    C = 20
+    lab = synth.synth_coherent_labels(1, 2, C, 64, 2048)
+    pred = synth.synth_coherent_labels(2, 2, C, 64, 2048, block=16)
+    confmat = ops.new_confmat(C, cuda)
+    ops.confusion_ece(pred.to(cuda), lab.to(cuda), None, num_classes=C, confmat=confmat)
+    assert torch.equal(confmat.cpu(), om.confusion_counts(pred, lab, C))
+    assert int(confmat.sum()) == lab.numel()

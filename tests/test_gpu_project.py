@@ -1,0 +1,166 @@
+"""Parity of the projection / back-projection kernels: indices, winners, images and labels are
+compared BIT-EXACTLY with the reference's golden vectors (tests/golden/projection_small.npz,
+kitti_loader.npz, MANIFEST.json digests) and with the oracle on seeded scans."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import projection as oproj
+from semanticlidarunc_b200 import ops, synth
+from semanticlidarunc_b200.dataset.definitions import build_id_lut
+from semanticlidarunc_b200.dataset.utils import spherical_projection
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def to_dev(xyzi, raw, cuda):
+    return (torch.from_numpy(xyzi).to(cuda), torch.from_numpy(raw.view(np.int32)).to(cuda),
+            torch.from_numpy(build_id_lut()).to(cuda))
+
+
+def hwc_from_planes(img6):
+    """[6,H,W] planes (x,y,z,range,intensity,label) -> the reference's [H,W,5] (x,y,z,i,label)."""
+    p = img6.cpu().numpy()
+    return np.stack([p[0], p[1], p[2], p[4], p[5]], axis=-1)
+
+
+SMALL = ["tiny_auto", "tiny_range", "tiny_farthest", "edge", "ragged_1pt"]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_batch_projection_vs_reference_golden(cuda, golden, name):
+    g = golden("projection_small.npz")
+    xyzi, raw = g[name + "/xyzi"], g[name + "/raw"]
+    H, W = (int(v) for v in g[name + "/hw"])
+    tr = g[name + "/theta_range"]
+    tr = None if np.isnan(tr).any() else (float(tr[0]), float(tr[1]))
+    far = bool(int(g[name + "/largest_first"]))
+    dx, dr, dl = to_dev(xyzi, raw, cuda)
+    res = ops.project_batch(dx, dr, [0, xyzi.shape[0]], H, W, lut=dl, theta_range=tr, farthest_wins=far)
+    torch.cuda.synchronize()
+    assert np.array_equal(res["pix"].cpu().numpy().astype(np.int64), g[name + "/pix"])
+    assert np.array_equal(res["winner"].cpu().numpy().reshape(-1).astype(np.int64), g[name + "/winner"])
+    assert np.array_equal(hwc_from_planes(res["img"][0]), g[name + "/img"])          # bit-exact float32 image
+    if tr is None:
+        assert np.array_equal(res["theta"][0].cpu().numpy(), g[name + "/theta"])
+    assert int(res["diag"][0, 0]) == 0
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_generic_projection_vs_reference_golden(cuda, golden, name):
+    g = golden("projection_small.npz")
+    xyzi, raw = g[name + "/xyzi"], g[name + "/raw"]
+    H, W = (int(v) for v in g[name + "/hw"])
+    tr = g[name + "/theta_range"]
+    tr = None if np.isnan(tr).any() else (float(tr[0]), float(tr[1]))
+    far = bool(int(g[name + "/largest_first"]))
+    sem = build_id_lut()[(raw & 0xFFFF).astype(np.int64)].astype(np.int64)
+    pc = np.concatenate([xyzi, sem[:, None]], axis=-1)                 # float64 [N,5] as the loaders build it
+    img, alpha, (tmin, tmax), (pmin, pmax) = spherical_projection(pc, H, W, theta_range=tr, sort_largest_first=far)
+    assert img.dtype == np.float32 and img.shape == (H, W, 5)
+    assert np.array_equal(img, g[name + "/img"])
+    assert sha(alpha) == bytes(g[name + "/alpha_sha"]).hex()
+    assert (pmin, pmax) == (-np.pi, np.pi)
+    if tr is None:
+        assert np.array_equal(np.array([tmin, tmax]), g[name + "/theta"])
+
+
+def test_full_size_digests(cuda):
+    """HDL-64 (120k pts -> 64x2048) and OS1-128 (262k pts -> 128x2048) against reference digests."""
+    with open(os.path.join(HERE, "golden", "MANIFEST.json")) as f:
+        cases = json.load(f)["projection_full"]
+    for name, c in cases.items():
+        xyzi, raw = synth.synth_scan(c["seed"], c["sensor"])
+        assert sha(xyzi) == c["xyzi_sha"] and sha(raw) == c["raw_sha"], "synthetic generator drifted"
+        dx, dr, dl = to_dev(xyzi, raw, cuda)
+        tr = None if c["theta_range"] is None else tuple(c["theta_range"])
+        res = ops.project_batch(dx, dr, [0, xyzi.shape[0]], c["H"], c["W"], lut=dl, theta_range=tr)
+        assert sha(res["pix"].cpu().numpy().astype(np.int64)) == c["pix_sha"], name
+        assert sha(res["winner"].cpu().numpy().reshape(-1).astype(np.int64)) == c["winner_sha"], name
+        assert sha(hwc_from_planes(res["img"][0])) == c["img_sha"], name
+        assert int((res["winner"] >= 0).sum()) == c["occupied"]
+        if tr is None:
+            assert float(res["theta"][0, 0]) == c["theta_min"] and float(res["theta"][0, 1]) == c["theta_max"]
+
+
+def test_kitti_loader_planes_vs_reference(cuda, golden):
+    g = golden("kitti_loader.npz")
+    H, W = (int(v) for v in g["hw"])
+    dx, dr, dl = to_dev(g["xyzi"], g["raw"], cuda)
+    img = ops.project_batch(dx, dr, [0, g["xyzi"].shape[0]], H, W, lut=dl)["img"][0].cpu().numpy()
+    assert np.array_equal(img[0:3], g["xyz"])
+    assert np.array_equal(img[3:4], g["range"])                  # fp32 norm, bit-exact
+    assert np.array_equal(img[4:5], g["reflectivity"])
+    assert np.array_equal(img[5:6].astype(np.int64), g["semantics"])
+
+
+def test_ragged_batch_vs_oracle_and_backprojection(cuda):
+    """Batch of ragged scans incl. an empty one; back-projected labels are bit-exact vs the oracle."""
+    lut = build_id_lut()
+    scans = [synth.synth_scan(31, "tiny"), synth.synth_scan(32, "tiny", n_points=1234),
+             (np.zeros((0, 4), np.float32), np.zeros((0,), np.uint32)), synth.synth_scan(33, "tiny", n_points=17)]
+    H, W = 16, 256
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    xyzi = np.concatenate([s[0] for s in scans])
+    raw = np.concatenate([s[1] for s in scans])
+    dx, dr, dl = to_dev(xyzi, raw, cuda)
+    res = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+    rng = np.random.default_rng(0)
+    label_img = torch.from_numpy(rng.integers(0, 20, (len(scans), H, W))).to(cuda)
+    back = ops.backproject(label_img, res["pix"], offs).cpu().numpy()
+    for b, (a, r) in enumerate(scans):
+        if a.shape[0] == 0:
+            assert int((res["winner"][b] >= 0).sum()) == 0 and float(res["img"][b].abs().sum()) == 0.0
+            continue
+        o = oproj.kitti_frame(a, r, H, W, lut)
+        sl = slice(offs[b], offs[b + 1])
+        assert np.array_equal(res["pix"][sl].cpu().numpy().astype(np.int64), o["pix"])
+        assert np.array_equal(res["winner"][b].cpu().numpy().reshape(-1).astype(np.int64), o["winner"])
+        img = res["img"][b].cpu().numpy()
+        assert np.array_equal(img[0:3], o["xyz"]) and np.array_equal(img[3:4], o["range"])
+        assert np.array_equal(img[5:6].astype(np.int64), o["semantics"])
+        row, col = o["pix"] // W, o["pix"] % W
+        assert np.array_equal(back[sl], oproj.backproject_labels(label_img[b].cpu().numpy(), row, col))
+
+
+def test_projection_properties_at_full_size(cuda):
+    """Size-independent properties on an OS1-128 batch: every point lands in an occupied pixel, each
+    winner projects to its own pixel and is the nearest point of that pixel, idempotent re-projection."""
+    B = 4
+    scans = [synth.synth_scan(100 + i, "os1-128") for i in range(B)]
+    H, W = 128, 2048
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    dx, dr, dl = to_dev(np.concatenate([s[0] for s in scans]), np.concatenate([s[1] for s in scans]), cuda)
+    res = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+    pix, win = res["pix"].long(), res["winner"].reshape(B, -1).long()
+    r2 = (dx[:, :3].double() ** 2).sum(1)
+    for b in range(B):
+        sl = slice(int(offs[b]), int(offs[b + 1]))
+        p, w = pix[sl], win[b]
+        assert int(p.min()) >= 0 and int(p.max()) < H * W
+        occ = torch.nonzero(w >= 0).squeeze(1)
+        assert torch.equal(torch.unique(p), occ)
+        assert torch.equal(p[w[occ]], occ)                                   # winner lies in its pixel
+        best = torch.full((H * W,), float("inf"), dtype=torch.float64, device=cuda)
+        best.scatter_reduce_(0, p, r2[sl], reduce="amin")
+        assert torch.equal(r2[sl][w[occ]], best[occ])                        # and is the nearest there
+    again = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+    assert torch.equal(again["img"], res["img"]) and torch.equal(again["winner"], res["winner"])
+
+
+def test_organized_cloud_identity(cuda):
+    """Ouster-style organised cloud: pixel = n, back-projection is label_img.reshape(-1) (dataset.md:109)."""
+    H, W = 8, 64
+    label_img = torch.arange(H * W, device=cuda).reshape(1, H, W)
+    pix = torch.arange(H * W, dtype=torch.int32, device=cuda)
+    out = ops.backproject(label_img, pix, [0, H * W])
+    assert torch.equal(out, label_img.reshape(-1))

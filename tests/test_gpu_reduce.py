@@ -1,0 +1,158 @@
+"""Parity of the fused reduction + metrics kernel (slu_reduce_metrics) against the oracle and the
+reference's golden vectors.  Tolerances (BASELINE.json): counts and indices bit-exact on
+margin-enforced inputs; entropy / MI / confidence within 1e-5 relative (atol 1e-6 absorbs the
+cancellation in MI = H - E[H], whose operands are O(1))."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from oracle import uncertainty as ou
+from semanticlidarunc_b200 import ops, synth
+from tests.helpers import enforce_margins, rel_close
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def run_both(x, lab, C, cuda, direct=False, ignore_index=0, n_bins=15, want_pbar=True):
+    confmat = ops.new_confmat(C, cuda)
+    bins = ops.new_ece_bins(n_bins, cuda)
+    want = ("p_bar", "pred", "conf", "H_norm", "MI_norm") if want_pbar else ("pred", "conf", "H_norm", "MI_norm")
+    out = ops.reduce_metrics(x.to(cuda), lab.to(cuda), kind="logits", conf_mode=ops.CONF_RENORM,
+                             ignore_index=ignore_index, confmat=confmat, ece_bins=bins, want=want, direct=direct)
+    torch.cuda.synchronize()
+    ref = ou.mc_reduce(x)
+    ref["confmat"] = om.confusion_counts(ref["pred"], lab, C)
+    conf, corr = om.ece_samples(ref["p_bar"], lab, "probs", ignore_index=ignore_index)
+    ref["bins"] = om.ece_bin_counts(conf.numpy(), corr.numpy(), n_bins)
+    ref["conf_map"] = om.to_probs(ref["p_bar"], "probs").max(dim=1).values
+    return out, confmat.cpu(), bins.cpu(), ref
+
+
+def check(out, confmat, bins, ref, exact=True):
+    for k, rk in (("H_norm", "H_norm"), ("MI_norm", "MI_norm"), ("conf", "conf_map")):
+        ok, aerr, rerr = rel_close(out[k].cpu().numpy(), ref[rk].numpy(), RTOL, ATOL)
+        assert ok, f"{k}: max abs err {aerr:.3e}, max rel err {rerr:.3e}"
+    if "p_bar" in out:
+        ok, aerr, rerr = rel_close(out["p_bar"].cpu().numpy(), ref["p_bar"].numpy(), RTOL, 1e-9)
+        assert ok, f"p_bar: max abs err {aerr:.3e}, max rel err {rerr:.3e}"
+    if exact:
+        assert torch.equal(out["pred"].cpu(), ref["pred"])
+        assert torch.equal(confmat, ref["confmat"])
+        n, nc, cs = ref["bins"]
+        assert np.array_equal(bins[0].numpy(), n)
+        assert np.array_equal(bins[1].numpy(), nc)
+        got = bins[2].numpy().astype(np.float64) / 2.0 ** 32
+        assert np.allclose(got, cs, rtol=1e-6, atol=1e-6)
+    else:
+        flips = int((out["pred"].cpu() != ref["pred"]).sum())
+        assert flips <= max(2, out["pred"].numel() // 20000), f"{flips} argmax flips on unconstrained input"
+
+
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("shape", [(20, 2, 20, 8, 256), (5, 3, 20, 4, 192), (1, 2, 20, 4, 256), (4, 1, 7, 3, 40),
+                                   (3, 2, 13, 5, 100), (2, 1, 32, 2, 128), (6, 1, 2, 2, 64)])
+def test_mc_logits_vs_oracle(cuda, shape, direct):
+    T, B, C, H, W = shape
+    x, lab = synth.synth_mc_logits(7 + T + C, T, B, C, H, W)
+    x, lab = enforce_margins(x, lab)
+    check(*run_both(x, lab, C, cuda, direct=direct))
+
+
+def test_ragged_width_falls_back_to_direct(cuda):
+    # HW % 4 != 0 cannot use 16-byte bulk copies: slu_reduce_metrics must dispatch the direct kernel itself
+    x, lab = synth.synth_mc_logits(3, 4, 2, 20, 3, 37)
+    x, lab = enforce_margins(x, lab)
+    check(*run_both(x, lab, 20, cuda))
+
+
+def test_unconstrained_inputs_flip_count(cuda):
+    x, lab = synth.synth_mc_logits(5, 20, 1, 20, 16, 512)
+    check(*run_both(x, lab, 20, cuda), exact=False)
+
+
+def test_golden_reference_vectors(cuda, golden):
+    g = golden("mc_reduce.npz")
+    for name in ("mc_small", "mc_peaked", "mc_c7"):
+        x = torch.from_numpy(g[name + "/logits"])
+        out = ops.reduce_metrics(x.to(cuda), None, kind="logits", want=("p_bar", "pred", "H_norm", "MI_norm"))
+        for k in ("H_norm", "MI_norm"):
+            ok, aerr, rerr = rel_close(out[k].cpu().numpy(), g[name + "/" + k], RTOL, ATOL)
+            assert ok, f"{name}/{k}: abs {aerr:.3e} rel {rerr:.3e}"
+        ok, aerr, rerr = rel_close(out["p_bar"].cpu().numpy(), g[name + "/p_bar"], RTOL, 1e-9)
+        assert ok, f"{name}/p_bar: abs {aerr:.3e} rel {rerr:.3e}"
+        # argmax may only differ where the reference's own top-2 gap is at rounding level
+        pb = torch.from_numpy(g[name + "/p_bar"])
+        top = pb.topk(2, dim=1).values
+        safe = (top[:, 0] - top[:, 1]) > 1e-5
+        assert torch.equal(out["pred"].cpu()[safe], torch.from_numpy(g[name + "/pred"])[safe])
+
+
+def test_probs_kind_and_entropy_mc(cuda, golden):
+    from semanticlidarunc_b200.utils.mc_dropout import (mc_mutual_information_norm, mc_predictive_entropy_norm,
+                                                        predictive_entropy_mc)
+    g = golden("mc_reduce.npz")
+    x = torch.from_numpy(g["mc_small/logits"])
+    probs = torch.softmax(x, dim=2).to(cuda)
+    for fn, key in ((predictive_entropy_mc, "H_mc"), (mc_predictive_entropy_norm, "H_norm"), (mc_mutual_information_norm, "MI_norm")):
+        ok, aerr, rerr = rel_close(fn(probs).cpu().numpy(), g["mc_small/" + key], RTOL, ATOL)
+        assert ok, f"{key}: abs {aerr:.3e} rel {rerr:.3e}"
+    raw = predictive_entropy_mc(probs, normalize=False).cpu().numpy()
+    ok, aerr, rerr = rel_close(raw, g["mc_small/H_mc"] * math.log(20), RTOL, ATOL)
+    assert ok
+
+
+def test_large_eps_uses_literal_clamp(cuda):
+    x, lab = synth.synth_mc_logits(9, 6, 1, 20, 4, 128, scale=6.0)
+    out = ops.reduce_metrics(x.to(cuda), None, kind="logits", eps=1e-3, want=("H_norm", "MI_norm"))
+    ref = ou.mc_reduce(x, eps=1e-3)
+    for k in ("H_norm", "MI_norm"):
+        ok, aerr, rerr = rel_close(out[k].cpu().numpy(), ref[k].numpy(), RTOL, ATOL)
+        assert ok, f"{k}: abs {aerr:.3e} rel {rerr:.3e}"
+
+
+def test_neg_inf_logits(cuda):
+    x, lab = synth.synth_mc_logits(10, 3, 1, 20, 2, 64)
+    x[:, :, 5] = float("-inf")                      # a masked class
+    out = ops.reduce_metrics(x.to(cuda), None, kind="logits", want=("H_norm", "MI_norm", "pred"))
+    ref = ou.mc_reduce(x)
+    for k in ("H_norm", "MI_norm"):
+        got = out[k].cpu().numpy()
+        assert np.isfinite(got).all()
+        ok, aerr, rerr = rel_close(got, ref[k].numpy(), RTOL, ATOL)
+        assert ok, f"{k}: abs {aerr:.3e} rel {rerr:.3e}"
+
+
+def test_accumulators_add_and_ignore_semantics(cuda):
+    C = 20
+    x, lab = synth.synth_mc_logits(11, 2, 2, C, 4, 64)
+    x, lab = enforce_margins(x, lab)
+    lab[0, 0, :8] = -1          # out-of-range labels: dropped from confmat, still ECE samples (ece.py:78)
+    lab[0, 1, :8] = C + 3
+    confmat = ops.new_confmat(C, cuda)
+    bins = ops.new_ece_bins(15, cuda)
+    for _ in range(2):           # two updates accumulate
+        ops.reduce_metrics(x.to(cuda), lab.to(cuda), kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0,
+                           confmat=confmat, ece_bins=bins, want=())
+    ref = ou.mc_reduce(x)
+    cm = om.confusion_counts(ref["pred"], lab, C)
+    conf, corr = om.ece_samples(ref["p_bar"], lab, "probs", ignore_index=0)
+    n, nc, cs = om.ece_bin_counts(conf.numpy(), corr.numpy(), 15)
+    assert torch.equal(confmat.cpu(), 2 * cm)
+    assert np.array_equal(bins[0].cpu().numpy(), 2 * n) and np.array_equal(bins[1].cpu().numpy(), 2 * nc)
+    assert int(confmat.sum()) == 2 * int(((lab >= 0) & (lab < C)).sum())      # histogram invariant
+    assert int(bins[0].sum()) == 2 * int((lab != 0).sum())
+
+
+def test_argument_errors(cuda):
+    x = torch.zeros((2, 1, 40, 2, 8), device=cuda)
+    with pytest.raises(ValueError):
+        ops.reduce_metrics(x, None, kind="logits")           # C > 32
+    x = torch.zeros((2, 1, 20, 2, 8), device=cuda)
+    with pytest.raises(ValueError):
+        ops.reduce_metrics(x, None, kind="alpha")            # alpha needs T == 1
+    with pytest.raises(ValueError):
+        ops.reduce_metrics(x, None, kind="logits", confmat=ops.new_confmat(20, cuda))    # histogram without labels
