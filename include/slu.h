@@ -131,6 +131,8 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
  *     d_img    [B,6,HW] float32  planes x,y,z,range,intensity,label; 0 where empty
  *     d_pix    [n_total] int32   pixel (row*W+col) every point projects to
  *     d_winner [B,HW]   int32    index (within its scan) of the winning point, -1 where empty
+ *     d_label  [B,HW]   int64    train id of the winning point (0 where empty): the loaders' `semantics`
+ *                                tensor (dataloader_semantic_KITTI.py:97), ready to be the metrics' labels
  *     d_theta  [B,2]    float64  (theta_min, theta_max) used per scan
  *     d_diag   [B,2]    int32    [#points with a raw id missing from the LUT,
  *                                 #points within 4 ulp of a bin edge (index could differ from numpy's)]
@@ -140,8 +142,8 @@ int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const in
                       const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
                       void* d_work,
-                      float* d_img, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
-                      slu_stream_t stream);
+                      float* d_img, int64_t* d_label, int32_t* d_pix, int32_t* d_winner, double* d_theta,
+                      int32_t* d_diag, slu_stream_t stream);
 
 /* Generic form of spherical_projection: pc [N,Cin] float64 (any Cin >= 3), one scan, output in the
  * reference's [H,W,Cin] float32 layout (src/dataset/utils.py:341-344).  Same workspace rule with B=1. */

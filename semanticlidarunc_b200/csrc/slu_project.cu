@@ -113,6 +113,7 @@ struct ProjParams {
     int* pix;                      // [n_total]
     int* winner;                   // [B*HW]
     float* img;                    // [B,6,HW] planes, or [H,W,Cin] generic
+    long long* label_img;          // [B,HW] int64 train ids (planes form only)
     double* theta_out;             // [B,2]
     int* diag;                     // [B,2]
 };
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const _
             rng = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
         }
         p.winner[cell] = w;
+        if (p.label_img) p.label_img[cell] = (long long)lab;
         if (p.img) {
             float* o = p.img + (long long)b * 6 * p.HW + px;
             o[0] = v.x; o[p.HW] = v.y; o[2 * p.HW] = v.z; o[3 * p.HW] = rng; o[4 * p.HW] = v.w; o[5 * p.HW] = lab;
@@ -365,8 +367,8 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
                                  const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                                  int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
                                  void* d_work,
-                                 float* d_img, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
-                                 slu_stream_t stream) {
+                                 float* d_img, int64_t* d_label, int32_t* d_pix, int32_t* d_winner, double* d_theta,
+                                 int32_t* d_diag, slu_stream_t stream) {
     using namespace slu;
     if (B < 1 || B > MAX_SCANS) return fail(SLU_E_RANGE, "B=%d outside [1,%d]", B, MAX_SCANS);
     if (H < 1 || W < 1 || (long long)H * W > 0x7fffffffLL) return fail(SLU_E_RANGE, "image %dx%d unsupported", H, W);
@@ -388,6 +390,7 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     p.use_range = use_theta_range; p.theta_lo = theta_lo; p.theta_hi = theta_hi;
     p.farthest = farthest_wins;
     p.img = d_img; p.theta_out = d_theta;
+    p.label_img = reinterpret_cast<long long*>(d_label);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = project_common(p, n_total, d_work, d_pix, d_winner, d_diag, false, st);
     if (rc) return rc;

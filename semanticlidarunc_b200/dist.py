@@ -1,0 +1,50 @@
+"""Multi-GPU plumbing: scans shard by index, only the integer evaluation counts are combined.
+
+The reference is single-process (its one dormant collective is an all_reduce of [sum, count],
+src/utils/agg.py:75-83).  Here every rank owns `scans[rank::world]`, runs stages 1-4 on them with no
+data-path collective, and the confusion matrix + reliability bins (C*C + 3*n_bins int64, ~3.6 KB)
+are summed with ONE all-reduce at the end of a sweep.  Integer sums are order independent, so the
+N-GPU counts are bit-identical to the 1-GPU counts.  Backend: NCCL for CUDA tensors (NVLink /
+NVSwitch: pure latency at this size), gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(n_items: int, rank: Optional[int] = None, world_size: Optional[int] = None) -> range:
+    """Indices of the scans rank `rank` owns: i = rank, rank+world, ...."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside [0,{world_size})")
+    return range(rank, n_items, world_size)
+
+
+def pack_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None) -> torch.Tensor:
+    parts = [confmat.reshape(-1)]
+    if ece_bins is not None:
+        parts.append(ece_bins.reshape(-1))
+    return torch.cat(parts).to(torch.int64)
+
+
+def allreduce_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None, group=None) -> None:
+    """Sum the evaluation counters over all ranks, in place, with a single all-reduce."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    buf = pack_counts(confmat, ece_bins)
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    n = confmat.numel()
+    confmat.copy_(buf[:n].view_as(confmat))
+    if ece_bins is not None:
+        ece_bins.copy_(buf[n:].view_as(ece_bins))

@@ -123,12 +123,13 @@ def _offsets_array(offsets):
 
 def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets, H: int, W: int, *,
                   lut: Optional[torch.Tensor] = None, theta_range=None, farthest_wins: bool = False,
-                  want_img: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
+                  want_img: bool = True, want_label: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
     """Batched stage 1 (slu_project_batch).
 
     xyzi [n_total,4] float32 CUDA (scans concatenated), raw_label [n_total] uint32-as-int32 CUDA or None,
     offsets: host sequence of B+1 point offsets.  Returns img [B,6,H,W] (x,y,z,range,intensity,label),
-    pix [n_total] int32, winner [B,H,W] int32, theta [B,2] float64, diag [B,2] int32.
+    label [B,H,W] int64 (train ids, the loaders' `semantics`), pix [n_total] int32, winner [B,H,W] int32,
+    theta [B,2] float64, diag [B,2] int32.
     """
     _lib.require_cuda()
     xyzi = _lib.as_buffer(xyzi, torch.float32, "xyzi")
@@ -155,6 +156,7 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
     img = torch.empty((B, 6, H, W), dtype=torch.float32, device=dev) if want_img else None
+    label = torch.empty((B, H, W), dtype=torch.int64, device=dev) if want_label else None
     pix = torch.empty((n_total,), dtype=torch.int32, device=dev)
     winner = torch.empty((B, H, W), dtype=torch.int32, device=dev)
     theta = torch.empty((B, 2), dtype=torch.float64, device=dev)
@@ -163,10 +165,10 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
     lo, hi = (float(theta_range[0]), float(theta_range[1])) if use_range else (0.0, 0.0)
     rc = _lib.lib().slu_project_batch(_lib.ptr(xyzi), _lib.ptr(raw_label), _lib.ptr(lut), off_p, n_total, B, H, W,
                                       int(use_range), lo, hi, int(farthest_wins), _lib.ptr(workspace),
-                                      _lib.ptr(img), _lib.ptr(pix), _lib.ptr(winner), _lib.ptr(theta), _lib.ptr(diag),
-                                      _lib.stream_ptr())
+                                      _lib.ptr(img), _lib.ptr(label), _lib.ptr(pix), _lib.ptr(winner), _lib.ptr(theta),
+                                      _lib.ptr(diag), _lib.stream_ptr())
     _lib.check(rc, "slu_project_batch")
-    return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
+    return {"img": img, "label": label, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
 
 
 def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthest_wins: bool = False,
