@@ -162,6 +162,13 @@ int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
 int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix, const int64_t* h_offsets,
                     int64_t n_total, int B, int64_t HW, int64_t* d_out, slu_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostic: stream n float32 from d_in once (16-byte loads, grid = 8 CTAs/SM) and write one
+ * float to d_out.  A read-only HBM yardstick for the roofline notes in profiles/; not on any
+ * product path.  d_in must be 16-byte aligned, n % 4 == 0.
+ */
+int slu_diag_read_stream(const float* d_in, int64_t n, float* d_out, slu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

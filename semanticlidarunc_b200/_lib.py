@@ -12,7 +12,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libslu.so")
+LIB_PATH = os.environ.get("SLU_LIB_PATH", os.path.join(_PKG, "libslu.so"))   # override: kernel experiments only
 
 IN_LOGITS, IN_PROBS, IN_ALPHA = 0, 1, 2
 CONF_RAW, CONF_RENORM = 0, 1
@@ -36,6 +36,7 @@ SIGNATURES = {
                                _p, _p, _p, _p, _p, _p, _p]),
     "slu_project_points": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p]),
     "slu_backproject": (_i, [_p, _p, _p, _i64, _i, _i64, _p, _p]),
+    "slu_diag_read_stream": (_i, [_p, _i64, _p, _p]),
 }
 
 _lib = None

@@ -15,8 +15,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
-BUILD = os.path.join(PKG, "build")
-LIB = os.path.join(PKG, "libslu.so")
+BUILD = os.path.join(PKG, "build", os.environ.get("SLU_LIB_NAME", "libslu.so")[:-3])
+LIB = os.path.join(PKG, os.environ.get("SLU_LIB_NAME", "libslu.so"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -53,7 +53,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("SLU_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -14,25 +14,43 @@
 // cores (there is no contraction here).
 //
 // Staged kernel (default).  One producer warp streams [C x TILE] fp32 slabs (C bulk async copies
-// of TILE*4 B, TMA engine, mbarrier complete_tx) through a STAGES-deep shared-memory ring, running
-// ahead of the 8 consumer warps across (t, tile) boundaries; consumers copy their pixel's C values
+// of TILE*4 B, TMA engine, mbarrier complete_tx) through a STAGES-deep shared-memory ring (3 x 20 KB
+// at C=20, three CTAs per SM), running ahead of the 8 consumer warps across (t, tile) boundaries; consumers copy their pixel's C values
 // to registers, release the slot at once, and do the math.  CTAs are persistent (grid = resident
 // CTAs), tiles are strided over CTAs.
 //
-// Per (pixel, t) with logits x_c (fast path, 7 issue slots per value):
+// Per (pixel, t) with logits x_c (fast path, ~6.5 issue slots per value):
 //   m = max_c x_c;  a_c = x_c*log2e - m*log2e;  e_c = 2^a_c;  S = sum e_c;  A = sum e_c*a_c
 //   p_c = e_c / S;  H_t = ln S - ln2 * A / S   ( = -sum p_c ln p_c, no per-value log )
+// and sum_t ln S_t is carried as a running product (one logf per 8 samples).
 // The eps clamp of the reference (p.clamp_min(1e-12) inside H_t) changes H_t by at most
-// C*eps*|ln eps| = 5.5e-10 for eps = 1e-12, below fp32 resolution of the result; it is applied
-// literally (per-value log) when eps is large enough to matter or when the fast path produced a
-// non-finite A (-inf logits).  The clamp on p_bar is always applied literally.
+// C*eps*|ln eps| = 5.5e-10 for eps = 1e-12, below fp32 resolution of the result; when eps is large
+// enough to matter, or the fast path's sum is not finite (-inf logits), the pixel's per-sample
+// entropies are recomputed with the reference's formulas verbatim (literal_entropy_sum).  The clamp
+// on p_bar is always applied literally.  The mean over T multiplies by fl(1/T) (the reference
+// divides; <= 1 ulp apart) and ln(p_bar) uses lg2.approx (relative error <= 2^-22): both far inside
+// the 1e-5 relative tolerance BASELINE.json states.
 #include <math.h>
 #include "slu_common.cuh"
 
 namespace slu {
 
-constexpr int TILE = 256;               // pixels per tile == consumer threads per CTA
-constexpr int STAGES = 4;               // ring depth (slabs of C*TILE*4 bytes)
+#ifndef SLU_TILE
+#define SLU_TILE 256
+#endif
+#ifndef SLU_STAGES
+#define SLU_STAGES 3
+#endif
+#ifndef SLU_CTAS_PER_SM
+#define SLU_CTAS_PER_SM 3
+#endif
+constexpr int TILE = SLU_TILE;          // pixels per tile == consumer threads per CTA
+constexpr int STAGES = SLU_STAGES;      // ring depth (slabs of C*TILE*4 bytes)
+// Resident CTAs per SM of the staged kernel.  Measured on B200 (profiles/reduce_variants_r01.md): the
+// consumers are latency-bound chains (max -> ex2 -> sums), so 24 consumer warps/SM (3 CTAs, <= 72
+// registers, no spills at C <= 20) reach 6.5 TB/s where 16 warps/SM (2 CTAs, 96 registers) stop at 5.8.
+constexpr int CTAS_PER_SM = SLU_CTAS_PER_SM;
+template <int CP> struct Occ { static constexpr int staged = CP <= 20 ? CTAS_PER_SM : 2; };
 constexpr int NCONS_WARPS = TILE / 32;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -58,6 +76,7 @@ struct ReduceParams {
     int tiles_per_scan;
     long long n_tiles;
     float logC;
+    float invT;
     int literal_clamp;   // apply the eps clamp per value inside H_t
     int need_ht;         // mutual information requested (per-sample entropies needed)
 };
@@ -71,9 +90,22 @@ struct HistSmem {
     float edges[SLU_MAX_BINS + 1];
 };
 
-// ---- per (pixel, t) step: turns x[] into p_t (scaled by `inv`) and returns H_t -------------------
-template <int CP, int KIND>
-__device__ __forceinline__ void sample_step(float (&x)[CP], float (&pbar)[CP], float& EH, const ReduceParams& p) {
+// ---- per-pixel running state ---------------------------------------------------------------------------
+// sum_t H[p_t] = sum_t ln S_t - ln2 * sum_t A_t/S_t.  The first sum is kept as a running PRODUCT of the
+// S_t (S_t in [1, C], flushed through one accurate logf every 8 samples so it cannot overflow), which
+// replaces T logf calls per pixel by ceil(T/8).
+template <int CP>
+struct Acc {
+    float pbar[CP];
+    float AS;      // sum_t A_t / S_t          (log2 units)
+    float P;       // running product of S_t since the last flush
+    float L;       // sum of ln(P) over flushes
+    float EH;      // literal sum_t H[p_t]     (PROBS kind only)
+};
+
+// ---- per (pixel, t) step: x[] (one sample's C values) is folded into the accumulators --------------------
+template <int CP, int KIND, bool EXACT>
+__device__ __forceinline__ void sample_step(float (&x)[CP], Acc<CP>& a, const ReduceParams& p, int t) {
     if (KIND == SLU_IN_LOGITS) {
         float m = x[0];
 #pragma unroll
@@ -82,29 +114,18 @@ __device__ __forceinline__ void sample_step(float (&x)[CP], float (&pbar)[CP], f
         float S = 0.f, A = 0.f;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-            const float a = fmaf(x[c], LOG2E, -m2);
-            const float e = ex2_approx(a);
+            const float arg = fmaf(x[c], LOG2E, -m2);
+            const float e = ex2_approx(arg);
             x[c] = e;
             S += e;
-            A = fmaf(e, a, A);
+            A = fmaf(e, arg, A);
         }
         const float inv = __frcp_rn(S);
-        if (p.need_ht) {
-            float Ht = fmaf(-LN2 * A, inv, logf(S));
-            if (p.literal_clamp || !(fabsf(Ht) <= 3.0e38f)) {
-                Ht = 0.f;
 #pragma unroll
-                for (int c = 0; c < CP; ++c) {
-                    if (c < p.C) {
-                        const float pc = fmaxf(x[c] * inv, p.eps);
-                        Ht = fmaf(-pc, logf(pc), Ht);
-                    }
-                }
-            }
-            EH += Ht;
-        }
-#pragma unroll
-        for (int c = 0; c < CP; ++c) pbar[c] = fmaf(x[c], inv, pbar[c]);
+        for (int c = 0; c < CP; ++c) a.pbar[c] = fmaf(x[c], inv, a.pbar[c]);
+        a.AS = fmaf(A, inv, a.AS);
+        a.P *= S;
+        if ((t & 7) == 7) { a.L += logf(a.P); a.P = 1.f; }
     } else {
         if (KIND == SLU_IN_ALPHA) {       // p = alpha / (alpha0 + eps)   (src/metrics/ece.py:57-58)
             float a0 = 0.f;
@@ -118,39 +139,65 @@ __device__ __forceinline__ void sample_step(float (&x)[CP], float (&pbar)[CP], f
             float Ht = 0.f;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                if (c < p.C) {
+                if (EXACT || c < p.C) {
                     const float pc = fmaxf(x[c], p.eps);
                     Ht = fmaf(-pc, logf(pc), Ht);
                 }
             }
-            EH += Ht;
+            a.EH += Ht;
         }
 #pragma unroll
-        for (int c = 0; c < CP; ++c) pbar[c] += x[c];
+        for (int c = 0; c < CP; ++c) a.pbar[c] += x[c];
     }
 }
 
+// The reference's formulas verbatim (softmax, clamp at eps, log per value), read straight from global
+// memory: used for the rare pixel whose fast-path sum is not finite (-inf logits) and for every pixel
+// when eps is large enough for the clamp inside H[p_t] to matter.
+__device__ __noinline__ float literal_entropy_sum(const ReduceParams& p, int b, long long px) {
+    float EH = 0.f;
+    for (int t = 0; t < p.T; ++t) {
+        const float* base = p.in + (((long long)t * p.B + b) * p.C) * p.HW + px;
+        float m = -INFINITY;
+        for (int c = 0; c < p.C; ++c) m = fmaxf(m, base[(long long)c * p.HW]);
+        float S = 0.f;
+        for (int c = 0; c < p.C; ++c) S += expf(base[(long long)c * p.HW] - m);
+        float Ht = 0.f;
+        for (int c = 0; c < p.C; ++c) {
+            const float pc = fmaxf(__fdiv_rn(expf(base[(long long)c * p.HW] - m), S), p.eps);
+            Ht = fmaf(-pc, logf(pc), Ht);
+        }
+        EH += Ht;
+    }
+    return EH;
+}
+
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ---- per pixel epilogue: mean, argmax, entropies, confidence, outputs, histograms ------------------
-template <int CP>
-__device__ __forceinline__ void pixel_epilogue(float (&pbar)[CP], float EH, bool live, int b, long long px,
+template <int CP, int KIND, bool EXACT>
+__device__ __forceinline__ void pixel_epilogue(Acc<CP>& a, bool live, int b, long long px,
                                                const ReduceParams& p, HistSmem& hs) {
-    const float Tf = (float)p.T;
-    float pmax = 0.f, Hb = 0.f, sump = 0.f;
+    float pmax = 0.f, Hb2 = 0.f, sump = 0.f;
     int arg = 0;
-    bool first = true;
     const long long obase = (long long)b * p.C * p.HW + px;
 #pragma unroll
     for (int c = 0; c < CP; ++c) {
-        if (c < p.C) {
-            const float pb = __fdiv_rn(pbar[c], Tf);
+        if (EXACT || c < p.C) {
+            const float pb = a.pbar[c] * p.invT;
             if (p.pbar && live) p.pbar[obase + (long long)c * p.HW] = pb;
             // torch.argmax: first maximal index, NaN counts as maximal
-            if (first || pb > pmax || (pb != pb && pmax == pmax)) { pmax = pb; arg = c; first = false; }
+            if (c == 0 || pb > pmax || (pb != pb && pmax == pmax)) { pmax = pb; arg = c; }
             const float pc = fmaxf(pb, p.eps);
-            Hb = fmaf(-pc, logf(pc), Hb);
+            Hb2 = fmaf(-pc, lg2_approx(pc), Hb2);          // log2 units; |rel err| of lg2.approx <= 2^-22
             sump += fmaxf(pb, 0.f);
         }
     }
+    const float Hb = Hb2 * LN2;
     float conf = pmax;
     if (p.conf_mode == SLU_CONF_RENORM) conf = __fdiv_rn(fmaxf(pmax, 0.f), fmaxf(sump, p.eps));
     const long long o = (long long)b * p.HW + px;
@@ -158,8 +205,17 @@ __device__ __forceinline__ void pixel_epilogue(float (&pbar)[CP], float EH, bool
         if (p.pred) p.pred[o] = arg;
         if (p.conf) p.conf[o] = conf;
         if (p.hnorm) p.hnorm[o] = __fdiv_rn(Hb, p.logC);
-        // T == 1: H[p_bar] and H[p_1] are the same number in the reference, so MI is exactly 0
-        if (p.minorm) p.minorm[o] = p.need_ht ? fmaxf(__fdiv_rn(Hb - __fdiv_rn(EH, Tf), p.logC), 0.f) : 0.f;
+        if (p.minorm) {
+            // T == 1: H[p_bar] and H[p_1] are the same number in the reference, so MI is exactly 0
+            float mi = 0.f;
+            if (p.need_ht) {
+                float EH = (KIND == SLU_IN_LOGITS) ? fmaf(-LN2, a.AS, a.L + logf(a.P)) : a.EH;
+                if (KIND == SLU_IN_LOGITS && (p.literal_clamp || !(fabsf(EH) <= 3.0e38f)))
+                    EH = literal_entropy_sum(p, b, px);
+                mi = fmaxf(__fdiv_rn(Hb - EH * p.invT, p.logC), 0.f);
+            }
+            p.minorm[o] = mi;
+        }
     }
     if (p.labels) {   // warp-uniform
         const long long lab = live ? p.labels[o] : -1;
@@ -174,6 +230,13 @@ __device__ __forceinline__ void pixel_epilogue(float (&pbar)[CP], float EH, bool
             warp_bins_add(hs.bin_n, hs.bin_c, hs.bin_s, bin, (long long)arg == lab, cf, ok);
         }
     }
+}
+
+template <int CP>
+__device__ __forceinline__ void acc_reset(Acc<CP>& a) {
+#pragma unroll
+    for (int c = 0; c < CP; ++c) a.pbar[c] = 0.f;
+    a.AS = 0.f; a.P = 1.f; a.L = 0.f; a.EH = 0.f;
 }
 
 __device__ __forceinline__ void hist_init(HistSmem& hs, const ReduceParams& p, int tid, int nthreads) {
@@ -196,8 +259,37 @@ __device__ __forceinline__ void hist_flush(HistSmem& hs, const ReduceParams& p, 
 // =====================================================================================================
 // Staged kernel: 8 consumer warps + 1 producer warp, STAGES-deep ring of [C x TILE] slabs.
 // =====================================================================================================
+// Consumer loop, compiled twice: EXACT (C == CP, no per-class predicates anywhere) and padded.
+template <int CP, int KIND, bool EXACT>
+__device__ __forceinline__ void consume_tiles(const ReduceParams& p, HistSmem& hs, const float* ring, uint32_t bar0) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int slab = (EXACT ? CP : p.C) * TILE;
+    unsigned k = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / p.tiles_per_scan);
+        const long long px0 = (tile % p.tiles_per_scan) * TILE;
+        const bool live = px0 + tid < p.HW;
+        Acc<CP> acc;
+        acc_reset(acc);
+        for (int t = 0; t < p.T; ++t, ++k) {
+            const int s = k % STAGES;
+            const uint32_t ph = (k / STAGES) & 1u;
+            mbar_wait(bar0 + 8 * s, ph);
+            const float* st = ring + (size_t)s * slab + tid;
+            float x[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                x[c] = (EXACT || c < p.C) ? st[c * TILE] : (KIND == SLU_IN_LOGITS ? -1.0e30f : 0.f);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + s));   // values are in registers: free the slot
+            sample_step<CP, KIND, EXACT>(x, acc, p, t);
+        }
+        pixel_epilogue<CP, KIND, EXACT>(acc, live, b, px0 + tid, p, hs);
+    }
+}
+
 template <int CP, int KIND>
-__global__ void __launch_bounds__(TILE + 32, 2) reduce_staged_kernel(const __grid_constant__ ReduceParams p) {
+__global__ void __launch_bounds__(TILE + 32, Occ<CP>::staged) reduce_staged_kernel(const __grid_constant__ ReduceParams p) {
     extern __shared__ __align__(128) float ring[];          // STAGES * C * TILE floats
     __shared__ __align__(8) unsigned long long bars[2 * STAGES];   // full[0..S) | empty[0..S)
     __shared__ HistSmem hs;
@@ -205,7 +297,6 @@ __global__ void __launch_bounds__(TILE + 32, 2) reduce_staged_kernel(const __gri
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t bar0 = smem_u32(bars);
-    const int slab = p.C * TILE;                             // floats per stage
 
     if (tid == 0) {
 #pragma unroll
@@ -221,6 +312,7 @@ __global__ void __launch_bounds__(TILE + 32, 2) reduce_staged_kernel(const __gri
     if (warp == NCONS_WARPS) {
         // ------------------------------- producer warp -------------------------------------------
         const uint64_t pol = policy_evict_first();           // input is read once: do not keep it in L2
+        const int slab = p.C * TILE;                         // floats per stage
         unsigned k = 0;
         for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const int b = (int)(tile / p.tiles_per_scan);
@@ -244,30 +336,8 @@ __global__ void __launch_bounds__(TILE + 32, 2) reduce_staged_kernel(const __gri
         }
     } else {
         // ------------------------------- consumer warps ------------------------------------------
-        unsigned k = 0;
-        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int b = (int)(tile / p.tiles_per_scan);
-            const long long px0 = (tile % p.tiles_per_scan) * TILE;
-            const bool live = px0 + tid < p.HW;
-            float pbar[CP];
-#pragma unroll
-            for (int c = 0; c < CP; ++c) pbar[c] = 0.f;
-            float EH = 0.f;
-            for (int t = 0; t < p.T; ++t, ++k) {
-                const int s = k % STAGES;
-                const uint32_t ph = (k / STAGES) & 1u;
-                mbar_wait(bar0 + 8 * s, ph);
-                const float* st = ring + (size_t)s * slab + tid;
-                float x[CP];
-#pragma unroll
-                for (int c = 0; c < CP; ++c)
-                    x[c] = (c < p.C) ? st[c * TILE] : (KIND == SLU_IN_LOGITS ? -1.0e30f : 0.f);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + 8 * (STAGES + s));   // values are in registers: free the slot
-                sample_step<CP, KIND>(x, pbar, EH, p);
-            }
-            pixel_epilogue<CP>(pbar, EH, live, b, px0 + tid, p, hs);
-        }
+        if (KIND == SLU_IN_LOGITS && p.C == CP) consume_tiles<CP, KIND, true>(p, hs, ring, bar0);
+        else consume_tiles<CP, KIND, false>(p, hs, ring, bar0);
     }
     __syncthreads();
     hist_flush(hs, p, tid, blockDim.x);
@@ -291,10 +361,11 @@ __global__ void __launch_bounds__(TILE, 2) reduce_direct_kernel(const __grid_con
         const long long pxs = live ? px : p.HW - 1;          // clamp so dead lanes load valid memory
         const long long tstride = (long long)p.B * p.C * p.HW;
         const float* base = p.in + ((long long)b * p.C) * p.HW + pxs;
-        float pbar[CP], x[CP], xn[CP];
+        Acc<CP> acc;
+        acc_reset(acc);
+        float x[CP], xn[CP];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) { pbar[c] = 0.f; xn[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : pad; }
-        float EH = 0.f;
+        for (int c = 0; c < CP; ++c) xn[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : pad;
         for (int t = 0; t < p.T; ++t) {
 #pragma unroll
             for (int c = 0; c < CP; ++c) x[c] = xn[c];
@@ -303,9 +374,9 @@ __global__ void __launch_bounds__(TILE, 2) reduce_direct_kernel(const __grid_con
 #pragma unroll
                 for (int c = 0; c < CP; ++c) xn[c] = (c < p.C) ? ldg_stream(nb + (long long)c * p.HW) : pad;
             }
-            sample_step<CP, KIND>(x, pbar, EH, p);
+            sample_step<CP, KIND, false>(x, acc, p, t);
         }
-        pixel_epilogue<CP>(pbar, EH, live, b, px, p, hs);
+        pixel_epilogue<CP, KIND, false>(acc, live, b, px, p, hs);
     }
     __syncthreads();
     hist_flush(hs, p, tid, blockDim.x);
@@ -316,7 +387,7 @@ template <int CP, int KIND>
 static int launch(const ReduceParams& p, bool staged, cudaStream_t stream) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
-    const long long max_ctas = 2LL * sms;
+    const long long max_ctas = (long long)(staged ? Occ<CP>::staged : 2) * sms;
     const int grid = (int)(p.n_tiles < max_ctas ? p.n_tiles : max_ctas);
     if (staged) {
         const size_t dyn = (size_t)STAGES * p.C * TILE * sizeof(float);
@@ -333,6 +404,10 @@ static int launch(const ReduceParams& p, bool staged, cudaStream_t stream) {
 template <int KIND>
 static int dispatch_cp(const ReduceParams& p, bool staged, cudaStream_t stream) {
     const int cp = (p.C + 3) / 4 * 4;
+#ifdef SLU_FAST_BUILD            // experiments only: one instantiation
+    if (cp == 20) return launch<20, KIND>(p, staged, stream);
+    return fail(SLU_E_RANGE, "fast build supports C in 17..20 only");
+#else
     switch (cp) {
         case 4: return launch<4, KIND>(p, staged, stream);
         case 8: return launch<8, KIND>(p, staged, stream);
@@ -344,6 +419,7 @@ static int dispatch_cp(const ReduceParams& p, bool staged, cudaStream_t stream) 
         case 32: return launch<32, KIND>(p, staged, stream);
     }
     return fail(SLU_E_RANGE, "C=%d outside [2,%d]", p.C, SLU_MAX_CLASSES);
+#endif
 }
 
 static int reduce_entry(const float* d_in, const int64_t* d_labels, int T, int B, int C, int64_t HW,
@@ -386,6 +462,7 @@ static int reduce_entry(const float* d_in, const int64_t* d_labels, int T, int B
     // the clamp matters once C*eps*|ln eps| reaches fp32 resolution of an O(1) entropy
     p.literal_clamp = (eps > 0.f && (double)C * eps * fabs(log((double)eps)) > 1e-8) ? 1 : 0;
     p.need_ht = (d_minorm != nullptr && T > 1) ? 1 : 0;
+    p.invT = 1.0f / (float)T;
 
     const bool staged = allow_staged && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
