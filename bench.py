@@ -251,7 +251,7 @@ def cpu_baseline(sample_scans: int, budget_s: float):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation (oracle port; /root/reference does not
+    """--impl reference: the reference's own CPU implementation (oracle port; the reference tree does not
     travel to the GPU box and is pure Python) on all host threads.  A step is a bounded sample of the
     workload: `--cpu-scans-per-step` scans of the 16-scan batch."""
     rank = int(os.environ.get("RANK", "0"))

@@ -101,6 +101,32 @@ int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_labels,
                               slu_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Stage 3+4 for the evidential (Dirichlet) head, single pass.
+ * Replaces: src/models/tester.py:484-512 = to_alpha_concentrations_from_shape_and_scale
+ *           (src/models/probability_helper.py:89-105), get_predictive_entropy (:116-121),
+ *           get_aleatoric_uncertainty (:124-130), get_epistemic_uncertainty (:133-136), the Dirichlet
+ *           mutual information of src/metrics/auroc.py:55-63, IoUEvaluator.update and
+ *           ECEAggregator.update(mode='alpha').
+ *   exactly one of:  d_outputs  [B,C+1,HW] float32 head output (C shape logits, then 1 scale logit)
+ *                    d_alpha_in [B,C,HW]   float32 concentrations
+ *   temperature (reference global 1.0), eps (probability_helper eps, 1e-8), eps_metrics (ECE/AUROC eps, 1e-12)
+ *   outputs (each may be NULL):
+ *     d_alpha_out [B,C,HW] alpha = 1 + softplus(s/T) * softmax(z) + eps
+ *     d_pred [B,HW] int64  argmax softmax(z) (argmax alpha when alpha is the input)
+ *     d_conf [B,HW]        max_c alpha / (alpha0 + eps_metrics)
+ *     d_h    [B,HW]        predictive entropy (/ log C when normalize)
+ *     d_au, d_eu [B,HW]    aleatoric / epistemic uncertainty in nats
+ *     d_mi   [B,HW]        Dirichlet mutual information, auroc.py convention (/ log C when normalize)
+ *   accumulators as in slu_reduce_metrics.
+ */
+int slu_evidential_reduce(const float* d_outputs, const float* d_alpha_in, const int64_t* d_labels,
+                          int B, int C, int64_t HW, float temperature, float eps, float eps_metrics,
+                          int normalize, int has_ignore, int64_t ignore, int n_bins, const float* h_edges,
+                          float* d_alpha_out, int64_t* d_pred, float* d_conf, float* d_h, float* d_au,
+                          float* d_eu, float* d_mi, int64_t* d_confmat, int64_t* d_ece_bins,
+                          slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 4 standalone: histograms from already-reduced maps (integer inputs).
  * Replaces: IoUEvaluator.update (src/models/evaluator.py:39-53) and the binning of
  *           ECEAggregator (src/metrics/ece.py:75-90,131-140).

@@ -92,6 +92,52 @@ def reduce_metrics(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, ki
     return out
 
 
+def evidential_reduce(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, from_outputs: bool,
+                      temperature: float = 1.0, eps: float = 1e-8, eps_metrics: float = 1e-12, normalize: bool = True,
+                      ignore_index: Optional[int] = None, edges=None,
+                      confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None,
+                      want: Sequence[str] = ("pred", "conf", "H", "AU", "EU", "MI")) -> dict:
+    """Evidential stage 3+4 (slu_evidential_reduce).
+
+    x: head output [B,C+1,H,W] (from_outputs=True: C shape logits + 1 scale logit) or alpha [B,C,H,W].
+    `want` may contain "alpha", "pred", "conf", "H", "AU", "EU", "MI".
+    """
+    _lib.require_cuda()
+    x = _lib.as_buffer(x, torch.float32, "x")
+    if x.dim() != 4:
+        raise ValueError("x must be [B,C(+1),H,W]")
+    B, Cx, H, W = x.shape
+    Cc = Cx - 1 if from_outputs else Cx
+    dev = x.device
+    if labels is not None:
+        if labels.dim() == 4 and labels.size(1) == 1:
+            labels = labels[:, 0]
+        if tuple(labels.shape) != (B, H, W):
+            raise ValueError(f"labels shape {tuple(labels.shape)} != {(B, H, W)}")
+        labels = _lib.as_buffer(labels, torch.int64, "labels")
+    out = {}
+    def mk(name, shape, dtype):
+        if name in want:
+            out[name] = torch.empty(shape, dtype=dtype, device=dev)
+            return out[name]
+        return None
+    alpha = mk("alpha", (B, Cc, H, W), torch.float32)
+    pred = mk("pred", (B, H, W), torch.int64)
+    conf, h, au, eu, mi = (mk(k, (B, H, W), torch.float32) for k in ("conf", "H", "AU", "EU", "MI"))
+    n_bins, h_edges = 0, None
+    if ece_bins is not None:
+        n_bins = ece_bins.size(1)
+        h_edges = _lib.edges_array(uniform_edges(n_bins) if edges is None else np.asarray(edges, dtype=np.float32))
+    rc = _lib.lib().slu_evidential_reduce(_lib.ptr(x) if from_outputs else None, None if from_outputs else _lib.ptr(x),
+                                          _lib.ptr(labels), B, Cc, H * W, float(temperature), float(eps), float(eps_metrics),
+                                          int(normalize), 0 if ignore_index is None else 1,
+                                          0 if ignore_index is None else int(ignore_index), n_bins, h_edges,
+                                          _lib.ptr(alpha), _lib.ptr(pred), _lib.ptr(conf), _lib.ptr(h), _lib.ptr(au),
+                                          _lib.ptr(eu), _lib.ptr(mi), _lib.ptr(confmat), _lib.ptr(ece_bins), _lib.stream_ptr())
+    _lib.check(rc, "slu_evidential_reduce")
+    return out
+
+
 def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None, *,
                   num_classes: int, ignore_index: Optional[int] = None, edges=None,
                   confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None) -> None:

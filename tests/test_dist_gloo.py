@@ -1,0 +1,90 @@
+"""world_size-2 gloo test of the N>1 path's host logic: scans shard by index, only the integer
+counters are combined, and the combined counters equal the single-process result bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import metrics as om
+from semanticlidarunc_b200 import dist as sdist
+
+C, NB, N_SCANS = 20, 15, 7
+
+
+def _scan(i):
+    g = torch.Generator().manual_seed(100 + i)
+    pred = torch.randint(0, C, (8, 64), generator=g)
+    lab = torch.randint(0, C, (8, 64), generator=g)
+    conf = torch.rand((8, 64), generator=g)
+    return pred, lab, conf
+
+
+def _counts(indices):
+    cm = torch.zeros((C, C), dtype=torch.int64)
+    bins = torch.zeros((3, NB), dtype=torch.int64)
+    for i in indices:
+        pred, lab, conf = _scan(i)
+        cm += om.confusion_counts(pred, lab, C)
+        valid = lab != 0
+        n, nc, _ = om.ece_bin_counts(conf[valid].numpy(), (pred[valid] == lab[valid]).numpy(), NB)
+        fx = torch.round(conf[valid].double() * 2.0 ** 32).to(torch.int64)
+        idx = torch.from_numpy(om.ece_bin_index(conf[valid].numpy(), om.ece_edges(NB)))
+        bins[0] += torch.from_numpy(n)
+        bins[1] += torch.from_numpy(nc)
+        bins[2].index_add_(0, idx, fx)
+    return cm, bins
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sdist.shard_indices(N_SCANS)
+    assert list(mine) == list(range(rank, N_SCANS, world))
+    cm, bins = _counts(mine)
+    sdist.allreduce_counts(cm, bins)
+    q.put((rank, cm.numpy(), bins.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_counts_equal_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=100) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    cm_ref, bins_ref = _counts(range(N_SCANS))
+    for _, cm, bins in got:
+        assert np.array_equal(cm, cm_ref.numpy()) and np.array_equal(bins, bins_ref.numpy())
+
+
+def test_shard_indices_cover_everything_once():
+    for world in (1, 2, 4, 8):
+        seen = sorted(i for r in range(world) for i in sdist.shard_indices(4071, r, world))
+        assert seen == list(range(4071))
+    with pytest.raises(ValueError):
+        sdist.shard_indices(10, 3, 2)
+
+
+def test_allreduce_is_noop_without_process_group():
+    cm = torch.ones((C, C), dtype=torch.int64)
+    sdist.allreduce_counts(cm, None)
+    assert int(cm.sum()) == C * C
