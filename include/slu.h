@@ -127,6 +127,22 @@ int slu_evidential_reduce(const float* d_outputs, const float* d_alpha_in, const
                           slu_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Evidential loss terms, forward + backward in one pass (training-step data path, config 5).
+ * Replaces: DirichletMSELoss (src/losses/dirichlet_losses.py:317-385), KL_offClasses_to_uniform
+ *           (src/losses/regularizers.py:291-389, with_conf_weighting=False), _valid_mask (:15-70).
+ *   d_alpha  [B,C,HW] float32;  d_target [B,HW] int64 (0 <= target < C on valid pixels)
+ *   validity: d_keep_mask [B,HW] uint8 (1 = valid) if given, else target not in h_ignore[0..n_ignore)
+ *   d_sums   [3] float64, ADDED to: sum of per-pixel mse | sum of per-pixel kl | number of valid pixels.
+ *            loss_term = sums[term] / max(sums[2], 1)
+ *   d_grad_* [B,C,HW] float32 or NULL: d(per-pixel term)/d(alpha), 0 on masked pixels; the caller
+ *            scales by upstream_grad / max(n_valid, 1).
+ */
+int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
+                       int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                       float eps_mse, float eps_kl, int want_mse, int want_kl,
+                       double* d_sums, float* d_grad_mse, float* d_grad_kl, slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 4 standalone: histograms from already-reduced maps (integer inputs).
  * Replaces: IoUEvaluator.update (src/models/evaluator.py:39-53) and the binning of
  *           ECEAggregator (src/metrics/ece.py:75-90,131-140).

@@ -1,0 +1,206 @@
+// slu_loss.cu -- evidential loss terms, forward + backward in one pass (config 5 of BASELINE.json).
+//
+// Replaces (reference file:line): DirichletMSELoss src/losses/dirichlet_losses.py:317-385 and
+// KL_offClasses_to_uniform src/losses/regularizers.py:291-389 (with_conf_weighting=False), the two
+// terms the shipped configs enable (src/configs/SemanticKitti_default.yaml:50-62), with the mask
+// semantics of _valid_mask src/losses/dirichlet_losses.py:15-70.  The reference materialises a
+// one-hot [B,C,H,W], several [B,C,H,W] temporaries and a permuted boolean gather, then autograd walks
+// the graph backwards; here a thread owns a pixel, reads its C concentrations once and writes the
+// analytic per-pixel gradients of each term, so each term stays an independently differentiable scalar
+// (GradNorm calls autograd.grad per term, src/utils/grad_norm.py:52).
+//
+// Per pixel, with a0 = sum(alpha), D = a0 + eps, p = alpha / D, y = one-hot(target):
+//   mse  = sum_c (y_c - p_c)^2 + (a0^2 - sum alpha_c^2) / G,          G = (a0^2 + eps)(a0 + 1)
+//   dmse/dalpha_j = -2 (y_j - p_j)/D + 2 Q/D + (2 a0 - 2 alpha_j)/G - N G'/G^2
+//                   Q = p_y - sum p_c^2,  N = a0^2 - sum alpha_c^2,  G' = 2 a0 (a0+1) + a0^2 + eps
+//   kl   = lgamma(s) - sum lgamma(a_c) + sum (a_c - 1)(psi(a_c) - psi(s)),  a = max(y + (1-y) alpha, eps), s = sum a
+//   dkl/dalpha_j = (a_j - 1) psi'(a_j) - (s - C) psi'(s)      for j != target and alpha_j > eps, else 0
+// Loss = sum over valid pixels / max(n_valid, 1); the division and the upstream gradient are applied by
+// the caller (one scalar), so the kernel needs no second pass.
+// Bound: instruction-bound (lgamma + digamma + trigamma per class), 88 B/px read, 84 B/px written per term.
+#include <math.h>
+#include "slu_common.cuh"
+#include "slu_special.cuh"
+
+namespace slu {
+
+constexpr int LOSS_THREADS = 256;
+constexpr int MAX_IGNORE = 8;
+
+struct LossParams {
+    const float* alpha;
+    const long long* target;
+    const unsigned char* keep;     // optional [B*HW] bool mask, 1 = valid (overrides the ignore list)
+    int B, C;
+    long long HW, n_px;
+    long long ignore[MAX_IGNORE];
+    int n_ignore;
+    float eps_mse, eps_kl;
+    int want_mse, want_kl;
+    double* sums;                  // [3] sum mse | sum kl | n_valid
+    float* grad_mse;               // [B,C,HW] or NULL
+    float* grad_kl;                // [B,C,HW] or NULL
+};
+
+template <int CP>
+__global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __grid_constant__ LossParams p) {
+    const int tid = threadIdx.x;
+    double acc_mse = 0.0, acc_kl = 0.0;
+    unsigned n_valid = 0;
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long g = ch * LOSS_THREADS + tid;
+        if (g >= p.n_px) continue;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const long long tgt = p.target[g];
+        bool valid;
+        if (p.keep) {
+            valid = p.keep[g] != 0;
+        } else {
+            valid = true;
+#pragma unroll
+            for (int i = 0; i < MAX_IGNORE; ++i)
+                if (i < p.n_ignore && tgt == p.ignore[i]) valid = false;
+        }
+        const float* base = p.alpha + ((long long)b * p.C) * p.HW + px;
+        float* gm = p.grad_mse ? p.grad_mse + ((long long)b * p.C) * p.HW + px : nullptr;
+        float* gk = p.grad_kl ? p.grad_kl + ((long long)b * p.C) * p.HW + px : nullptr;
+        if (!valid) {                      // masked pixels contribute nothing and get zero gradient
+            for (int c = 0; c < p.C; ++c) {
+                if (gm) gm[(long long)c * p.HW] = 0.f;
+                if (gk) gk[(long long)c * p.HW] = 0.f;
+            }
+            continue;
+        }
+        ++n_valid;
+        float a[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) a[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
+        const int y = (int)tgt;            // the reference's scatter_ requires 0 <= target < C on valid pixels
+
+        if (p.want_mse) {
+            float a0 = 0.f, s2 = 0.f, ay = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) { a0 += a[c]; s2 = fmaf(a[c], a[c], s2); if (c == y) ay = a[c]; }
+            const float D = a0 + p.eps_mse, invD = 1.0f / D;
+            const float G = (a0 * a0 + p.eps_mse) * (a0 + 1.0f), invG = 1.0f / G;
+            float sq = 0.f, sp2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (c < p.C) {
+                    const float pc = a[c] * invD;
+                    const float d = (c == y ? 1.0f : 0.0f) - pc;
+                    sq = fmaf(d, d, sq);
+                    sp2 = fmaf(pc, pc, sp2);
+                }
+            }
+            float var = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < p.C) var = fmaf(a[c] * (a0 - a[c]), invG, var);
+            acc_mse += (double)(sq + var);
+            if (gm) {
+                const float N = a0 * a0 - s2;
+                const float Gp = 2.0f * a0 * (a0 + 1.0f) + (a0 * a0 + p.eps_mse);
+                const float Q = ay * invD - sp2;
+                const float common = 2.0f * Q * invD + 2.0f * a0 * invG - N * Gp * invG * invG;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (c < p.C) {
+                        const float pc = a[c] * invD;
+                        const float yc = (c == y ? 1.0f : 0.0f);
+                        gm[(long long)c * p.HW] = fmaf(-2.0f * (yc - pc), invD, fmaf(-2.0f * a[c], invG, common));
+                    }
+                }
+            }
+        }
+        if (p.want_kl) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
+            const float psi_s = digamma_pos(s);
+            float kl = lgammaf(s);
+            float tail = 0.f;
+            if (gk) tail = (s - (float)p.C) * trigamma_pos(s);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (c < p.C) {
+                    float gj = 0.f;
+                    if (c != y) {
+                        const float ac = fmaxf(a[c], p.eps_kl);
+                        kl -= lgammaf(ac);
+                        kl = fmaf(ac - 1.0f, digamma_pos(ac) - psi_s, kl);
+                        if (gk && a[c] > p.eps_kl) gj = fmaf(ac - 1.0f, trigamma_pos(ac), -tail);
+                    }
+                    if (gk) gk[(long long)c * p.HW] = gj;
+                }
+            }
+            acc_kl += (double)kl;
+        }
+    }
+    // block reduction -> one atomic triple per CTA
+    __shared__ double s_m[LOSS_THREADS / 32], s_k[LOSS_THREADS / 32];
+    __shared__ unsigned s_n[LOSS_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
+        acc_kl += __shfl_xor_sync(0xffffffffu, acc_kl, o);
+        n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    }
+    if ((tid & 31) == 0) { s_m[tid >> 5] = acc_mse; s_k[tid >> 5] = acc_kl; s_n[tid >> 5] = n_valid; }
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0, k = 0.0, n = 0.0;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) { m += s_m[i]; k += s_k[i]; n += (double)s_n[i]; }
+        if (p.want_mse) atomicAdd(&p.sums[0], m);
+        if (p.want_kl) atomicAdd(&p.sums[1], k);
+        atomicAdd(&p.sums[2], n);
+    }
+}
+
+template <int CP>
+static int launch_loss(const LossParams& p, cudaStream_t st) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    const long long cap = 6LL * sms;
+    dirichlet_loss_kernel<CP><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("dirichlet_loss_kernel");
+    return 0;
+}
+
+}  // namespace slu
+
+extern "C" int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
+                                  int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                                  float eps_mse, float eps_kl, int want_mse, int want_kl,
+                                  double* d_sums, float* d_grad_mse, float* d_grad_kl, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_alpha || !d_target || !d_sums) return fail(SLU_E_ARG, "d_alpha / d_target / d_sums is NULL");
+    if (B < 1 || HW < 1) return fail(SLU_E_ARG, "B=%d HW=%lld must be >= 1", B, (long long)HW);
+    if (C < 2 || C > SLU_MAX_CLASSES) return fail(SLU_E_RANGE, "C=%d outside [2,%d]", C, SLU_MAX_CLASSES);
+    if (n_ignore < 0 || n_ignore > MAX_IGNORE) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,%d]", n_ignore, MAX_IGNORE);
+    if (n_ignore > 0 && !h_ignore) return fail(SLU_E_ARG, "h_ignore is NULL");
+    if (!want_mse && !want_kl) return fail(SLU_E_ARG, "no loss term requested");
+    if ((d_grad_mse && !want_mse) || (d_grad_kl && !want_kl)) return fail(SLU_E_ARG, "gradient requested for a term that is off");
+    LossParams p{};
+    p.alpha = d_alpha; p.target = reinterpret_cast<const long long*>(d_target); p.keep = d_keep_mask;
+    p.B = B; p.C = C; p.HW = HW; p.n_px = (long long)B * HW;
+    for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
+    p.n_ignore = n_ignore;
+    p.eps_mse = eps_mse; p.eps_kl = eps_kl; p.want_mse = want_mse; p.want_kl = want_kl;
+    p.sums = d_sums; p.grad_mse = d_grad_mse; p.grad_kl = d_grad_kl;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch ((C + 3) / 4 * 4) {
+        case 4: return launch_loss<4>(p, st);
+        case 8: return launch_loss<8>(p, st);
+        case 12: return launch_loss<12>(p, st);
+        case 16: return launch_loss<16>(p, st);
+        case 20: return launch_loss<20>(p, st);
+        case 24: return launch_loss<24>(p, st);
+        case 28: return launch_loss<28>(p, st);
+        default: return launch_loss<32>(p, st);
+    }
+}

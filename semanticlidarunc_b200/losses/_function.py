@@ -1,0 +1,34 @@
+"""autograd bridge: one fused forward+backward kernel launch per loss term."""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ._mask import split_ignore
+
+MAX_IDS = 8
+
+
+class _DirichletTerm(torch.autograd.Function):
+    """term 0 = expected-squared-error (DirichletMSELoss), term 1 = KL of off classes to uniform."""
+
+    @staticmethod
+    def forward(ctx, alpha, target, term: int, ignore_index, eps: float):
+        ids, keep = split_ignore(ignore_index)
+        if len(ids) > MAX_IDS:                       # rare: fold a long id list into a keep mask
+            keep = ~torch.isin(target, torch.as_tensor(ids, device=target.device, dtype=target.dtype))
+            ids = ()
+        need_grad = ctx.needs_input_grad[0]
+        r = ops.dirichlet_loss(alpha.detach(), target, ignore=ids, keep_mask=keep, eps_mse=eps, eps_kl=eps,
+                               want_mse=(term == 0), want_kl=(term == 1), want_grad=need_grad)
+        n = r["sums"][2].clamp_min(1.0)
+        loss = (r["sums"][term] / n).to(alpha.dtype)
+        if need_grad:
+            ctx.save_for_backward(r["grad_mse"] if term == 0 else r["grad_kl"], n)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g, n = ctx.saved_tensors
+        scale = (grad_out.double() / n).to(g.dtype)
+        return g * scale, None, None, None, None

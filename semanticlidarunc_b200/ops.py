@@ -138,6 +138,41 @@ def evidential_reduce(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *,
     return out
 
 
+def dirichlet_loss(alpha: torch.Tensor, target: torch.Tensor, *, ignore=(), keep_mask: Optional[torch.Tensor] = None,
+                   eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_mse: bool = True, want_kl: bool = True,
+                   want_grad: bool = True, sums: Optional[torch.Tensor] = None) -> dict:
+    """Evidential loss terms forward + analytic backward (slu_dirichlet_loss).
+
+    alpha [B,C,H,W] float32 CUDA, target [B,H,W] int64.  Returns sums float64[3] (sum mse | sum kl |
+    n_valid; accumulated into `sums` when given) and the per-pixel gradients grad_mse / grad_kl [B,C,H,W].
+    """
+    _lib.require_cuda()
+    alpha = _lib.as_buffer(alpha, torch.float32, "alpha")
+    if alpha.dim() != 4:
+        raise ValueError("alpha must be [B,C,H,W]")
+    B, Cc, H, W = alpha.shape
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    if tuple(target.shape) != (B, H, W):
+        raise ValueError(f"target shape {tuple(target.shape)} != {(B, H, W)}")
+    target = _lib.as_buffer(target.to(alpha.device), torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask.to(alpha.device), torch.bool, "keep_mask")
+        if keep_mask.numel() != B * H * W:
+            raise ValueError("keep_mask must have B*H*W elements")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    if sums is None:
+        sums = torch.zeros(3, dtype=torch.float64, device=alpha.device)
+    g_mse = torch.empty_like(alpha) if (want_grad and want_mse) else None
+    g_kl = torch.empty_like(alpha) if (want_grad and want_kl) else None
+    rc = _lib.lib().slu_dirichlet_loss(_lib.ptr(alpha), _lib.ptr(target), _lib.ptr(keep_mask), B, Cc, H * W,
+                                       h_ign, len(ign), float(eps_mse), float(eps_kl), int(want_mse), int(want_kl),
+                                       _lib.ptr(sums), _lib.ptr(g_mse), _lib.ptr(g_kl), _lib.stream_ptr())
+    _lib.check(rc, "slu_dirichlet_loss")
+    return {"sums": sums, "grad_mse": g_mse, "grad_kl": g_kl}
+
+
 def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None, *,
                   num_classes: int, ignore_index: Optional[int] = None, edges=None,
                   confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None) -> None:
