@@ -180,6 +180,10 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
  *                                 #points within 4 ulp of a bin edge (index could differ from numpy's)]
  */
 int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW);
+/* Test / profiling switch: on=1 makes slu_project_batch run the exact fp64 kernels for every point instead
+ * of the fp32-prefiltered ones (bit-identical results, ~2x slower); on=0 restores the default; on<0 only
+ * queries.  Returns the previous setting.  Process-wide host state, not for concurrent use. */
+int slu_debug_project_exact(int on);
 int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
                       const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,

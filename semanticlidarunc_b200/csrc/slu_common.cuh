@@ -86,28 +86,24 @@ __device__ __forceinline__ void warp_hist_add(unsigned* hist, int key, bool acti
 }
 
 // Reliability bins: n, n_correct (u32 per CTA) and sum(conf) as 2^-32 fixed point (u64).
-// Loops over the distinct bins present in the warp; all 32 lanes must call it.
+// Lanes are grouped by bin with one __match_any_sync; each group reduces its confidences with REDUX
+// on its own lane mask (the hardware runs one REDUX per distinct group) and its leader issues the three
+// shared-memory atomics.  All 32 lanes must call it.
 __device__ __forceinline__ void warp_bins_add(unsigned* bin_n, unsigned* bin_c, unsigned long long* bin_s,
                                               int bin, bool correct, float conf, bool active) {
-    const unsigned lane = threadIdx.x & 31;
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    const unsigned okm = __ballot_sync(0xffffffffu, active && correct);
+    if (!active) return;
     // conf in [0,1]: conf * 2^32 is exact for conf >= 2^-9 and fits 33 bits
-    const unsigned long long fx = active ? __float2ull_rn(conf * 4294967296.0f) : 0ull;
-    const unsigned fx_lo = (unsigned)(fx & 0xffffu), fx_hi = (unsigned)(fx >> 16);
-    unsigned todo = __ballot_sync(0xffffffffu, active);
-    while (todo) {
-        const int leader = __ffs(todo) - 1;
-        const int k = __shfl_sync(0xffffffffu, bin, leader);
-        const bool mine = active && (bin == k);
-        const unsigned grp = __ballot_sync(0xffffffffu, mine);
-        const unsigned ok = __ballot_sync(0xffffffffu, mine && correct);
-        const unsigned lo = __reduce_add_sync(0xffffffffu, mine ? fx_lo : 0u);
-        const unsigned hi = __reduce_add_sync(0xffffffffu, mine ? fx_hi : 0u);
-        if (lane == (unsigned)leader) {
-            atomicAdd(&bin_n[k], (unsigned)__popc(grp));
-            if (ok) atomicAdd(&bin_c[k], (unsigned)__popc(ok));
-            atomicAdd(&bin_s[k], ((unsigned long long)hi << 16) + lo);
-        }
-        todo &= ~grp;
+    const unsigned long long fx = __float2ull_rn(conf * 4294967296.0f);
+    const unsigned peers = __match_any_sync(act, bin);
+    const unsigned lo = __reduce_add_sync(peers, (unsigned)(fx & 0xffffu));
+    const unsigned hi = __reduce_add_sync(peers, (unsigned)(fx >> 16));
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) {
+        atomicAdd(&bin_n[bin], (unsigned)__popc(peers));
+        const unsigned ok = peers & okm;
+        if (ok) atomicAdd(&bin_c[bin], (unsigned)__popc(ok));
+        atomicAdd(&bin_s[bin], ((unsigned long long)hi << 16) + lo);
     }
 }
 

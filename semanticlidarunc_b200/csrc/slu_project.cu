@@ -7,6 +7,8 @@
 // The reference sorts the cloud far->near (argsort + gather), digitizes against two linspace edge
 // arrays and lets a fancy-index scatter keep the last write; here every point is handled in place:
 //
+// (exact kernels, used by the generic fp64 entry point; the batched entry point runs the
+//  fp32-prefiltered variants further down, which give bit-identical results)
 //   K0 init      key[b,px] = ~0, winner[b,px] = INT_MAX, theta min/max cells, diagnostics
 //   K1 angles    per point (fp64, same operation order as numpy, no FMA contraction):
 //                r, phi, theta -> column index from the fixed azimuth edges, range key, and a
@@ -28,6 +30,7 @@
 // from the step and an exact fix-up against those edges, then row = (H-1-cnt) mod H (the
 // reference's digitize(...)-1 with negative indices wrapping).
 #include <math.h>
+#include <stdlib.h>
 #include "slu_common.cuh"
 
 namespace slu {
@@ -109,6 +112,12 @@ struct ProjParams {
     int* col;                      // [n_total]
     unsigned long long* key;       // [B*HW]
     unsigned long long* tminmax;   // [B*2] ordered bits: min | max
+    // fast (fp32-prefiltered) path
+    float* theta32;                // [n_total]
+    float* part_min;               // [B*gx] per-block fp32 theta min
+    float* part_max;               // [B*gx]
+    int* part_diag;                // [B*gx*2] per-block (missing ids, near-edge points)
+    int gx;                        // blocks per scan of the point kernels
     // outputs
     int* pix;                      // [n_total]
     int* winner;                   // [B*HW]
@@ -228,6 +237,175 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
     if ((threadIdx.x & 31) == 0 && near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
 }
 
+
+// ====================================================================================================
+// Fast path of the batched entry point.  Two double atan2 per point made the exact kernels FP64-bound
+// (46 us for 1.9 M points).  Here every point is first classified with fp32 angles; their error is
+// bounded (atan2f <= 3 ulp of pi = 7.2e-7 rad, plus 1.2e-7 for sqrtf and the pi/2 subtraction), so a
+// point whose fp32 angle lies more than ANGLE_MARGIN from every bin edge is in the same bin as its fp64
+// angle and never needs the fp64 evaluation; the others (~0.5 % of columns, ~0.2 % of rows) take the
+// exact path unchanged.  The scan's theta min/max are found the same way: fp32 min/max first, then only
+// the points within the margin of them are evaluated in fp64.  Results are bit-identical to the exact
+// kernels (tests/test_gpu_project.py runs both against the reference's golden vectors).
+// ====================================================================================================
+constexpr double ANGLE_MARGIN = 8.0e-6;     // rad; >= 7x the fp32 angle error bound
+
+__device__ __forceinline__ double exact_phi(const float4 v) { return atan2((double)v.y, (double)v.x); }
+__device__ __forceinline__ double exact_theta(const float4 v) {
+    const double x = (double)v.x, y = (double)v.y, z = (double)v.z;
+    const double rho = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+    return __dadd_rn(-atan2(rho, z), HALF_PI);
+}
+
+// certified bin from an fp32 angle: returns cnt = #{edges <= v} or -1 if v is within the margin of an edge
+__device__ __forceinline__ int fast_count_le(double start, double step, double inv_step, int num, float a32) {
+    if (!(step > 0.0) || !(fabsf(a32) <= 4.0f)) return -1;
+    const double t = ((double)a32 - start) * inv_step;
+    const double fl = floor(t);
+    const double lo = (t - fl) * step, hi = (fl + 1.0 - t) * step;
+    if (!(lo > ANGLE_MARGIN && hi > ANGLE_MARGIN) || fl < 0.0 || fl > (double)(num - 2)) return -1;
+    return (int)fl + 1;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    // this launch also resets the per-pixel depth-test state and the per-scan scalars
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.HW; i += (long long)gridDim.x * blockDim.x) {
+        p.key[(long long)b * p.HW + i] = ~0ull;
+        p.winner[(long long)b * p.HW + i] = 0x7fffffff;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.tminmax[2 * b] = ~0ull; p.tminmax[2 * b + 1] = 0ull;
+        p.diag[2 * b] = 0; p.diag[2 * b + 1] = 0;
+    }
+    const Edges ew = make_edges(-PI, PI, p.W);
+    const double inv_step_w = ew.step > 0.0 ? 1.0 / ew.step : 0.0;
+    float tmin = INFINITY, tmax = -INFINITY;
+    int missing = 0, near_cnt = 0;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(p.xyzi + n);
+        if (p.raw_label && p.lut && __ldg(p.lut + (__ldg(p.raw_label + n) & 0xffffu)) < 0) ++missing;
+        const double x = (double)v.x, y = (double)v.y, z = (double)v.z;
+        const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
+        p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
+        const float phi32 = atan2f(v.y, v.x);
+        const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
+        int cnt_w = fast_count_le(ew.start, ew.step, inv_step_w, ew.num, phi32);
+        if (cnt_w < 0) {
+            bool near;
+            cnt_w = count_le(ew, exact_phi(v), near);
+            if (near) ++near_cnt;
+        }
+        int c = (p.W - 1 - cnt_w) % p.W;
+        if (c < 0) c += p.W;
+        p.col[n] = c;
+        p.theta32[n] = th32;
+        if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
+    }
+    __shared__ float s_min[PT_THREADS / 32], s_max[PT_THREADS / 32];
+    __shared__ int s_miss[PT_THREADS / 32], s_near[PT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        missing += __shfl_xor_sync(0xffffffffu, missing, o);
+        near_cnt += __shfl_xor_sync(0xffffffffu, near_cnt, o);
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_min[w] = tmin; s_max[w] = tmax; s_miss[w] = missing; s_near[w] = near_cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < PT_THREADS / 32; ++i) {
+            tmin = fminf(tmin, s_min[i]); tmax = fmaxf(tmax, s_max[i]);
+            missing += s_miss[i]; near_cnt += s_near[i];
+        }
+        const long long slot = (long long)b * p.gx + blockIdx.x;       // every block writes its slot: no init needed
+        p.part_min[slot] = tmin; p.part_max[slot] = tmax;
+        p.part_diag[2 * slot] = missing; p.part_diag[2 * slot + 1] = near_cnt;
+    }
+}
+
+// fp32 min/max of the scan from the per-block partials (every block reduces them again: <= gx values)
+__device__ __forceinline__ void scan_minmax32(const ProjParams& p, int b, float& lo, float& hi) {
+    __shared__ float s_lo[PT_THREADS / 32], s_hi[PT_THREADS / 32];
+    float a = INFINITY, c = -INFINITY;
+    for (int i = threadIdx.x; i < p.gx; i += blockDim.x) {
+        a = fminf(a, p.part_min[(long long)b * p.gx + i]);
+        c = fmaxf(c, p.part_max[(long long)b * p.gx + i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = a; s_hi[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    a = s_lo[0]; c = s_hi[0];
+    for (int i = 1; i < PT_THREADS / 32; ++i) { a = fminf(a, s_lo[i]); c = fmaxf(c, s_hi[i]); }
+    lo = a; hi = c;
+}
+
+// exact fp64 theta min/max: only points within the margin of the fp32 extremes are evaluated in fp64
+__global__ void __launch_bounds__(PT_THREADS) proj_fast_extremes_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    float lo32, hi32;
+    scan_minmax32(p, b, lo32, hi32);
+    const float m = (float)ANGLE_MARGIN;
+    double tmin = INFINITY, tmax = -INFINITY;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        const float t = p.theta32[n];
+        if (t <= lo32 + m || t >= hi32 - m || t != t) {
+            const double th = exact_theta(__ldg(p.xyzi + n));
+            if (th == th) { tmin = fmin(tmin, th); tmax = fmax(tmax, th); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && tmin <= tmax) {
+        atomicMin(&p.tminmax[2 * b], order_bits(tmin));
+        atomicMax(&p.tminmax[2 * b + 1], order_bits(tmax));
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    double lo, hi;
+    scan_theta_range(p, b, lo, hi);
+    const Edges eh = make_edges(lo, hi, p.H);
+    const double inv_step_h = eh.step > 0.0 ? 1.0 / eh.step : 0.0;
+    int near_cnt = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (p.theta_out) { p.theta_out[2 * b] = lo; p.theta_out[2 * b + 1] = hi; }
+        int missing = 0;
+        for (int i = 0; i < p.gx; ++i) { missing += p.part_diag[2 * ((long long)b * p.gx + i)]; near_cnt += p.part_diag[2 * ((long long)b * p.gx + i) + 1]; }
+        if (missing) atomicAdd(&p.diag[2 * b], missing);
+    }
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        int cnt_h = fast_count_le(eh.start, eh.step, inv_step_h, eh.num, p.theta32[n]);
+        if (cnt_h < 0) {
+            bool near;
+            const double th = exact_theta(__ldg(p.xyzi + n));
+            cnt_h = count_le(eh, th, near);
+            if (near && !p.use_range) near = !(th == lo || th == hi);
+            if (near) ++near_cnt;
+        }
+        int r = (p.H - 1 - cnt_h) % p.H;
+        if (r < 0) r += p.H;
+        const int px = r * p.W + p.col[n];
+        p.pix[n] = px;
+        atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
+    }
+    near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
+    if ((threadIdx.x & 31) == 0 && near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
+}
+
 __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
@@ -294,8 +472,9 @@ __global__ void __launch_bounds__(PT_THREADS) backproject_kernel(const long long
 // ---- host ------------------------------------------------------------------------------------------
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+constexpr int MAX_GX = 2048;         // upper bound of blocks per scan (partials are sized for it)
 struct Workspace {
-    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, total;
+    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, theta32, part_min, part_max, part_diag, total;
 };
 static Workspace carve(int64_t n_total, int B, int64_t HW) {
     Workspace w;
@@ -308,6 +487,11 @@ static Workspace carve(int64_t n_total, int B, int64_t HW) {
     w.pix = o;     o = align_up(o + n_total * 4, 256);
     w.winner = o;  o = align_up(o + (int64_t)B * HW * 4, 256);
     w.diag = o;    o = align_up(o + (int64_t)B * 8, 256);
+    w.theta32 = o; o = align_up(o + n_total * 4, 256);
+    const int64_t gx_max = n_total / PT_THREADS + 1 < MAX_GX ? n_total / PT_THREADS + 1 : MAX_GX;
+    w.part_min = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
+    w.part_max = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
+    w.part_diag = o; o = align_up(o + (int64_t)B * gx_max * 8, 256);
     w.total = o;
     return w;
 }
@@ -318,8 +502,14 @@ static int point_grid_x(const long long* offsets, int B, int sms) {
     long long gx = (max_n + PT_THREADS - 1) / PT_THREADS;
     const long long cap = (8LL * sms + B - 1) / B;           // ~8 resident CTAs per SM over the batch
     if (gx > cap) gx = cap;
+    if (gx > MAX_GX) gx = MAX_GX;
     return (int)(gx < 1 ? 1 : gx);
 }
+
+// A/B switch for tests and profiles/: run the exact fp64 kernels in the batched entry point too.
+// Initial value from SLU_PROJECT_EXACT=1, changed at run time by slu_debug_project_exact().
+static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && e[0] == '1') ? 1 : 0; }();
+static bool exact_only() { return g_exact_only != 0; }
 
 static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t* d_pix, int32_t* d_winner,
                           int32_t* d_diag, bool generic, cudaStream_t st) {
@@ -336,12 +526,33 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     p.pix = d_pix ? d_pix : reinterpret_cast<int*>(base + w.pix);
     p.winner = d_winner ? d_winner : reinterpret_cast<int*>(base + w.winner);
     p.diag = d_diag ? d_diag : reinterpret_cast<int*>(base + w.diag);
+    p.theta32 = reinterpret_cast<float*>(base + w.theta32);
+    p.part_min = reinterpret_cast<float*>(base + w.part_min);
+    p.part_max = reinterpret_cast<float*>(base + w.part_max);
+    p.part_diag = reinterpret_cast<int*>(base + w.part_diag);
+    const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
+    p.gx = (int)gp.x;
+    if (!generic && !exact_only()) {
+        // fp32-prefiltered path: angles(+init) -> [exact extremes] -> rows -> ties
+        proj_fast_angles_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
+        if (!p.use_range && n_total > 0) {
+            proj_fast_extremes_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_fast_extremes_kernel");
+        }
+        proj_fast_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
+        if (n_total > 0) {
+            proj_ties_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_ties_kernel");
+        }
+        return 0;
+    }
 
     const long long cells = (long long)p.B * p.HW;
     const int gi = (int)((cells + PT_THREADS - 1) / PT_THREADS < 8LL * sms ? (cells + PT_THREADS - 1) / PT_THREADS : 8LL * sms);
     proj_init_kernel<<<gi < 1 ? 1 : gi, PT_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("proj_init_kernel");
-    const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
     if (n_total > 0) {
         if (generic) proj_angles_kernel<true><<<gp, PT_THREADS, 0, st>>>(p);
         else proj_angles_kernel<false><<<gp, PT_THREADS, 0, st>>>(p);
@@ -357,6 +568,12 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
 }
 
 }  // namespace slu
+
+extern "C" int slu_debug_project_exact(int on) {
+    const int prev = slu::g_exact_only;
+    if (on >= 0) slu::g_exact_only = on ? 1 : 0;
+    return prev;
+}
 
 extern "C" int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW) {
     if (n_total < 0 || B < 1 || HW < 1) return slu::fail(SLU_E_ARG, "bad workspace query");

@@ -164,3 +164,37 @@ def test_organized_cloud_identity(cuda):
     pix = torch.arange(H * W, dtype=torch.int32, device=cuda)
     out = ops.backproject(label_img, pix, [0, H * W])
     assert torch.equal(out, label_img.reshape(-1))
+
+
+def test_fast_and_exact_kernels_agree_bit_for_bit(cuda):
+    """The batched entry point classifies points with fp32 angles and falls back to fp64 near bin edges;
+    slu_debug_project_exact(1) forces fp64 for every point.  Both must give identical bits, including on
+    points placed a few fp32/fp64 ulps around bin edges."""
+    from semanticlidarunc_b200 import _lib
+    H, W = 64, 2048
+    xyzi, raw = synth.synth_scan(77, "hdl64")
+    # adversarial points: directions sitting (almost) exactly on column edges and on the seam
+    edges = np.linspace(-np.pi, np.pi, W)
+    k = np.arange(0, 400)
+    for j, d in enumerate((0.0, 1e-7, -1e-7, 1e-15, -1e-15, 5e-6, -5e-6, 1e-5)):
+        ang = edges[(k * 5 + j) % W] + d
+        sl = slice(j * 400, (j + 1) * 400)
+        rr = np.linalg.norm(xyzi[sl, :2], axis=1)
+        xyzi[sl, 0] = (rr * np.cos(ang)).astype(np.float32)
+        xyzi[sl, 1] = (rr * np.sin(ang)).astype(np.float32)
+    scans = [(xyzi, raw), synth.synth_scan(78, "hdl64", n_points=50_000)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    dx, dr, dl = to_dev(np.concatenate([s[0] for s in scans]), np.concatenate([s[1] for s in scans]), cuda)
+    fast = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+    prev = _lib.lib().slu_debug_project_exact(1)
+    try:
+        exact = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+    finally:
+        _lib.lib().slu_debug_project_exact(prev)
+    for k in ("pix", "winner", "img", "label", "theta"):
+        assert torch.equal(fast[k], exact[k]), k
+    assert torch.equal(fast["diag"], exact["diag"])
+    for b, (a, r) in enumerate(scans):                  # and both equal the oracle
+        o = oproj.kitti_frame(a, r, H, W, build_id_lut())
+        assert np.array_equal(fast["pix"][offs[b]:offs[b + 1]].cpu().numpy().astype(np.int64), o["pix"])
+        assert np.array_equal(fast["winner"][b].cpu().numpy().reshape(-1).astype(np.int64), o["winner"])
