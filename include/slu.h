@@ -168,6 +168,8 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
  *   H, W                    image size;  all angle math is float64 (the loaders feed float64)
  *   theta_lo/hi             row range; if use_theta_range == 0 the per-scan min/max of theta is used
  *   farthest_wins           0: nearest point wins (reference default); 1: sort_largest_first=True
+ *   d_yaw_cs    [B,2]       float64  (cos a, sin a) of the loaders' yaw augmentation rotate_z
+ *                                    (src/dataset/utils.py:4-18), applied in float64 before projection; NULL = none
  *   d_work      workspace of slu_project_workspace_bytes(n_total, B, H*W) bytes, 16-byte aligned
  *   outputs (each may be NULL):
  *     d_img    [B,6,HW] float32  planes x,y,z,range,intensity,label; 0 where empty
@@ -187,7 +189,7 @@ int slu_debug_project_exact(int on);
 int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
                       const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
-                      void* d_work,
+                      const double* d_yaw_cs, void* d_work,
                       float* d_img, int64_t* d_label, int32_t* d_pix, int32_t* d_winner, double* d_theta,
                       int32_t* d_diag, slu_stream_t stream);
 
@@ -198,6 +200,21 @@ int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
                        void* d_work,
                        float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
                        slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loader glue behind the projection.
+ * Replaces: src/dataset/dataloader_semantic_KITTI.py:60-97 -- cv2.resize INTER_NEAREST (:61-62),
+ *           flip + y negation (:71-73), channel split, range (:83), build_normal_xyz (:85,
+ *           src/dataset/utils.py:30-59) and the tensor packing (:91-97).
+ *   d_img  [B,6,Hs*Ws] planes from slu_project_batch;  (Hd,Wd) output size (nearest-neighbour resize)
+ *   h_flip [B] host bytes (1 = mirror columns and negate y) or NULL;  norm_factor: Scharr scale is 1/norm_factor
+ *   outputs (each may be NULL): d_range [B,1,Hd*Wd], d_refl [B,1,..], d_xyz [B,3,..], d_normals [B,3,..]
+ *   (needs d_xyz), d_sem [B,1,..] int64 -- the five tensors Dataset.__getitem__ returns, stacked over B.
+ */
+int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
+                      const uint8_t* h_flip, float norm_factor,
+                      float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
+                      slu_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 2: label back-projection, pixels -> points (the reference has no code

@@ -149,6 +149,40 @@ def gen_kitti_loader():
                         normals=normals.numpy(), semantics=sem.numpy())
 
 
+def gen_kitti_loader_aug():
+    """SemanticKitti.__getitem__ with resize / flip / rotate; np.random is seeded so the draws are known."""
+    from dataset.dataloader_semantic_KITTI import SemanticKitti
+
+    xyzi, raw = synth.synth_scan(22, "tiny")
+    out = {"xyzi": xyzi, "raw": raw}
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "000000.bin"), os.path.join(d, "000000.label")
+        xyzi.tofile(fb)
+        raw.tofile(fl)
+        # case A: resize to 128x2048 (hard-coded in the reference), no augmentation
+        ds = SemanticKitti([(fb, fl)], rotate=False, flip=False, projection=(16, 256), resize=True)
+        r = [t.numpy() for t in ds[0]]
+        for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+            out["resize/" + k + "_sha"] = np.frombuffer(bytes.fromhex(sha(a)), dtype=np.uint8)
+        out["resize/normals_sub"] = r[3][:, ::4, ::16].copy()
+        out["resize/xyz_sub"] = r[2][:, ::4, ::16].copy()
+        # case B: rotate + flip at native resolution; find a seed whose coin flips heads
+        seed = 0
+        while True:
+            np.random.seed(seed)
+            angle = float(np.random.randint(-180, 180))
+            if np.random.rand() < 0.5:
+                break
+            seed += 1
+        np.random.seed(seed)
+        ds = SemanticKitti([(fb, fl)], rotate=True, flip=True, projection=(16, 256), resize=False)
+        r = [t.numpy() for t in ds[0]]
+        out["aug/angle"] = np.array(angle)
+        for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+            out["aug/" + k] = a
+    np.savez_compressed(os.path.join(GOLD, "kitti_loader_aug.npz"), **out)
+
+
 # ---------------------------------------------------------------- uncertainty
 def gen_mc():
     pe, mi = extract_closures(os.path.join(_refshim.REF_SRC, "models", "tester.py"),
@@ -272,6 +306,7 @@ def main():
         "projection_full": gen_projection(),
     }
     gen_kitti_loader()
+    gen_kitti_loader_aug()
     gen_mc()
     gen_evidential()
     gen_metrics()

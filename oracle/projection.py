@@ -131,3 +131,50 @@ def kitti_frame(xyzi, raw_label, height, width, lut, theta_range=None, flip=Fals
         "semantics": img[..., 4][None].astype(np.int64),
         "pix": pix, "winner": win, "theta_min": float(tmin), "theta_max": float(tmax),
     }
+
+
+def rotate_z(xyz, angle_deg):
+    """src/dataset/utils.py:4-18: xyz @ [[c,-s,0],[s,c,0],[0,0,1]] in float64."""
+    a = np.radians(angle_deg)
+    rot = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    return np.dot(xyz, rot)
+
+
+def build_normal_xyz(xyz, norm_factor=0.25):
+    """src/dataset/utils.py:30-59 (six 3x3 Scharr filters via OpenCV, cross product, normalise)."""
+    import cv2
+    x, y, z = (xyz[..., i].astype(np.float32) for i in range(3))
+    sc = 1.0 / norm_factor
+    Sxx = cv2.Scharr(x, cv2.CV_32FC1, 1, 0, scale=sc); Sxy = cv2.Scharr(x, cv2.CV_32FC1, 0, 1, scale=sc)
+    Syx = cv2.Scharr(y, cv2.CV_32FC1, 1, 0, scale=sc); Syy = cv2.Scharr(y, cv2.CV_32FC1, 0, 1, scale=sc)
+    Szx = cv2.Scharr(z, cv2.CV_32FC1, 1, 0, scale=sc); Szy = cv2.Scharr(z, cv2.CV_32FC1, 0, 1, scale=sc)
+    normal = -np.dstack((Syx * Szy - Szx * Syy, Szx * Sxy - Szy * Sxx, Sxx * Syy - Syx * Sxy))
+    n = np.linalg.norm(normal, axis=2) + 1e-10
+    normal[:, :, 0] /= n
+    normal[:, :, 1] /= n
+    normal[:, :, 2] /= n
+    return normal
+
+
+def kitti_item(xyzi, raw_label, lut, projection=(64, 2048), resize=True, flip=False, yaw_deg=None):
+    """SemanticKitti.__getitem__ (src/dataset/dataloader_semantic_KITTI.py:31-99) with the random draws
+    (yaw angle :53, flip coin :71) passed in.  Returns the five arrays in the reference's order/dtypes."""
+    import cv2
+    sem = lut[(raw_label & 0xFFFF).astype(np.int64)].astype(np.int64)
+    pc = np.concatenate([xyzi, sem[..., np.newaxis]], axis=-1)
+    if yaw_deg is not None:
+        pc[..., 0:3] = rotate_z(pc[..., 0:3].reshape(-1, 3), float(yaw_deg))
+    img, _, _, _ = spherical_projection(pc, projection[0], projection[1])
+    if resize:
+        img = cv2.resize(img, (2048, 128), interpolation=cv2.INTER_NEAREST)
+    if flip:
+        img = img[:, ::-1, :]
+        img[..., 1] *= -1
+    label_img = img[..., 4:5]
+    refl = img[..., 3]
+    xyz = img[..., 0:3]
+    rng = np.linalg.norm(xyz, axis=-1)
+    normals = build_normal_xyz(xyz[..., 0:3])
+    return (rng[..., None].transpose(2, 0, 1).astype("float32"), refl[..., None].transpose(2, 0, 1).astype("float32"),
+            xyz.transpose(2, 0, 1).astype("float32"), normals.transpose(2, 0, 1).astype("float32"),
+            label_img.transpose(2, 0, 1).astype("int64"))

@@ -1,0 +1,143 @@
+// slu_loader.cu -- loader glue behind the projection, on the device.
+//
+// Replaces (reference file:line): src/dataset/dataloader_semantic_KITTI.py:60-97 --
+// cv2.resize(..., INTER_NEAREST) :61-62, horizontal flip + y negation :71-73, channel split :75-78,
+// range = ||xyz|| :83, build_normal_xyz :85 (src/dataset/utils.py:30-59: six 3x3 Scharr filters, cross
+// product, normalisation) and the tensor packing :91-97.
+//
+//   frame_resample_kernel  one thread per OUTPUT pixel: nearest-neighbour source index exactly as
+//                          OpenCV computes it (sx = min(floor(x * (1 / (dst/src))), src-1)), optional
+//                          column flip with y -> -y; writes xyz, range, reflectivity, semantics.
+//   frame_normals_kernel   one thread per output pixel: Scharr d/dx and d/dy of x, y, z with
+//                          BORDER_REFLECT_101, in OpenCV's separable order (row pass, then column
+//                          pass; derivative taps -1,0,1; smoothing taps 3,10,3 scaled by 1/norm_factor),
+//                          n = -(dy x dz style cross product), n /= (||n|| + 1e-10).
+// Pure copies are bit-exact; the normals agree with cv2 to float32 rounding (cv2's SIMD paths may fuse
+// multiply-adds differently), tested at 1e-5.
+#include "slu_common.cuh"
+
+namespace slu {
+
+constexpr int FR_THREADS = 256;
+
+struct FrameParams {
+    const float* img;        // [B,6,Hs*Ws] x,y,z,range,intensity,label
+    int B, Hs, Ws, Hd, Wd;
+    double ify, ifx;         // OpenCV's inverse scale factors
+    unsigned long long flip_bits[4];   // bit b = flip scan b (B <= 256)
+    float tap_c, tap_s;      // Scharr smoothing taps (10, 3) * scale
+    float* range;            // [B,1,Hd*Wd]
+    float* refl;             // [B,1,Hd*Wd]
+    float* xyz;              // [B,3,Hd*Wd]
+    float* normals;          // [B,3,Hd*Wd]
+    long long* sem;          // [B,1,Hd*Wd]
+};
+
+__global__ void __launch_bounds__(FR_THREADS) frame_resample_kernel(const __grid_constant__ FrameParams p) {
+    const int b = blockIdx.y;
+    const long long HWs = (long long)p.Hs * p.Ws, HWd = (long long)p.Hd * p.Wd;
+    const bool flip = (p.flip_bits[b >> 6] >> (b & 63)) & 1ull;
+    const float* src = p.img + (long long)b * 6 * HWs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HWd; i += (long long)gridDim.x * blockDim.x) {
+        const int yd = (int)(i / p.Wd);
+        int xd = (int)(i - (long long)yd * p.Wd);
+        if (flip) xd = p.Wd - 1 - xd;                                   // resized[:, ::-1]
+        int ys = (int)floor((double)yd * p.ify), xs = (int)floor((double)xd * p.ifx);
+        ys = ys < p.Hs - 1 ? ys : p.Hs - 1;
+        xs = xs < p.Ws - 1 ? xs : p.Ws - 1;
+        const long long s = (long long)ys * p.Ws + xs;
+        const float x = src[s], z = src[2 * HWs + s];
+        float y = src[HWs + s];
+        if (flip) y = -y;                                               // :73
+        const long long o = (long long)b * HWd + i;
+        if (p.xyz) {
+            float* q = p.xyz + (long long)b * 3 * HWd + i;
+            q[0] = x; q[HWd] = y; q[2 * HWd] = z;
+        }
+        if (p.range) p.range[o] = src[3 * HWs + s];
+        if (p.refl) p.refl[o] = src[4 * HWs + s];
+        if (p.sem) p.sem[o] = (long long)src[5 * HWs + s];
+    }
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+__global__ void __launch_bounds__(FR_THREADS) frame_normals_kernel(const __grid_constant__ FrameParams p) {
+    const int b = blockIdx.y;
+    const long long HW = (long long)p.Hd * p.Wd;
+    const float* base = p.xyz + (long long)b * 3 * HW;
+    float* out = p.normals + (long long)b * 3 * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / p.Wd), x = (int)(i - (long long)y * p.Wd);
+        const int ym = reflect101(y - 1, p.Hd), yp = reflect101(y + 1, p.Hd);
+        const int xm = reflect101(x - 1, p.Wd), xp = reflect101(x + 1, p.Wd);
+        float gx[3], gy[3];                      // d/dx and d/dy of the planes x, y, z
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* P = base + (long long)c * HW;
+            const float a00 = P[(long long)ym * p.Wd + xm], a01 = P[(long long)ym * p.Wd + x], a02 = P[(long long)ym * p.Wd + xp];
+            const float a10 = P[(long long)y * p.Wd + xm], a11 = P[(long long)y * p.Wd + x], a12 = P[(long long)y * p.Wd + xp];
+            const float a20 = P[(long long)yp * p.Wd + xm], a21 = P[(long long)yp * p.Wd + x], a22 = P[(long long)yp * p.Wd + xp];
+            // Scharr(dx=1): rows (a02-a00, a12-a10, a22-a20), then column taps (s, c, s)
+            const float d0 = __fsub_rn(a02, a00), d1 = __fsub_rn(a12, a10), d2 = __fsub_rn(a22, a20);
+            gx[c] = __fadd_rn(__fmul_rn(p.tap_c, d1), __fmul_rn(p.tap_s, __fadd_rn(d0, d2)));
+            // Scharr(dy=1): rows smoothed with (s, c, s), then column taps (-1, 0, 1)
+            const float r0 = __fadd_rn(__fmul_rn(p.tap_c, a01), __fmul_rn(p.tap_s, __fadd_rn(a00, a02)));
+            const float r2 = __fadd_rn(__fmul_rn(p.tap_c, a21), __fmul_rn(p.tap_s, __fadd_rn(a20, a22)));
+            gy[c] = __fsub_rn(r2, r0);
+            (void)a11;
+        }
+        // utils.py:49-51: normal = -(Syx*Szy - Szx*Syy, Szx*Sxy - Szy*Sxx, Sxx*Syy - Syx*Sxy)
+        const float Sxx = gx[0], Sxy = gy[0], Syx = gx[1], Syy = gy[1], Szx = gx[2], Szy = gy[2];
+        float nx = -__fsub_rn(__fmul_rn(Syx, Szy), __fmul_rn(Szx, Syy));
+        float ny = -__fsub_rn(__fmul_rn(Szx, Sxy), __fmul_rn(Szy, Sxx));
+        float nz = -__fsub_rn(__fmul_rn(Sxx, Syy), __fmul_rn(Syx, Sxy));
+        const float n = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz))), 1e-10f);
+        out[i] = __fdiv_rn(nx, n);
+        out[HW + i] = __fdiv_rn(ny, n);
+        out[2 * HW + i] = __fdiv_rn(nz, n);
+    }
+}
+
+}  // namespace slu
+
+extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
+                                 const uint8_t* h_flip, float norm_factor,
+                                 float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
+                                 slu_stream_t stream) {
+    using namespace slu;
+    if (!d_img) return fail(SLU_E_ARG, "d_img is NULL");
+    if (B < 1 || B > 256) return fail(SLU_E_RANGE, "B=%d outside [1,256]", B);
+    if (Hs < 1 || Ws < 1 || Hd < 1 || Wd < 1) return fail(SLU_E_ARG, "image sizes must be >= 1");
+    if (d_normals && !d_xyz) return fail(SLU_E_ARG, "normals need the xyz output");
+    if (!(norm_factor > 0.f)) return fail(SLU_E_ARG, "norm_factor must be > 0");
+    FrameParams p{};
+    p.img = d_img; p.B = B; p.Hs = Hs; p.Ws = Ws; p.Hd = Hd; p.Wd = Wd;
+    p.ify = 1.0 / ((double)Hd / (double)Hs);          // cv::resize: inv_scale = dsize/ssize, ify = 1/inv_scale
+    p.ifx = 1.0 / ((double)Wd / (double)Ws);
+    for (int b = 0; b < B && h_flip; ++b)
+        if (h_flip[b]) p.flip_bits[b >> 6] |= 1ull << (b & 63);
+    const float scale = 1.0f / norm_factor;
+    p.tap_c = 10.0f * scale; p.tap_s = 3.0f * scale;
+    p.range = d_range; p.refl = d_refl; p.xyz = d_xyz; p.normals = d_normals;
+    p.sem = reinterpret_cast<long long*>(d_sem);
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long HWd = (long long)Hd * Wd;
+    long long gx = (HWd + FR_THREADS - 1) / FR_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;
+    if (gx > cap) gx = cap;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    frame_resample_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("frame_resample_kernel");
+    if (d_normals) {
+        frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("frame_normals_kernel");
+    }
+    return 0;
+}

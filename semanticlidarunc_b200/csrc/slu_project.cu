@@ -93,12 +93,15 @@ __device__ __forceinline__ double unorder_bits(unsigned long long u) {
 }
 #endif
 
+struct ProjParams;
+struct Pt { double x, y, z; };
 struct ProjParams {
     // input, one of the two forms
     const float4* xyzi;            // [n_total] x,y,z,intensity
     const unsigned* raw_label;     // [n_total] or NULL
     const int* lut;                // [65536] or NULL
     const double* pc;              // generic form: [N,Cin] float64
+    const double* yaw;             // [B,2] (cos, sin) of a per-scan yaw applied before projection, or NULL
     int cin;
     long long offsets[MAX_SCANS + 1];
     int B, H, W;
@@ -126,6 +129,20 @@ struct ProjParams {
     double* theta_out;             // [B,2]
     int* diag;                     // [B,2]
 };
+
+// A point of the batched form as the loaders see it: float32 file values widened to float64, then the
+// optional yaw augmentation rotate_z (src/dataset/utils.py:4-18: xyz @ [[c,-s,0],[s,c,0],[0,0,1]]).
+__device__ __forceinline__ Pt load_pt(const ProjParams& p, int b, const float4 v) {
+    Pt q;
+    q.x = (double)v.x; q.y = (double)v.y; q.z = (double)v.z;
+    if (p.yaw) {
+        const double c = p.yaw[2 * b], s = p.yaw[2 * b + 1];
+        const double x = __dadd_rn(__dmul_rn(q.x, c), __dmul_rn(q.y, s));
+        const double y = __dadd_rn(__dmul_rn(q.x, -s), __dmul_rn(q.y, c));
+        q.x = x; q.y = y;
+    }
+    return q;
+}
 
 __global__ void __launch_bounds__(PT_THREADS) proj_init_kernel(const __grid_constant__ ProjParams p) {
     const long long total = (long long)p.B * p.HW;
@@ -156,8 +173,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_angles_kernel(const __grid_co
             const double* q = p.pc + n * p.cin;
             x = q[0]; y = q[1]; z = q[2];
         } else {
-            const float4 v = __ldg(p.xyzi + n);
-            x = (double)v.x; y = (double)v.y; z = (double)v.z;
+            const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
+            x = q.x; y = q.y; z = q.z;
             if (p.raw_label && p.lut && __ldg(p.lut + (__ldg(p.raw_label + n) & 0xffffu)) < 0) ++missing;
         }
         // r = sqrt(x**2 + y**2 + z**2), p = sqrt(x**2 + y**2)   (utils.py:299, :63), each op rounded
@@ -250,11 +267,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
 // ====================================================================================================
 constexpr double ANGLE_MARGIN = 8.0e-6;     // rad; >= 7x the fp32 angle error bound
 
-__device__ __forceinline__ double exact_phi(const float4 v) { return atan2((double)v.y, (double)v.x); }
-__device__ __forceinline__ double exact_theta(const float4 v) {
-    const double x = (double)v.x, y = (double)v.y, z = (double)v.z;
-    const double rho = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
-    return __dadd_rn(-atan2(rho, z), HALF_PI);
+__device__ __forceinline__ double exact_phi(const Pt q) { return atan2(q.y, q.x); }
+__device__ __forceinline__ double exact_theta(const Pt q) {
+    const double rho = __dsqrt_rn(__dadd_rn(__dmul_rn(q.x, q.x), __dmul_rn(q.y, q.y)));
+    return __dadd_rn(-atan2(rho, q.z), HALF_PI);
 }
 
 // certified bin from an fp32 angle: returns cnt = #{edges <= v} or -1 if v is within the margin of an edge
@@ -284,9 +300,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     float tmin = INFINITY, tmax = -INFINITY;
     int missing = 0, near_cnt = 0;
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const float4 v = __ldg(p.xyzi + n);
+        const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
         if (p.raw_label && p.lut && __ldg(p.lut + (__ldg(p.raw_label + n) & 0xffffu)) < 0) ++missing;
-        const double x = (double)v.x, y = (double)v.y, z = (double)v.z;
+        const double x = q.x, y = q.y, z = q.z;
+        const float4 v = make_float4((float)x, (float)y, (float)z, 0.f);     // fp32 view for the prefilter
         const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
         const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
         p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
@@ -295,7 +312,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         int cnt_w = fast_count_le(ew.start, ew.step, inv_step_w, ew.num, phi32);
         if (cnt_w < 0) {
             bool near;
-            cnt_w = count_le(ew, exact_phi(v), near);
+            cnt_w = count_le(ew, exact_phi(q), near);
             if (near) ++near_cnt;
         }
         int c = (p.W - 1 - cnt_w) % p.W;
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_extremes_kernel(const __
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
         const float t = p.theta32[n];
         if (t <= lo32 + m || t >= hi32 - m || t != t) {
-            const double th = exact_theta(__ldg(p.xyzi + n));
+            const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
             if (th == th) { tmin = fmin(tmin, th); tmax = fmax(tmax, th); }
         }
     }
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         int cnt_h = fast_count_le(eh.start, eh.step, inv_step_h, eh.num, p.theta32[n]);
         if (cnt_h < 0) {
             bool near;
-            const double th = exact_theta(__ldg(p.xyzi + n));
+            const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
             cnt_h = count_le(eh, th, near);
             if (near && !p.use_range) near = !(th == lo || th == hi);
             if (near) ++near_cnt;
@@ -429,6 +446,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const _
             w = -1;
         } else {
             v = __ldg(p.xyzi + n0 + w);
+            if (p.yaw) {                                   // the image carries float32(rotated float64 coordinate)
+                const Pt q = load_pt(p, b, v);
+                v.x = (float)q.x; v.y = (float)q.y;
+            }
             if (p.raw_label) {
                 const unsigned raw = __ldg(p.raw_label + n0 + w) & 0xffffu;
                 lab = (float)(p.lut ? __ldg(p.lut + raw) : (int)raw);
@@ -583,7 +604,7 @@ extern "C" int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t H
 extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
                                  const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                                  int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
-                                 void* d_work,
+                                 const double* d_yaw_cs, void* d_work,
                                  float* d_img, int64_t* d_label, int32_t* d_pix, int32_t* d_winner, double* d_theta,
                                  int32_t* d_diag, slu_stream_t stream) {
     using namespace slu;
@@ -602,6 +623,7 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     p.xyzi = reinterpret_cast<const float4*>(d_xyzi);
     p.raw_label = d_raw_label;
     p.lut = d_lut;
+    p.yaw = d_yaw_cs;
     for (int b = 0; b <= B; ++b) p.offsets[b] = h_offsets[b];
     p.B = B; p.H = H; p.W = W; p.HW = (long long)H * W;
     p.use_range = use_theta_range; p.theta_lo = theta_lo; p.theta_hi = theta_hi;

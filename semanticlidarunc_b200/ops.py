@@ -204,11 +204,13 @@ def _offsets_array(offsets):
 
 def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets, H: int, W: int, *,
                   lut: Optional[torch.Tensor] = None, theta_range=None, farthest_wins: bool = False,
-                  want_img: bool = True, want_label: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
+                  yaw_deg=None, want_img: bool = True, want_label: bool = True,
+                  workspace: Optional[torch.Tensor] = None) -> dict:
     """Batched stage 1 (slu_project_batch).
 
     xyzi [n_total,4] float32 CUDA (scans concatenated), raw_label [n_total] uint32-as-int32 CUDA or None,
-    offsets: host sequence of B+1 point offsets.  Returns img [B,6,H,W] (x,y,z,range,intensity,label),
+    offsets: host sequence of B+1 point offsets; yaw_deg: optional per-scan yaw angles in degrees (the
+    loaders' rotate_z augmentation).  Returns img [B,6,H,W] (x,y,z,range,intensity,label),
     label [B,H,W] int64 (train ids, the loaders' `semantics`), pix [n_total] int32, winner [B,H,W] int32,
     theta [B,2] float64, diag [B,2] int32.
     """
@@ -242,10 +244,14 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
     winner = torch.empty((B, H, W), dtype=torch.int32, device=dev)
     theta = torch.empty((B, 2), dtype=torch.float64, device=dev)
     diag = torch.empty((B, 2), dtype=torch.int32, device=dev)
+    yaw = None
+    if yaw_deg is not None:
+        a = np.radians(np.broadcast_to(np.asarray(yaw_deg, dtype=np.float64), (B,)))
+        yaw = torch.from_numpy(np.stack([np.cos(a), np.sin(a)], axis=1).copy()).to(dev)
     use_range = theta_range is not None
     lo, hi = (float(theta_range[0]), float(theta_range[1])) if use_range else (0.0, 0.0)
     rc = _lib.lib().slu_project_batch(_lib.ptr(xyzi), _lib.ptr(raw_label), _lib.ptr(lut), off_p, n_total, B, H, W,
-                                      int(use_range), lo, hi, int(farthest_wins), _lib.ptr(workspace),
+                                      int(use_range), lo, hi, int(farthest_wins), _lib.ptr(yaw), _lib.ptr(workspace),
                                       _lib.ptr(img), _lib.ptr(label), _lib.ptr(pix), _lib.ptr(winner), _lib.ptr(theta),
                                       _lib.ptr(diag), _lib.stream_ptr())
     _lib.check(rc, "slu_project_batch")
@@ -275,6 +281,33 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
                                        _lib.ptr(theta), _lib.ptr(diag), _lib.stream_ptr())
     _lib.check(rc, "slu_project_points")
     return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag}
+
+
+def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True) -> dict:
+    """Loader glue on the device (slu_frame_tensors): img [B,6,H,W] planes -> the loaders' five tensors,
+    stacked over B: range [B,1,h,w], reflectivity [B,1,h,w], xyz [B,3,h,w], normals [B,3,h,w], semantics
+    [B,1,h,w] int64.  out_hw=(h,w) resizes with cv2's INTER_NEAREST rule; flip: per-scan booleans."""
+    _lib.require_cuda()
+    img = _lib.as_buffer(img, torch.float32, "img")
+    if img.dim() != 4 or img.size(1) != 6:
+        raise ValueError("img must be [B,6,H,W]")
+    B, _, Hs, Ws = img.shape
+    Hd, Wd = (Hs, Ws) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
+    dev = img.device
+    h_flip = None
+    if flip is not None:
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(flip, dtype=np.uint8), (B,)))
+        h_flip = f.ctypes.data_as(_lib.C.c_void_p)
+    out = {"range": torch.empty((B, 1, Hd, Wd), dtype=torch.float32, device=dev),
+           "reflectivity": torch.empty((B, 1, Hd, Wd), dtype=torch.float32, device=dev),
+           "xyz": torch.empty((B, 3, Hd, Wd), dtype=torch.float32, device=dev),
+           "normals": torch.empty((B, 3, Hd, Wd), dtype=torch.float32, device=dev) if want_normals else None,
+           "semantics": torch.empty((B, 1, Hd, Wd), dtype=torch.int64, device=dev)}
+    rc = _lib.lib().slu_frame_tensors(_lib.ptr(img), B, Hs, Ws, Hd, Wd, h_flip, float(norm_factor),
+                                      _lib.ptr(out["range"]), _lib.ptr(out["reflectivity"]), _lib.ptr(out["xyz"]),
+                                      _lib.ptr(out["normals"]), _lib.ptr(out["semantics"]), _lib.stream_ptr())
+    _lib.check(rc, "slu_frame_tensors")
+    return out
 
 
 def backproject(label_img: torch.Tensor, pix: torch.Tensor, offsets) -> torch.Tensor:

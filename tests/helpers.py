@@ -41,3 +41,24 @@ def rel_close(a, b, rtol, atol):
     b = np.asarray(b, dtype=np.float64)
     err = np.abs(a - b) - (atol + rtol * np.abs(b))
     return float(err.max()) <= 0.0, float(np.abs(a - b).max()), float((np.abs(a - b) / np.maximum(np.abs(b), 1e-30)).max())
+
+
+def normals_condition_mask(xyz_chw, thresh=1e-2):
+    """Pixels where build_normal_xyz is well conditioned.
+
+    The normal is the normalised cross product of the Scharr d/dx and d/dy vectors.  Where those two
+    vectors are (nearly) parallel -- e.g. the block corners of a nearest-neighbour upsampled image --
+    the cross product is pure float32 rounding noise and its normalised direction is arbitrary in ANY
+    implementation (cv2 itself changes with its SIMD dispatch).  mask = |gx x gy| > thresh * |gx| |gy|,
+    or both gradients zero (normal exactly 0)."""
+    import cv2
+    g = []
+    for c in range(3):
+        p = np.ascontiguousarray(xyz_chw[c], dtype=np.float32)
+        g.append((cv2.Scharr(p, cv2.CV_32FC1, 1, 0, scale=4.0).astype(np.float64),
+                  cv2.Scharr(p, cv2.CV_32FC1, 0, 1, scale=4.0).astype(np.float64)))
+    gx = np.stack([a for a, _ in g], -1)
+    gy = np.stack([b for _, b in g], -1)
+    cr = np.linalg.norm(np.cross(gx, gy), axis=-1)
+    den = np.linalg.norm(gx, axis=-1) * np.linalg.norm(gy, axis=-1)
+    return (cr > thresh * den) | (den == 0)

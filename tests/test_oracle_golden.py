@@ -158,3 +158,17 @@ def test_oracle_vs_live_reference_on_fresh_seeds():
     assert torch.equal(alpha, ou.to_alpha_concentrations_from_shape_and_scale(o[:, :20], o[:, 20:21]))
     assert torch.equal(ph.get_aleatoric_uncertainty(alpha), ou.get_aleatoric_uncertainty(alpha))
     assert torch.equal(ph.get_predictive_entropy_norm(alpha), ou.get_predictive_entropy_norm(alpha))
+
+
+def test_kitti_item_oracle_vs_golden(golden):
+    """Full __getitem__ restatement (resize, flip, yaw, normals through cv2) against the reference Dataset."""
+    import hashlib
+    g = golden("kitti_loader_aug.npz")
+    lut = build_id_lut()
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    r = oproj.kitti_item(g["xyzi"], g["raw"], lut, projection=(16, 256), resize=True)
+    for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+        assert sha(a) == bytes(g["resize/" + k + "_sha"]).hex(), k
+    r = oproj.kitti_item(g["xyzi"], g["raw"], lut, projection=(16, 256), resize=False, flip=True, yaw_deg=float(g["aug/angle"]))
+    for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+        assert np.array_equal(a, g["aug/" + k]), k
