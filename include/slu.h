@@ -156,6 +156,19 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
                       int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Error/score histogram: the sufficient statistic of the reference's AUROC, risk-coverage
+ * and accuracy-vs-uncertainty aggregators, which keep every pixel on the host and sort at compute().
+ * Replaces the accumulation in AUROCAggregator.update (src/metrics/auroc.py:101-141),
+ *           UncertaintyAccuracyAggregator.update (src/models/evaluator.py:660-701),
+ *           UncertaintyAggregator.add_batch (src/metrics/aurc.py:273-304).
+ *   d_score [n] float32 (clamped to [0,1]; NaN skipped), d_pred / d_labels [n] int64,
+ *   h_ignore: up to 4 label values to skip;  d_hist [2, n_score_bins] int64, ADDED to:
+ *   hist[0][k] = correct pixels, hist[1][k] = wrong pixels with floor(score * n_score_bins) == k.
+ */
+int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                   int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Stage 1: spherical range-image projection with a nearest-range depth test, batched.
  * Replaces: spherical_projection (src/dataset/utils.py:288-349) + to_deflection_coordinates
  *           (:61-67) + the KITTI loader glue around it

@@ -271,6 +271,34 @@ def gen_metrics():
                     f"ece_{mode}/n": stats["n"].to_numpy(), f"ece_{mode}/acc": stats["acc"].to_numpy(),
                     f"ece_{mode}/avg_conf": stats["conf"].to_numpy(),
                     f"ece_{mode}/ece_mce": np.array([ece, mce])})
+    # AUROC (error detection) and accuracy-vs-uncertainty bins, every pixel kept (max_samples=None)
+    from metrics.auroc import AUROCAggregator
+    from models.evaluator import UncertaintyAccuracyAggregator
+    x = torch.softmax(torch.randn((2, C, 16, 128), generator=g) * 2.0, dim=1)
+    labels = torch.randint(0, C, (2, 16, 128), generator=g)
+    with torch.no_grad():
+        labels = torch.where(torch.rand((2, 16, 128), generator=g) < 0.6, x.argmax(1), labels)
+    out["auroc/probs"] = x.numpy(); out["auroc/labels"] = labels.numpy()
+    for score in ("entropy_norm", "entropy", "1-maxprob"):
+        a = AUROCAggregator(mode="probs", score=score, ignore_index=0, max_samples=None)
+        a.update(x[:1], labels[:1]); a.update(x[1:], labels[1:])
+        out[f"auroc/probs_{score}"] = np.array(a.compute(save_plot_path=os.path.join(tempfile.gettempdir(), "slu_gold_roc.png"))[0])
+    override = torch.rand((2, 16, 128), generator=g)
+    a = AUROCAggregator(mode="probs", score="mi_norm", ignore_index=0, max_samples=None)
+    a.update(x, labels, score_override=override)
+    out["auroc/override"] = override.numpy(); out["auroc/probs_override"] = np.array(a.compute(save_plot_path=os.path.join(tempfile.gettempdir(), "slu_gold_roc.png"))[0])
+    alpha = torch.nn.functional.softplus(torch.randn((2, C, 16, 128), generator=g) * 3.0) + 1.0
+    out["auroc/alpha"] = alpha.numpy()
+    for score in ("mi_norm", "entropy_norm"):
+        a = AUROCAggregator(mode="alpha", score=score, ignore_index=0, max_samples=None)
+        a.update(alpha, labels)
+        out[f"auroc/alpha_{score}"] = np.array(a.compute(save_plot_path=os.path.join(tempfile.gettempdir(), "slu_gold_roc.png"))[0])
+    ua = UncertaintyAccuracyAggregator(max_samples=None)
+    ua.update(labels=labels, preds=x.argmax(1), uncertainty=override, ignore_ids=(0,))
+    for nb in (10, 20):
+        df = ua.binned_accuracy(num_bins=nb)
+        out[f"ua/n_{nb}"] = df["n"].to_numpy(); out[f"ua/acc_{nb}"] = df["accuracy"].to_numpy()
+
     # empty aggregator: 2-tuple with NaNs (ece.py:157-158)
     r = ECEAggregator(n_bins=15, mode="probs", ignore_index=0).compute(save_plot_path=None)
     out["ece_empty/len"] = np.array(len(r))

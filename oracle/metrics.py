@@ -132,3 +132,25 @@ def ece_from_counts(n, n_correct, conf_sum):
         acc = np.where(n > 0, np.asarray(n_correct, dtype=np.float64) / n, np.nan)
         avg = np.where(n > 0, np.asarray(conf_sum, dtype=np.float64) / n, np.nan)
     return ece_from_stats(n, acc, avg)
+
+
+def auroc_error_detection(scores: np.ndarray, is_error: np.ndarray) -> float:
+    """src/metrics/auroc.py:65-78 (`_roc_from_scores`): sort by descending score, trapezoid over (fpr, tpr)."""
+    order = np.argsort(-scores)
+    y = is_error[order].astype(np.float64)
+    P, N = y.sum(), y.size - y.sum()
+    if P == 0 or N == 0:
+        return float("nan")
+    tpr = np.concatenate(([0.0], np.cumsum(y) / P, [1.0]))
+    fpr = np.concatenate(([0.0], np.cumsum(1.0 - y) / N, [1.0]))
+    return float(np.trapezoid(tpr, fpr))
+
+
+def binned_accuracy(uncert: np.ndarray, correct: np.ndarray, num_bins: int):
+    """src/models/evaluator.py:726-749: np.histogram over float32 uniform edges -> (n, accuracy)."""
+    edges = np.linspace(0.0, 1.0, num_bins + 1, dtype=np.float32)
+    edges[0], edges[-1] = 0.0, 1.0
+    n = np.histogram(uncert, bins=edges)[0].astype(int)
+    csum = np.histogram(uncert, bins=edges, weights=correct.astype(np.float32))[0]
+    acc = np.divide(csum, n, out=np.full_like(csum, np.nan, dtype=float), where=n > 0)
+    return n, acc

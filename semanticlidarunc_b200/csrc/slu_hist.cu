@@ -94,7 +94,54 @@ __global__ void __launch_bounds__(HIST_THREADS) confusion_ece_kernel(const __gri
         }
 }
 
+// ---- error/score histogram: the sufficient statistic of AUROC, risk-coverage and accuracy-vs-uncertainty ----
+// Replaces the per-pixel host arrays of AUROCAggregator (src/metrics/auroc.py:101-141), UncertaintyAccuracyAggregator
+// (src/models/evaluator.py:660-701) and UncertaintyAggregator (src/metrics/aurc.py:273-304): every valid pixel adds 1 to
+// hist[is_error][floor(clamp(score,0,1) * M)].  M is large (default 60000), so the histogram lives in global memory
+// (2*M int64 ~ 1 MB, L2-resident) and is updated with fire-and-forget RED atomics; 20 B/px read.
+__global__ void __launch_bounds__(HIST_THREADS) score_hist_kernel(const float* __restrict__ score, const long long* __restrict__ pred,
+                                                                  const long long* __restrict__ labels, long long n, int M,
+                                                                  int n_ignore, long long ig0, long long ig1, long long ig2, long long ig3,
+                                                                  unsigned long long* __restrict__ hist) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long lb = __ldg(labels + i), pr = __ldg(pred + i);
+        const float s = __ldg(score + i);
+        bool valid = s == s;
+        if (n_ignore > 0 && lb == ig0) valid = false;
+        if (n_ignore > 1 && lb == ig1) valid = false;
+        if (n_ignore > 2 && lb == ig2) valid = false;
+        if (n_ignore > 3 && lb == ig3) valid = false;
+        if (!valid) continue;
+        const double c = (double)fminf(fmaxf(s, 0.f), 1.f) * (double)M;       // exact product: bin = #{k/M <= s} - 1
+        int bin = (int)c;
+        bin = bin > M - 1 ? M - 1 : bin;
+        atomicAdd(&hist[(pr != lb ? (long long)M : 0ll) + bin], 1ull);
+    }
+}
+
 }  // namespace slu
+
+extern "C" int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                              int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream) {
+    using namespace slu;
+    if (n < 0) return fail(SLU_E_ARG, "n < 0");
+    if (n == 0) return 0;
+    if (!d_score || !d_pred || !d_labels || !d_hist) return fail(SLU_E_ARG, "NULL pointer");
+    if (n_score_bins < 1 || n_score_bins > (1 << 24)) return fail(SLU_E_RANGE, "n_score_bins=%d outside [1,2^24]", n_score_bins);
+    if (n_ignore < 0 || n_ignore > 4 || (n_ignore > 0 && !h_ignore)) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,4]", n_ignore);
+    long long ig[4] = {0, 0, 0, 0};
+    for (int i = 0; i < n_ignore; ++i) ig[i] = h_ignore[i];
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long want = (n + HIST_THREADS - 1) / HIST_THREADS;
+    const long long cap = 8LL * sms;
+    score_hist_kernel<<<(unsigned)(want < cap ? want : cap), HIST_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_score, reinterpret_cast<const long long*>(d_pred), reinterpret_cast<const long long*>(d_labels), n, n_score_bins,
+        n_ignore, ig[0], ig[1], ig[2], ig[3], reinterpret_cast<unsigned long long*>(d_hist));
+    SLU_LAUNCH_CHECK("score_hist_kernel");
+    return 0;
+}
 
 extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const float* d_conf,
                                  int64_t n, int C, int has_ignore, int64_t ignore,

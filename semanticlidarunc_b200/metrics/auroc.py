@@ -1,0 +1,119 @@
+"""`AUROCAggregator` with the reference's interface (src/metrics/auroc.py:8-164), as a device histogram.
+
+Same constructor `(mode, score, ignore_index, max_samples, seed, eps)`, `update(preds, labels,
+score_override=None)`, `compute(save_plot_path, title, dpi)`, `reset()`.  The reference keeps every
+(score, is_error) pair on the host and argsorts them at compute(); here `update` is the fused
+uncertainty kernel (score map) plus one histogram kernel, and the state is `[2, 60000]` int64 counts.
+
+AUROC from the histogram treats the samples of one fine bin as tied (the reference orders exact ties
+arbitrarily); the difference is at most half the probability that a wrong and a correct pixel share a
+bin of width 1/60000 -- below 1e-5 for continuous scores, and far below the sampling noise of the
+reference's `max_samples` subsample, which is accepted and ignored here (every pixel is counted).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+
+_MODES = {"alpha": ("alpha", ops.CONF_RAW), "logits": ("logits", ops.CONF_RAW), "probs": ("probs", ops.CONF_RENORM)}
+
+
+def roc_from_hist(hist: np.ndarray):
+    """(fpr, tpr, thresholds, auroc) for 'high score => error', from [2,M] counts (row 1 = errors)."""
+    ok, err = hist[0].astype(np.float64), hist[1].astype(np.float64)
+    P, N = err.sum(), ok.sum()
+    if P == 0 or N == 0:
+        return None, None, None, float("nan")
+    M = hist.shape[1]
+    tps = np.cumsum(err[::-1])
+    fps = np.cumsum(ok[::-1])
+    tpr = np.concatenate(([0.0], tps / P, [1.0]))
+    fpr = np.concatenate(([0.0], fps / N, [1.0]))
+    thr = np.concatenate(([np.inf], (np.arange(M)[::-1]) / M, [-np.inf]))
+    return fpr, tpr, thr, float(np.trapezoid(tpr, fpr))
+
+
+class AUROCAggregator:
+    def __init__(self, mode="alpha", score="entropy_norm", ignore_index=None, max_samples=None, seed=0, eps=1e-12,
+                 n_score_bins: int = ops.SCORE_BINS):
+        assert mode in {"alpha", "logits", "probs"}
+        assert score in {"entropy", "entropy_norm", "mi", "mi_norm", "1-maxprob"}
+        self.mode, self.score = mode, score
+        self.ignore_index = ignore_index
+        self.max_samples = max_samples
+        self.eps = float(eps)
+        self.n_score_bins = int(n_score_bins)
+        self._hist = None
+
+    def _accumulator(self, dev=None):
+        if self._hist is None:
+            self._hist = ops.new_score_hist(_lib.require_cuda(dev), self.n_score_bins)
+        return self._hist
+
+    def reset(self):
+        if self._hist is not None:
+            self._hist.zero_()
+
+    @property
+    def _seen(self) -> int:
+        return 0 if self._hist is None else int(self._hist.sum().item())
+
+    @torch.no_grad()
+    def _scores_and_pred(self, preds: torch.Tensor):
+        """(score map in [0,1]-ish, argmax map) exactly as _uncertainty_score / _to_probs (auroc.py:36-63)."""
+        C = preds.size(1)
+        if self.mode == "alpha" and self.score in {"mi", "mi_norm"}:
+            # AUROC depends on ranks only: the un-normalised scores ('mi', 'entropy') are histogrammed as their
+            # /log C versions, a monotone map into [0,1]
+            r = ops.evidential_reduce(preds, from_outputs=False, eps_metrics=self.eps, normalize=True, want=("MI", "pred"))
+            return r["MI"], r["pred"]
+        kind, conf_mode = _MODES[self.mode]
+        r = ops.reduce_metrics(preds, kind=kind, conf_mode=conf_mode, eps=self.eps, want=("H_norm", "conf", "pred"),
+                               normalize=True)
+        if self.score == "1-maxprob":
+            return 1.0 - r["conf"], r["pred"]
+        return r["H_norm"], r["pred"]
+
+    @torch.no_grad()
+    def update(self, preds: torch.Tensor, labels: torch.Tensor, score_override: torch.Tensor | None = None):
+        assert preds.dim() == 4 and (labels.dim() == 3 or (labels.dim() == 4 and labels.size(1) == 1)), \
+            "labels must be [B,H,W] or [B,1,H,W]"
+        if labels.dim() == 4:
+            labels = labels[:, 0]
+        dev = preds.device if preds.is_cuda else _lib.require_cuda()
+        preds, labels = preds.to(dev, non_blocking=True), labels.to(dev, non_blocking=True)
+        score_map, pred = self._scores_and_pred(preds)
+        if score_override is not None:
+            score_map = score_override.to(dev)          # expected in [0,1] (H_norm / MI_norm maps); clamped otherwise
+        ops.score_hist(score_map, pred, labels, self._accumulator(dev),
+                       ignore=() if self.ignore_index is None else (self.ignore_index,))
+
+    def add_maps(self, score_map: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor):
+        """Accumulate from maps the fused kernel already produced (no second pass over the class axis)."""
+        ops.score_hist(score_map, pred, labels, self._accumulator(score_map.device),
+                       ignore=() if self.ignore_index is None else (self.ignore_index,))
+
+    def compute(self, save_plot_path: str | None = None, title: str = "ROC: error detection", dpi: int = 200):
+        if self._hist is None or self._seen == 0:
+            return float("nan"), {}
+        fpr, tpr, thr, auroc = roc_from_hist(self._hist.cpu().numpy())
+        if math.isnan(auroc):
+            return auroc, {}
+        fig = None
+        if save_plot_path is not None:
+            try:
+                import matplotlib
+                matplotlib.use("Agg")
+                import matplotlib.pyplot as plt
+                fig, ax = plt.subplots(figsize=(6.0, 5.0), dpi=dpi)
+                ax.plot([0, 1], [0, 1]); ax.plot(fpr, tpr)
+                ax.set_xlim(0, 1); ax.set_ylim(0, 1); ax.set_xlabel("FPR"); ax.set_ylabel("TPR")
+                ax.set_title(f"{title}\nAUROC = {auroc:.4f}"); ax.grid(True, alpha=0.3)
+                fig.tight_layout(); fig.savefig(save_plot_path, bbox_inches="tight", dpi=dpi); plt.close(fig)
+            except Exception:
+                fig = None
+        return auroc, {"fpr": fpr, "tpr": tpr, "thresholds": thr}, fig

@@ -11,6 +11,7 @@ host until `.confmat` / `.compute()` is read.  `device` only says where `.confma
 from __future__ import annotations
 
 import numpy as np
+import pandas as pd
 import torch
 
 from .. import _lib, ops
@@ -90,3 +91,63 @@ class IoUEvaluator:
             miou = float("nan")
         out["mIoU"] = miou
         return miou, out
+
+
+class UncertaintyAccuracyAggregator:
+    """Accuracy per uncertainty bin with the reference's interface (src/models/evaluator.py:640-749):
+    `update(labels, preds, uncertainty, ignore_ids=())`, `binned_accuracy(num_bins, bin_width, bin_edges)`,
+    `make_bins(...)`, `reset()`.  State is the device error/score histogram ([2, 60000] int64) instead of
+    per-pixel host arrays; coarse bins whose edges are multiples of 1/60000 (10, 15, 20, 50, 100 bins ...)
+    are exact, other edges are exact up to the pixels inside the one fine bin that straddles each edge.
+    `max_samples` is accepted and ignored (every pixel is counted)."""
+
+    def __init__(self, max_samples: int | None = None, seed: int = 0, n_score_bins: int = ops.SCORE_BINS):
+        self.max_samples = max_samples
+        self.n_score_bins = int(n_score_bins)
+        self._hist = None
+
+    def reset(self):
+        if self._hist is not None:
+            self._hist.zero_()
+
+    @property
+    def _seen(self) -> int:
+        return 0 if self._hist is None else int(self._hist.sum().item())
+
+    @torch.no_grad()
+    def update(self, labels: torch.Tensor, preds: torch.Tensor, uncertainty: torch.Tensor, ignore_ids=()):
+        assert labels.shape == preds.shape == uncertainty.shape, "shapes must match"
+        dev = uncertainty.device if uncertainty.is_cuda else _lib.require_cuda()
+        if self._hist is None:
+            self._hist = ops.new_score_hist(dev, self.n_score_bins)
+        ops.score_hist(uncertainty.detach().to(dev), preds.detach().to(dev), labels.detach().to(dev), self._hist,
+                       ignore=tuple(ignore_ids))
+
+    def make_bins(self, num_bins: int | None = None, bin_width: float | None = None, bin_edges=None) -> np.ndarray:
+        if bin_edges is not None:
+            edges = np.asarray(bin_edges, dtype=np.float32)
+        elif bin_width is not None:
+            edges = np.linspace(0.0, 1.0, max(1, int(round(1.0 / float(bin_width)))) + 1, dtype=np.float32)
+        else:
+            edges = np.linspace(0.0, 1.0, (int(num_bins) if num_bins is not None else 10) + 1, dtype=np.float32)
+        edges[0] = 0.0
+        edges[-1] = 1.0
+        assert np.all(np.diff(edges) > 0), "bin edges must be strictly increasing"
+        return edges
+
+    def binned_accuracy(self, num_bins: int = 10, bin_width: float | None = None, bin_edges=None) -> pd.DataFrame:
+        if self._hist is None or self._seen == 0:
+            return pd.DataFrame(columns=["low", "high", "label", "n", "pct", "accuracy"])
+        h = self._hist.cpu().numpy()
+        edges = self.make_bins(num_bins=num_bins, bin_width=bin_width, bin_edges=bin_edges)
+        M = h.shape[1]
+        starts = np.arange(M, dtype=np.float64) / M                       # lower edge of every fine bin
+        coarse = np.searchsorted(edges.astype(np.float64), starts + 0.5 / M, side="right") - 1
+        coarse = np.clip(coarse, 0, len(edges) - 2)
+        n = np.bincount(coarse, weights=(h[0] + h[1]).astype(np.float64), minlength=len(edges) - 1)
+        c = np.bincount(coarse, weights=h[0].astype(np.float64), minlength=len(edges) - 1)
+        acc = np.divide(c, n, out=np.full_like(c, np.nan, dtype=float), where=n > 0)
+        lows, highs = edges[:-1], edges[1:]
+        labels = [f"[{l:.2f}, {hh:.2f})" if i < len(lows) - 1 else f"[{l:.2f}, {hh:.2f}]" for i, (l, hh) in enumerate(zip(lows, highs))]
+        return pd.DataFrame({"low": lows, "high": highs, "label": labels, "n": n.astype(int),
+                             "pct": 100.0 * n / max(1.0, n.sum()), "accuracy": acc})

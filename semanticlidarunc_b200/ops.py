@@ -197,6 +197,31 @@ def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch
     _lib.check(rc, "slu_confusion_ece")
 
 
+SCORE_BINS = 60000          # divisible by 10, 15, 20, 50, 100: the usual coarse binnings fall on fine edges
+
+
+def new_score_hist(device, n_score_bins: int = SCORE_BINS) -> torch.Tensor:
+    """[2, n_score_bins] int64: row 0 correct pixels, row 1 wrong pixels, per score bin."""
+    return torch.zeros((2, n_score_bins), dtype=torch.int64, device=device)
+
+
+def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, ignore=()) -> None:
+    """Accumulate (score, pred != label) pairs into `hist` (slu_score_hist)."""
+    _lib.require_cuda()
+    score = _lib.as_buffer(score, torch.float32, "score").reshape(-1)
+    pred = _lib.as_buffer(pred, torch.int64, "pred").reshape(-1)
+    labels = _lib.as_buffer(labels, torch.int64, "labels").reshape(-1)
+    if not (score.numel() == pred.numel() == labels.numel()):
+        raise ValueError("score, pred and labels differ in size")
+    if hist.dtype != torch.int64 or not hist.is_contiguous() or hist.dim() != 2 or hist.size(0) != 2:
+        raise ValueError("hist must be a contiguous [2,M] int64 tensor")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    rc = _lib.lib().slu_score_hist(_lib.ptr(score), _lib.ptr(pred), _lib.ptr(labels), score.numel(), hist.size(1),
+                                   h_ign, len(ign), _lib.ptr(hist), _lib.stream_ptr())
+    _lib.check(rc, "slu_score_hist")
+
+
 def _offsets_array(offsets):
     off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
     return off, off.ctypes.data_as(_lib.C.c_void_p)

@@ -86,3 +86,42 @@ def test_coherent_labels_same_counts(cuda):
     ops.confusion_ece(pred.to(cuda), lab.to(cuda), None, num_classes=C, confmat=confmat)
     assert torch.equal(confmat.cpu(), om.confusion_counts(pred, lab, C))
     assert int(confmat.sum()) == lab.numel()
+
+
+def test_auroc_aggregator_vs_reference_golden(cuda, golden):
+    """Histogram AUROC (60000 score bins) vs the reference's sort-based value on every pixel: 1e-4."""
+    from semanticlidarunc_b200.metrics.auroc import AUROCAggregator
+    g = golden("metrics.npz")
+    x, lab = torch.from_numpy(g["auroc/probs"]), torch.from_numpy(g["auroc/labels"])
+    for score in ("entropy_norm", "entropy", "1-maxprob"):
+        a = AUROCAggregator(mode="probs", score=score, ignore_index=0, max_samples=None)
+        a.update(x[:1], lab[:1])
+        a.update(x[1:].to(cuda), lab[1:].to(cuda))
+        auroc, curves, fig = a.compute()
+        ref = float(g[f"auroc/probs_{score}"])
+        assert abs(auroc - ref) < 1e-4, (score, auroc, ref)
+        assert curves["fpr"][0] == 0.0 and curves["tpr"][-1] == 1.0
+    a = AUROCAggregator(mode="probs", score="mi_norm", ignore_index=0)
+    a.update(x.to(cuda), lab.to(cuda), score_override=torch.from_numpy(g["auroc/override"]).to(cuda))
+    assert abs(a.compute()[0] - float(g["auroc/probs_override"])) < 1e-4
+    alpha = torch.from_numpy(g["auroc/alpha"]).to(cuda)
+    for score in ("mi_norm", "entropy_norm"):
+        a = AUROCAggregator(mode="alpha", score=score, ignore_index=0)
+        a.update(alpha, lab.to(cuda))
+        assert abs(a.compute()[0] - float(g[f"auroc/alpha_{score}"])) < 1e-4, score
+    assert a._seen == int((lab != 0).sum())
+    e = AUROCAggregator(mode="probs")
+    assert np.isnan(e.compute()[0])
+
+
+def test_uncertainty_accuracy_aggregator_vs_reference_golden(cuda, golden):
+    from semanticlidarunc_b200.models.evaluator import UncertaintyAccuracyAggregator
+    g = golden("metrics.npz")
+    x, lab = torch.from_numpy(g["auroc/probs"]), torch.from_numpy(g["auroc/labels"])
+    ua = UncertaintyAccuracyAggregator(max_samples=None)
+    ua.update(labels=lab.to(cuda), preds=x.argmax(1).to(cuda), uncertainty=torch.from_numpy(g["auroc/override"]).to(cuda), ignore_ids=(0,))
+    for nb in (10, 20):
+        df = ua.binned_accuracy(num_bins=nb)
+        assert np.array_equal(df["n"].to_numpy(), g[f"ua/n_{nb}"])                 # 10 and 20 divide 60000: exact
+        assert np.allclose(df["accuracy"].to_numpy(), g[f"ua/acc_{nb}"], rtol=1e-6, equal_nan=True)
+    assert list(df.columns) == ["low", "high", "label", "n", "pct", "accuracy"]

@@ -172,3 +172,19 @@ def test_kitti_item_oracle_vs_golden(golden):
     r = oproj.kitti_item(g["xyzi"], g["raw"], lut, projection=(16, 256), resize=False, flip=True, yaw_deg=float(g["aug/angle"]))
     for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
         assert np.array_equal(a, g["aug/" + k]), k
+
+
+def test_auroc_and_binned_accuracy_oracle_vs_golden(golden):
+    g = golden("metrics.npz")
+    x, lab = torch.from_numpy(g["auroc/probs"]), torch.from_numpy(g["auroc/labels"])
+    valid = (lab != 0).numpy().reshape(-1)
+    p = om.to_probs(x, "probs")
+    pred = p.argmax(1)
+    err = (pred != lab).numpy().reshape(-1)[valid]
+    H = (-(p.clamp_min(1e-12) * p.clamp_min(1e-12).log()).sum(1) / np.log(20)).numpy().reshape(-1)[valid]
+    assert abs(om.auroc_error_detection(H, err) - float(g["auroc/probs_entropy_norm"])) < 1e-12
+    ov = g["auroc/override"].reshape(-1)[valid]
+    assert abs(om.auroc_error_detection(ov, err) - float(g["auroc/probs_override"])) < 1e-12
+    for nb in (10, 20):
+        n, acc = om.binned_accuracy(ov, ~err, nb)
+        assert np.array_equal(n, g[f"ua/n_{nb}"]) and np.allclose(acc, g[f"ua/acc_{nb}"], equal_nan=True)
