@@ -31,18 +31,34 @@ def mc_mutual_information_norm(probs: torch.Tensor, eps: float = 1e-12) -> torch
 
 @torch.no_grad()
 def mc_reduce_from_logits(mc_logits: torch.Tensor, labels: torch.Tensor | None = None, *, eps: float = 1e-12,
-                          ignore_index=None, iou_evaluator=None, ece_eval=None,
-                          want=("pred", "conf", "H_norm", "MI_norm")) -> dict:
+                          ignore_index=None, iou_evaluator=None, ece_eval=None, auroc_eval=None, auroc_eval_mi=None,
+                          ua_agg=None, ua_ignore_ids=(0,), want=("pred", "conf", "H_norm", "MI_norm")) -> dict:
     """The whole MC block of Tester.test_epoch (tester.py:412-471) in one pass over the logits.
 
     mc_logits [T,B,C,H,W] straight from `mc_forward`; returns pred / conf / H_norm / MI_norm (and
     p_bar if asked) and, when given, updates `iou_evaluator` (models.evaluator.IoUEvaluator) and
-    `ece_eval` (metrics.ece.ECEAggregator, mode 'probs' semantics) in the same kernel.
+    `ece_eval` (metrics.ece.ECEAggregator, mode 'probs' semantics) in the same kernel, then
+    `auroc_eval` (entropy score, :468), `auroc_eval_mi` (MI score override, :470-471) and `ua_agg`
+    (accuracy vs H_norm, :460-464) from the small per-pixel maps -- p_bar is never materialised.
     """
     confmat = iou_evaluator._accumulator(mc_logits.device) if iou_evaluator is not None else None
     bins = ece_eval._accumulator(mc_logits.device) if ece_eval is not None else None
     edges = ece_eval._edges if ece_eval is not None else None
     if ece_eval is not None and ignore_index is None:
         ignore_index = ece_eval.ignore_index
-    return ops.reduce_metrics(mc_logits, labels, kind="logits", conf_mode=ops.CONF_RENORM, eps=eps,
-                              ignore_index=ignore_index, edges=edges, confmat=confmat, ece_bins=bins, want=want)
+    need = set(want)
+    if auroc_eval is not None or ua_agg is not None:
+        need |= {"pred", "H_norm"}
+    if auroc_eval_mi is not None:
+        need |= {"pred", "MI_norm"}
+    out = ops.reduce_metrics(mc_logits, labels, kind="logits", conf_mode=ops.CONF_RENORM, eps=eps,
+                             ignore_index=ignore_index, edges=edges, confmat=confmat, ece_bins=bins, want=tuple(need))
+    if labels is not None:
+        lab = labels[:, 0] if labels.dim() == 4 else labels
+        if auroc_eval is not None:
+            auroc_eval.add_maps(out["H_norm"], out["pred"], lab)
+        if auroc_eval_mi is not None:
+            auroc_eval_mi.add_maps(out["MI_norm"], out["pred"], lab)
+        if ua_agg is not None:
+            ua_agg.update(labels=lab, preds=out["pred"], uncertainty=out["H_norm"], ignore_ids=ua_ignore_ids)
+    return out

@@ -125,3 +125,27 @@ def test_uncertainty_accuracy_aggregator_vs_reference_golden(cuda, golden):
         assert np.array_equal(df["n"].to_numpy(), g[f"ua/n_{nb}"])                 # 10 and 20 divide 60000: exact
         assert np.allclose(df["accuracy"].to_numpy(), g[f"ua/acc_{nb}"], rtol=1e-6, equal_nan=True)
     assert list(df.columns) == ["low", "high", "label", "n", "pct", "accuracy"]
+
+
+def test_whole_mc_block_updates_every_aggregator(cuda):
+    """mc_reduce_from_logits == the reference tester's MC block: IoU, ECE, both AUROCs and the UA bins."""
+    from oracle import uncertainty as ou
+    from semanticlidarunc_b200 import synth
+    from semanticlidarunc_b200.metrics.auroc import AUROCAggregator
+    from semanticlidarunc_b200.models.evaluator import UncertaintyAccuracyAggregator
+    from semanticlidarunc_b200.utils.mc_dropout import mc_reduce_from_logits
+    C = 20
+    x, lab = synth.synth_mc_logits(21, 6, 2, C, 16, 256)
+    iou, ece = IoUEvaluator(C), ECEAggregator(n_bins=15, mode="probs", ignore_index=0)
+    au, au_mi = AUROCAggregator(mode="probs", score="entropy_norm", ignore_index=0), AUROCAggregator(mode="probs", score="mi_norm", ignore_index=0)
+    ua = UncertaintyAccuracyAggregator()
+    out = mc_reduce_from_logits(x.to(cuda), lab.to(cuda), iou_evaluator=iou, ece_eval=ece, auroc_eval=au, auroc_eval_mi=au_mi, ua_agg=ua)
+    ref = ou.mc_reduce(x)
+    valid = (lab != 0).numpy().reshape(-1)
+    err = (ref["pred"] != lab).numpy().reshape(-1)[valid]
+    assert abs(au.compute()[0] - om.auroc_error_detection(ref["H_norm"].numpy().reshape(-1)[valid], err)) < 2e-4
+    assert abs(au_mi.compute()[0] - om.auroc_error_detection(ref["MI_norm"].numpy().reshape(-1)[valid], err)) < 2e-4
+    n, acc = om.binned_accuracy(ref["H_norm"].numpy().reshape(-1)[valid].clip(0, 1), ~err, 10)
+    df = ua.binned_accuracy(num_bins=10)
+    assert abs(df["n"].to_numpy() - n).sum() <= 4          # a pixel within 1e-6 of a coarse edge may move
+    assert int(iou.confmat.sum()) == lab.numel() and ece._seen == int(valid.sum())
