@@ -13,8 +13,10 @@
 //   probability_helper: alpha0 = sum(alpha) + eps, H = -sum p log(p + eps)          (eps = 1e-8)
 //   AUROC MI          : a0 = sum(alpha) + e, p = alpha/a0, clamp(p, e) inside the log (e = 1e-12)
 //   ECE 'alpha'       : p = alpha / (sum(alpha) + e), conf = max p                  (e = 1e-12)
-// Bound: the per-class digamma (recurrence + log + series, ~55 instructions) makes this kernel
-// instruction-bound rather than HBM-bound at C=20: ~1300 instructions for 108 B per pixel.
+// Bound: the per-class digamma (4-step recurrence as one rational, logf, 5-term series: ~50 instructions)
+// makes this kernel instruction-bound rather than HBM-bound at C=20.  Softmax uses ex2.approx and one
+// reciprocal, the entropies lg2.approx, like the MC kernel; digamma keeps the accurate logf because AU and
+// EU are differences of O(ln alpha0) terms.
 #include <math.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
@@ -22,6 +24,12 @@
 namespace slu {
 
 constexpr int EV_THREADS = 256;
+
+__device__ __forceinline__ float lg2_fast(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 struct EvParams {
     const float* outputs;      // [B,C+1,HW] shape logits + scale logit, or NULL
@@ -80,12 +88,14 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
 #pragma unroll
             for (int c = 1; c < CP; ++c) m = fmaxf(m, z[c]);
             float S = 0.f;
+            const float m2 = m * 1.4426950408889634f;
 #pragma unroll
-            for (int c = 0; c < CP; ++c) { z[c] = expf(z[c] - m); S += z[c]; }
+            for (int c = 0; c < CP; ++c) { z[c] = ex2_approx(fmaf(z[c], 1.4426950408889634f, -m2)); S += z[c]; }
+            const float invS = __frcp_rn(S);
             float best = -1.f;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                const float pc = __fdiv_rn(z[c], S);
+                const float pc = z[c] * invS;
                 if (c < p.C && pc > best) { best = pc; pred = c; }          // tester.py:493-495
                 a[c] = __fadd_rn(__fadd_rn(1.0f, __fmul_rn(scale, pc)), p.eps);   // probability_helper.py:104
             }
@@ -113,21 +123,25 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
         if (want_unc) {                                    // warp-uniform
             const float psi0 = digamma_pos(a0 + 1.0f);
             const float psi0m = digamma_pos(a0m + 1.0f);
+            const float inv0 = __frcp_rn(a0), inv0m = __frcp_rn(a0m);
+            float H2 = 0.f, Hm2 = 0.f;                     // entropies in log2 units (lg2.approx, rel. error <= 2^-22)
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 if (c < p.C) {
-                    const float ph = __fdiv_rn(a[c], a0);
+                    const float ph = a[c] * inv0;
                     const float psi = digamma_pos(a[c] + 1.0f);
-                    H = fmaf(-ph, logf(ph + p.eps), H);                      // :121
+                    H2 = fmaf(-ph, lg2_fast(ph + p.eps), H2);                // :121
                     AU = fmaf(-ph, psi - psi0, AU);                          // :128-130
                     if (p.mi) {
-                        const float pm = __fdiv_rn(a[c], a0m);
+                        const float pm = a[c] * inv0m;
                         const float pmc = fmaxf(pm, p.eps_m);
-                        Hm = fmaf(-pmc, logf(pmc), Hm);                      // auroc.py:59
+                        Hm2 = fmaf(-pmc, lg2_fast(pmc), Hm2);                // auroc.py:59
                         EHm = fmaf(-pm, psi - psi0m, EHm);                   // auroc.py:60-61
                     }
                 }
             }
+            H = H2 * 0.6931471805599453f;
+            Hm = Hm2 * 0.6931471805599453f;
         }
         const float conf = __fdiv_rn(amax, asum + p.eps_m);                  // ece.py:57-58,75
         if (live) {

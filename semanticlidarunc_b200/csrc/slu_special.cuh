@@ -14,9 +14,15 @@ namespace slu {
 __device__ __forceinline__ float digamma_pos(float x) {
     float r = 0.f;
 #pragma unroll 1
-    while (x < 6.f) {
+    while (x < 2.f) {                 // rare in this code base: arguments are alpha + 1 >= 2
         r -= __frcp_rn(x);
         x += 1.f;
+    }
+    if (x < 6.f) {
+        // four recurrence steps at once: 1/x + 1/(x+1) + 1/(x+2) + 1/(x+3) = (2x+3)(2u+2) / (u(u+2)), u = x(x+3)
+        const float u = x * (x + 3.f);
+        r -= __fdividef(fmaf(2.f, x, 3.f) * fmaf(2.f, u, 2.f), u * (u + 2.f));
+        x += 4.f;
     }
     const float inv = __frcp_rn(x);
     const float z = inv * inv;
