@@ -99,6 +99,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from semanticlidarunc_b200.dist import bind_to_gpu_numa_node
+    local_cpus = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -183,7 +185,8 @@ def run_ours(args):
         e2e_ms = float(tmax.item())
     e2e = {"value": round(world * B * e2e_steps / (e2e_ms / 1e3), 2), "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": round(e2e_ms / e2e_steps, 3),
-           "api": "ScanEvaluator.step_host (pinned host buffers, one scan per chunk, copy/compute overlap)"}
+           "api": "ScanEvaluator.step_host (pinned host buffers, one scan per chunk, copy/compute overlap)",
+           "cpus_local_to_gpu": local_cpus}
 
     finish(args, world, rank, ms, value, launches, clk, e2e, roofline, summ, offs)
 
@@ -202,6 +205,10 @@ def finish(args, world, rank, ms, value, launches, clk, e2e, roofline, summ, off
         "result_check": {"mIoU": summ["mIoU"], "ece": summ["ece"], "confmat_sum": int(summ["confmat"].sum())},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))      # the CPU baseline may use every host core
+        except Exception:
+            pass
         line["cpu_baseline"] = cpu_baseline(sample_scans=args.cpu_scans, budget_s=20.0)
     if rank == 0:
         print(json.dumps(line))
@@ -229,7 +236,7 @@ def cpu_baseline(sample_scans: int, budget_s: float):
     from semanticlidarunc_b200 import synth
     from semanticlidarunc_b200.dataset.definitions import build_id_lut
     from oracle import metrics as om
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     lut = build_id_lut()
     g = torch.Generator().manual_seed(99)
