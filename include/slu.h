@@ -142,6 +142,21 @@ int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target, const uint
                        float eps_mse, float eps_kl, int want_mse, int want_kl,
                        double* d_sums, float* d_grad_mse, float* d_grad_kl, slu_stream_t stream);
 
+/* Fused training-step loss from the head output (SURVEY.md 8d "L", 176 B/px): alpha = 1 + softplus(l/T) *
+ * softmax(z) + eps_alpha, loss = w_mse * MSE + w_kl * KL, and d(loss)/d(head output) with the mean over valid
+ * pixels already applied.  Replaces src/models/trainer.py:532-578 plus autograd's backward through the
+ * alpha transform.  C >= 3 (the reference's MSE term is defined as 0 for C <= 2).
+ *   d_outputs [B,C+1,HW];  d_sums [3] float64 must be ZERO on entry: sum mse | sum kl | n_valid on exit;
+ *   loss = (w_mse*sums[0] + w_kl*sums[1]) / max(sums[2],1);  d_grad_outputs [B,C+1,HW] or NULL.
+ */
+int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
+                              int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                              float temperature, float eps_alpha, float eps_mse, float eps_kl,
+                              float w_mse, float w_kl, double* d_sums, float* d_grad_outputs, slu_stream_t stream);
+
+/* Diagnostic: d_out[3i..3i+2] = lgamma, digamma, trigamma of d_in[i] (> 0) as the loss kernels evaluate them. */
+int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 4 standalone: histograms from already-reduced maps (integer inputs).
  * Replaces: IoUEvaluator.update (src/models/evaluator.py:39-53) and the binning of

@@ -33,6 +33,8 @@ SIGNATURES = {
     "slu_evidential_reduce": (_i, [_p, _p, _p, _i, _i, _i64, _f, _f, _f, _i, _i, _i64, _i, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "slu_dirichlet_loss": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p]),
+    "slu_evidential_loss_fused": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p]),
+    "slu_diag_special": (_i, [_p, _i64, _p, _p]),
     "slu_confusion_ece": (_i, [_p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
     "slu_score_hist": (_i, [_p, _p, _p, _i64, _i, _p, _i, _p, _p]),
     "slu_project_workspace_bytes": (_i64, [_i64, _i, _i64]),

@@ -120,19 +120,19 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
 #pragma unroll
             for (int c = 0; c < CP; ++c)
                 if (c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
-            const float psi_s = digamma_pos(s);
-            float kl = lgammaf(s);
-            float tail = 0.f;
-            if (gk) tail = (s - (float)p.C) * trigamma_pos(s);
+            const LDT fs = ldt_pos(s);
+            float kl = fs.lg;
+            const float tail = (s - (float)p.C) * fs.tri;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 if (c < p.C) {
                     float gj = 0.f;
                     if (c != y) {
                         const float ac = fmaxf(a[c], p.eps_kl);
-                        kl -= lgammaf(ac);
-                        kl = fmaf(ac - 1.0f, digamma_pos(ac) - psi_s, kl);
-                        if (gk && a[c] > p.eps_kl) gj = fmaf(ac - 1.0f, trigamma_pos(ac), -tail);
+                        const LDT f = ldt_pos(ac);
+                        kl -= f.lg;
+                        kl = fmaf(ac - 1.0f, f.psi - fs.psi, kl);
+                        if (a[c] > p.eps_kl) gj = fmaf(ac - 1.0f, f.tri, -tail);
                     }
                     if (gk) gk[(long long)c * p.HW] = gj;
                 }
@@ -171,7 +171,226 @@ static int launch_loss(const LossParams& p, cudaStream_t st) {
     return 0;
 }
 
+
+// =====================================================================================================
+// Fused training-step loss: head output -> alpha -> w_mse * MSE + w_kl * KL and d(loss)/d(head output),
+// one read of [B,C+1,HW] + target, one write of the gradient (176 B/px, SURVEY.md 8d "L").
+// Replaces the trainer's chain src/models/trainer.py:532-578 (split shape/scale logits,
+// to_alpha_concentrations_from_shape_and_scale, the two loss modules, the weighted sum) and autograd's
+// backward through softplus / softmax.  With p = softmax(z), s = softplus(l/T), alpha = 1 + s p + eps and
+// g = d(loss)/d(alpha):   dL/dz_j = s p_j (g_j - sum_c g_c p_c),   dL/dl = (sum_c g_c p_c) sigmoid(l/T) / T.
+// The mean over valid pixels needs n_valid first: a count kernel (8 B/px) runs before the main kernel,
+// which reads the count from device memory, so the written gradient is final (already divided by n_valid).
+// =====================================================================================================
+struct FusedParams {
+    const float* outputs;          // [B,C+1,HW]
+    const long long* target;
+    const unsigned char* keep;
+    int B, C;
+    long long HW, n_px;
+    long long ignore[MAX_IGNORE];
+    int n_ignore;
+    float inv_temp, eps_alpha, eps_mse, eps_kl, w_mse, w_kl;
+    double* sums;                  // [3] sum mse | sum kl | n_valid   (n_valid written by the count kernel)
+    float* grad;                   // [B,C+1,HW] or NULL
+};
+
+__device__ __forceinline__ bool px_valid(const FusedParams& p, long long g, long long tgt) {
+    if (p.keep) return p.keep[g] != 0;
+    bool v = true;
+#pragma unroll
+    for (int i = 0; i < MAX_IGNORE; ++i)
+        if (i < p.n_ignore && tgt == p.ignore[i]) v = false;
+    return v;
+}
+
+__global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_constant__ FusedParams p) {
+    unsigned n = 0;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_px; g += (long long)gridDim.x * blockDim.x)
+        n += px_valid(p, g, p.target[g]) ? 1u : 0u;
+    n = __reduce_add_sync(0xffffffffu, n);
+    __shared__ unsigned s_n[LOSS_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_n[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) t += s_n[i];
+        if (t) atomicAdd(&p.sums[2], (double)t);
+    }
+}
+
+template <int CP>
+__global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(const __grid_constant__ FusedParams p) {
+    const int tid = threadIdx.x;
+    const float inv_n = (float)(1.0 / fmax(p.sums[2], 1.0));
+    double acc_mse = 0.0, acc_kl = 0.0;
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long g = ch * LOSS_THREADS + tid;
+        if (g >= p.n_px) continue;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const long long tgt = p.target[g];
+        const float* base = p.outputs + ((long long)b * (p.C + 1)) * p.HW + px;
+        float* go = p.grad ? p.grad + ((long long)b * (p.C + 1)) * p.HW + px : nullptr;
+        if (!px_valid(p, g, tgt)) {
+            if (go) for (int c = 0; c <= p.C; ++c) go[(long long)c * p.HW] = 0.f;
+            continue;
+        }
+        const int y = (int)tgt;
+        float pr[CP], a[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) pr[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : -1.0e30f;
+        const float sl = ldg_stream(base + (long long)p.C * p.HW) * p.inv_temp;
+        const float scale = sl > 20.f ? sl : log1pf(expf(sl));
+        const float dscale = sl > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl));       // d softplus
+        float m = pr[0];
+#pragma unroll
+        for (int c = 1; c < CP; ++c) m = fmaxf(m, pr[c]);
+        const float m2 = m * 1.4426950408889634f;
+        float S = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { pr[c] = ex2_approx(fmaf(pr[c], 1.4426950408889634f, -m2)); S += pr[c]; }
+        const float invS = __frcp_rn(S);
+        float a0 = 0.f, s2 = 0.f, ay = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            pr[c] *= invS;
+            a[c] = (c < p.C) ? __fadd_rn(__fadd_rn(1.0f, __fmul_rn(scale, pr[c])), p.eps_alpha) : 0.f;
+            a0 += a[c];
+            s2 = fmaf(a[c], a[c], s2);
+            if (c == y) ay = a[c];
+        }
+        // ---- MSE term (same algebra as dirichlet_loss_kernel)
+        const float D = a0 + p.eps_mse, invD = 1.0f / D;
+        const float G = (a0 * a0 + p.eps_mse) * (a0 + 1.0f), invG = 1.0f / G;
+        float sq = 0.f, sp2 = 0.f, var = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (c < p.C) {
+                const float pc = a[c] * invD;
+                const float d = (c == y ? 1.0f : 0.0f) - pc;
+                sq = fmaf(d, d, sq);
+                sp2 = fmaf(pc, pc, sp2);
+                var = fmaf(a[c] * (a0 - a[c]), invG, var);
+            }
+        }
+        acc_mse += (double)(sq + var);
+        const float N = a0 * a0 - s2;
+        const float Gp = 2.0f * a0 * (a0 + 1.0f) + (a0 * a0 + p.eps_mse);
+        const float common = 2.0f * (ay * invD - sp2) * invD + 2.0f * a0 * invG - N * Gp * invG * invG;
+        // ---- KL term
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+            if (c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
+        const LDT fs = ldt_pos(s);
+        float kl = fs.lg;
+        const float tail = (s - (float)p.C) * fs.tri;
+        float gp_sum = 0.f;                      // sum_c g_c p_c
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (c < p.C) {
+                const float pc = a[c] * invD;
+                float gc = p.w_mse * fmaf(-2.0f * ((c == y ? 1.0f : 0.0f) - pc), invD, fmaf(-2.0f * a[c], invG, common));
+                if (c != y) {
+                    const float ac = fmaxf(a[c], p.eps_kl);
+                    const LDT f = ldt_pos(ac);
+                    kl -= f.lg;
+                    kl = fmaf(ac - 1.0f, f.psi - fs.psi, kl);
+                    if (a[c] > p.eps_kl) gc = fmaf(p.w_kl, fmaf(ac - 1.0f, f.tri, -tail), gc);
+                }
+                a[c] = gc * inv_n;               // a[] now holds d(loss)/d(alpha_c)
+                gp_sum = fmaf(a[c], pr[c], gp_sum);
+            }
+        }
+        acc_kl += (double)kl;
+        if (go) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < p.C) go[(long long)c * p.HW] = scale * pr[c] * (a[c] - gp_sum);
+            go[(long long)p.C * p.HW] = gp_sum * dscale * p.inv_temp;
+        }
+    }
+    __shared__ double s_m[LOSS_THREADS / 32], s_k[LOSS_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
+        acc_kl += __shfl_xor_sync(0xffffffffu, acc_kl, o);
+    }
+    if ((tid & 31) == 0) { s_m[tid >> 5] = acc_mse; s_k[tid >> 5] = acc_kl; }
+    __syncthreads();
+    if (tid == 0) {
+        double mm = 0.0, kk = 0.0;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) { mm += s_m[i]; kk += s_k[i]; }
+        atomicAdd(&p.sums[0], mm);
+        atomicAdd(&p.sums[1], kk);
+    }
+}
+
+template <int CP>
+static int launch_fused(const FusedParams& p, cudaStream_t st) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    const long long cap = 6LL * sms;
+    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("count_valid_kernel");
+    evidential_loss_fused_kernel<CP><<<grid, LOSS_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("evidential_loss_fused_kernel");
+    return 0;
+}
+
+// diagnostic: out[3i..3i+2] = lgamma, digamma, trigamma of in[i] through ldt_pos (accuracy tests)
+__global__ void special_eval_kernel(const float* in, long long n, float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const LDT r = ldt_pos(in[i]);
+        out[3 * i] = r.lg; out[3 * i + 1] = r.psi; out[3 * i + 2] = r.tri;
+    }
+}
+
 }  // namespace slu
+extern "C" int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_in || !d_out || n < 1) return fail(SLU_E_ARG, "slu_diag_special: bad arguments");
+    special_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_in, n, d_out);
+    SLU_LAUNCH_CHECK("special_eval_kernel");
+    return 0;
+}
+
+extern "C" int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
+                                         int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                                         float temperature, float eps_alpha, float eps_mse, float eps_kl,
+                                         float w_mse, float w_kl, double* d_sums, float* d_grad_outputs,
+                                         slu_stream_t stream) {
+    using namespace slu;
+    if (!d_outputs || !d_target || !d_sums) return fail(SLU_E_ARG, "d_outputs / d_target / d_sums is NULL");
+    if (B < 1 || HW < 1) return fail(SLU_E_ARG, "B=%d HW=%lld must be >= 1", B, (long long)HW);
+    if (C < 3 || C > SLU_MAX_CLASSES) return fail(SLU_E_RANGE, "C=%d outside [3,%d]", C, SLU_MAX_CLASSES);
+    if (n_ignore < 0 || n_ignore > MAX_IGNORE || (n_ignore > 0 && !h_ignore)) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,%d]", n_ignore, MAX_IGNORE);
+    if (!(temperature > 0.f)) return fail(SLU_E_ARG, "temperature must be > 0");
+    FusedParams p{};
+    p.outputs = d_outputs; p.target = reinterpret_cast<const long long*>(d_target); p.keep = d_keep_mask;
+    p.B = B; p.C = C; p.HW = HW; p.n_px = (long long)B * HW;
+    for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
+    p.n_ignore = n_ignore;
+    p.inv_temp = 1.0f / temperature; p.eps_alpha = eps_alpha; p.eps_mse = eps_mse; p.eps_kl = eps_kl;
+    p.w_mse = w_mse; p.w_kl = w_kl;
+    p.sums = d_sums; p.grad = d_grad_outputs;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch ((C + 3) / 4 * 4) {
+        case 4: return launch_fused<4>(p, st);
+        case 8: return launch_fused<8>(p, st);
+        case 12: return launch_fused<12>(p, st);
+        case 16: return launch_fused<16>(p, st);
+        case 20: return launch_fused<20>(p, st);
+        case 24: return launch_fused<24>(p, st);
+        case 28: return launch_fused<28>(p, st);
+        default: return launch_fused<32>(p, st);
+    }
+}
 
 extern "C" int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
                                   int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,

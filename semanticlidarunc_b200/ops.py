@@ -173,6 +173,44 @@ def dirichlet_loss(alpha: torch.Tensor, target: torch.Tensor, *, ignore=(), keep
     return {"sums": sums, "grad_mse": g_mse, "grad_kl": g_kl}
 
 
+def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse: float = 1.0, w_kl: float = 0.05,
+                          ignore=(), keep_mask: Optional[torch.Tensor] = None, temperature: float = 1.0,
+                          eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True) -> dict:
+    """Head output [B,C+1,H,W] -> sums float64[3] (sum mse | sum kl | n_valid) and d(loss)/d(outputs)
+    (slu_evidential_loss_fused); loss = (w_mse*sums[0] + w_kl*sums[1]) / max(sums[2], 1)."""
+    _lib.require_cuda()
+    outputs = _lib.as_buffer(outputs, torch.float32, "outputs")
+    if outputs.dim() != 4:
+        raise ValueError("outputs must be [B,C+1,H,W]")
+    B, C1, H, W = outputs.shape
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    if tuple(target.shape) != (B, H, W):
+        raise ValueError(f"target shape {tuple(target.shape)} != {(B, H, W)}")
+    target = _lib.as_buffer(target.to(outputs.device), torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask.to(outputs.device), torch.bool, "keep_mask")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    sums = torch.zeros(3, dtype=torch.float64, device=outputs.device)
+    grad = torch.empty_like(outputs) if want_grad else None
+    rc = _lib.lib().slu_evidential_loss_fused(_lib.ptr(outputs), _lib.ptr(target), _lib.ptr(keep_mask), B, C1 - 1, H * W,
+                                              h_ign, len(ign), float(temperature), float(eps_alpha), float(eps_mse),
+                                              float(eps_kl), float(w_mse), float(w_kl), _lib.ptr(sums), _lib.ptr(grad),
+                                              _lib.stream_ptr())
+    _lib.check(rc, "slu_evidential_loss_fused")
+    return {"sums": sums, "grad": grad}
+
+
+def special_functions(x: torch.Tensor) -> torch.Tensor:
+    """[n,3] = lgamma, digamma, trigamma of x > 0 as the loss kernels evaluate them (slu_diag_special)."""
+    _lib.require_cuda()
+    x = _lib.as_buffer(x, torch.float32, "x").reshape(-1)
+    out = torch.empty((x.numel(), 3), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().slu_diag_special(_lib.ptr(x), x.numel(), _lib.ptr(out), _lib.stream_ptr()), "slu_diag_special")
+    return out
+
+
 def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None, *,
                   num_classes: int, ignore_index: Optional[int] = None, edges=None,
                   confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None) -> None:

@@ -69,3 +69,46 @@ def test_two_class_mse_is_zero_like_reference(cuda):
     alpha = (torch.rand((1, 2, 4, 32)) + 1.0).to(cuda).requires_grad_(True)
     target = torch.randint(0, 2, (1, 4, 32), device=cuda)
     assert float(DirichletMSELoss()(alpha, target)) == 0.0
+
+
+def test_special_functions_over_alpha_range(cuda):
+    """lgamma / digamma / trigamma as the LOSS kernels evaluate them, 1e-8 .. 1e4.  psi' (the only one the
+    gradients use) is held to 1e-5 relative; lgamma and psi enter the KL value only, next to the constant
+    lgamma(C) ~ 39, and are held to 1e-5 * max(1, |f|) (fast log2; zeros of lgamma at 1 and 2).  The
+    evaluation kernels use the accurate digamma of slu_special.cuh (tests/test_gpu_evidential.py)."""
+    import scipy.special as sp
+    from semanticlidarunc_b200 import ops
+    x = torch.cat([torch.logspace(-8, 4, 4000, dtype=torch.float64), torch.linspace(1.0, 1.3, 2000, dtype=torch.float64),
+                   torch.linspace(0.9, 8.0, 3000, dtype=torch.float64)]).float()
+    got = ops.special_functions(x.to(cuda)).cpu().double().numpy()
+    xd = x.double().numpy()
+    lg, ps, tr = sp.gammaln(xd), sp.digamma(xd), sp.polygamma(1, xd)
+    assert np.all(np.abs(got[:, 0] - lg) <= 1e-5 * np.maximum(1.0, np.abs(lg))), np.abs(got[:, 0] - lg).max()
+    assert np.all(np.abs(got[:, 1] - ps) <= 1e-5 * np.maximum(1.0, np.abs(ps))), np.abs(got[:, 1] - ps).max()
+    assert np.all(np.abs(got[:, 2] - tr) <= 1e-5 * np.abs(tr)), (np.abs(got[:, 2] - tr) / tr).max()
+
+
+@pytest.mark.parametrize("ignore", [None, 0, (0, 5)])
+@pytest.mark.parametrize("shape", [(2, 20, 8, 128), (1, 7, 5, 33)])
+def test_fused_loss_from_head_outputs_vs_oracle_chain(cuda, shape, ignore):
+    """outputs -> alpha -> w_mse*MSE + w_kl*KL and its gradient w.r.t. the head output, against the
+    reference chain evaluated in float64 with autograd."""
+    from oracle import uncertainty as ou
+    from semanticlidarunc_b200.losses.evidential import EvidentialLoss
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(C)
+    out = torch.randn((B, C + 1, H, W), generator=gen) * 3.0
+    target = torch.randint(0, C, (B, H, W), generator=gen)
+    o_ref = out.clone().double().requires_grad_(True)
+    alpha = ou.to_alpha_concentrations_from_shape_and_scale(o_ref[:, :C], o_ref[:, C:C + 1])
+    mse_ref, kl_ref = ol.dirichlet_mse(alpha, target, ignore_index=ignore), ol.kl_offclasses_to_uniform(alpha, target, ignore_index=ignore)
+    l_ref = 1.0 * mse_ref + 0.05 * kl_ref
+    (g_ref,) = torch.autograd.grad(l_ref, o_ref)
+    o = out.clone().to(cuda).requires_grad_(True)
+    loss, mse, kl = EvidentialLoss(1.0, 0.05, ignore_index=ignore)(o, target.to(cuda))
+    loss.backward()
+    for got, ref in ((loss, l_ref), (mse, mse_ref), (kl, kl_ref)):
+        assert abs(float(got.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach())) + 1e-9
+    ok, aerr, rerr = rel_close(o.grad.cpu().numpy(), g_ref.numpy(), 1e-5, 2e-6 * float(g_ref.abs().max()))
+    assert ok, f"grad: abs {aerr:.3e} rel {rerr:.3e} (max |g| {float(g_ref.abs().max()):.3e})"
+    assert not mse.requires_grad and not kl.requires_grad

@@ -83,6 +83,22 @@ for B in (1, 16):
         (mse(alpha, labels) + 0.05 * kl(alpha, labels)).backward()
     rows.append(row(f"Dirichlet MSE+KL fwd+bwd B={B}", timeit(loss_step, flush_l2=True), 176 * B * H * W, B, "scans",
                     "two term kernels + autograd scaling passes (torch)"))
+    from semanticlidarunc_b200.losses.evidential import EvidentialLoss
+    fused = EvidentialLoss(1.0, 0.05, ignore_index=0)
+    # (a) i.i.d. logits per pixel: every warp sees every class as somebody's arg-max (worst case for the
+    #     per-class fast path); (b) spatially coherent arg-max in 32x32 patches, as a trained model on real scans
+    coh = synth.synth_coherent_labels(5, B, C, H, W, device="cpu").to(dev)
+    ev_coh = ev.clone()
+    ev_coh[:, :C].scatter_add_(1, coh.unsqueeze(1), torch.full((B, 1, H, W), 8.0, device=dev))
+    for tag, e_in, lab_in in (("i.i.d. logits", ev, labels), ("coherent arg-max", ev_coh, coh)):
+        evg = e_in.clone().requires_grad_(True)
+        def fused_step():
+            evg.grad = None
+            fused(evg, lab_in)[0].backward()
+        rows.append(row(f"fused evidential loss fwd+bwd from head outputs B={B}, {tag}", timeit(fused_step, flush_l2=True),
+                        176 * B * H * W, B, "scans", "count kernel + fused kernel + one autograd scale pass"))
+        fe2 = lambda: ops.evidential_reduce(e_in, lab_in, from_outputs=True, ignore_index=0, confmat=cm, ece_bins=bins)
+        rows.append(row(f"evidential reduce+metrics B={B}, {tag}", timeit(fe2, flush_l2=True), (4 * (C + 1) + 8 + 8 + 5 * 4) * B * H * W, B, "scans", ""))
     del logits
 
 # config 4: 4k-scan sweep of confusion + ECE from reduced maps (chunks of 256 scans)
