@@ -244,6 +244,19 @@ int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
                       float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
                       slu_stream_t stream);
 
+/* Organised clouds (Ouster / SemanticTHAB: the sensor delivers H x W points, pixel n = point n, no projection;
+ * src/inference_ouster.py:59-62, documentation/dataset.md:109).
+ * Replaces: src/dataset/dataloader_semantic_THAB.py:35-66 (label remap, reshape, flip, yaw as image roll +
+ *           rotate_z, float64 range) -- writes the same [B,6,HW] planes slu_project_batch writes, so
+ *           slu_frame_tensors / slu_backproject (with pix[n] = n) apply unchanged.
+ *   d_xyzi [B*H*W,4] float32, d_raw_label [B*H*W] uint32 or NULL, d_lut [65536] or NULL,
+ *   h_flip [B] host bytes or NULL, d_col_shift [B] int32 device (np.roll shift) or NULL, d_yaw_cs [B,2] or NULL,
+ *   d_missing [B] int32 or NULL: number of raw ids missing from the LUT.
+ */
+int slu_organized_planes(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
+                         int B, int H, int W, const uint8_t* h_flip, const int32_t* d_col_shift,
+                         const double* d_yaw_cs, float* d_img, int32_t* d_missing, slu_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 2: label back-projection, pixels -> points (the reference has no code
  * for it: documentation/dataset.md:109 describes the organised-cloud case only).

@@ -183,6 +183,49 @@ def gen_kitti_loader_aug():
     np.savez_compressed(os.path.join(GOLD, "kitti_loader_aug.npz"), **out)
 
 
+def gen_other_loaders():
+    """SemanticCUDAL (projected, +-pi/8) and SemanticTHAB (organised 128x2048) items from the reference."""
+    from dataset.dataloader_semantic_CUDAL import SemanticCUDAL
+    from dataset.dataloader_semantic_THAB import SemanticTHAB
+
+    def subs(r, tag, out):
+        for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+            out[f"{tag}/{k}_sha"] = np.frombuffer(bytes.fromhex(sha(a)), dtype=np.uint8)
+            out[f"{tag}/{k}_sub"] = a[:, ::4, ::16].copy()
+
+    out = {}
+    xyzi, raw = synth.synth_scan(23, "tiny")
+    raw = raw.copy()
+    raw[:50] = (raw[:50] & np.uint32(0xFFFF0000)) | np.uint32(2)          # CUDAL-only id 2 -> 12
+    xyzi = xyzi.copy()
+    xyzi[:, 3] *= 3.0                                                      # reflectivity above 1: the max-normalisation matters
+    out["cudal/xyzi"], out["cudal/raw"] = xyzi, raw
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "0.bin"), os.path.join(d, "0.label")
+        xyzi.tofile(fb); raw.tofile(fl)
+        ds = SemanticCUDAL([(fb, fl)], rotate=False, flip=False, projection=(32, 256), resize=True)
+        subs([t.numpy() for t in ds[0]], "cudal", out)
+    # THAB: organised OS1-128 cloud; seed so that flip = True, then the angle is drawn
+    xyzi, raw = synth.synth_scan(24, "os1-128")
+    out["thab/seed"] = np.array(24)
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "0.bin"), os.path.join(d, "0.label")
+        xyzi.tofile(fb); raw.tofile(fl)
+        subs([t.numpy() for t in SemanticTHAB([(fb, fl)])[0]], "thab_plain", out)
+        seed = 0
+        while True:
+            np.random.seed(seed)
+            if np.random.choice([True, False]):
+                angle = int(np.random.randint(-180, 180))
+                break
+            seed += 1
+        np.random.seed(seed)
+        subs([t.numpy() for t in SemanticTHAB([(fb, fl)], rotate=True, flip=True)[0]], "thab_aug", out)
+        out["thab_aug/angle"] = np.array(angle)
+        out["thab_aug/np_seed"] = np.array(seed)
+    np.savez_compressed(os.path.join(GOLD, "other_loaders.npz"), **out)
+
+
 # ---------------------------------------------------------------- uncertainty
 def gen_mc():
     pe, mi = extract_closures(os.path.join(_refshim.REF_SRC, "models", "tester.py"),
@@ -335,6 +378,7 @@ def main():
     }
     gen_kitti_loader()
     gen_kitti_loader_aug()
+    gen_other_loaders()
     gen_mc()
     gen_evidential()
     gen_metrics()

@@ -156,15 +156,17 @@ def build_normal_xyz(xyz, norm_factor=0.25):
     return normal
 
 
-def kitti_item(xyzi, raw_label, lut, projection=(64, 2048), resize=True, flip=False, yaw_deg=None):
+def kitti_item(xyzi, raw_label, lut, projection=(64, 2048), resize=True, flip=False, yaw_deg=None,
+               theta_range=None, normalise_reflectivity=False):
     """SemanticKitti.__getitem__ (src/dataset/dataloader_semantic_KITTI.py:31-99) with the random draws
-    (yaw angle :53, flip coin :71) passed in.  Returns the five arrays in the reference's order/dtypes."""
+    (yaw angle :53, flip coin :71) passed in.  Returns the five arrays in the reference's order/dtypes.
+    theta_range / normalise_reflectivity give SemanticCUDAL.__getitem__ (dataloader_semantic_CUDAL.py:70-125)."""
     import cv2
     sem = lut[(raw_label & 0xFFFF).astype(np.int64)].astype(np.int64)
     pc = np.concatenate([xyzi, sem[..., np.newaxis]], axis=-1)
     if yaw_deg is not None:
         pc[..., 0:3] = rotate_z(pc[..., 0:3].reshape(-1, 3), float(yaw_deg))
-    img, _, _, _ = spherical_projection(pc, projection[0], projection[1])
+    img, _, _, _ = spherical_projection(pc, projection[0], projection[1], theta_range=theta_range)
     if resize:
         img = cv2.resize(img, (2048, 128), interpolation=cv2.INTER_NEAREST)
     if flip:
@@ -172,9 +174,30 @@ def kitti_item(xyzi, raw_label, lut, projection=(64, 2048), resize=True, flip=Fa
         img[..., 1] *= -1
     label_img = img[..., 4:5]
     refl = img[..., 3]
+    if normalise_reflectivity:
+        refl = refl / np.maximum(refl.max(), 1.0)                                 # CUDAL :107
     xyz = img[..., 0:3]
     rng = np.linalg.norm(xyz, axis=-1)
     normals = build_normal_xyz(xyz[..., 0:3])
     return (rng[..., None].transpose(2, 0, 1).astype("float32"), refl[..., None].transpose(2, 0, 1).astype("float32"),
             xyz.transpose(2, 0, 1).astype("float32"), normals.transpose(2, 0, 1).astype("float32"),
             label_img.transpose(2, 0, 1).astype("int64"))
+
+
+def thab_item(xyzi, raw_label, lut, flip=False, yaw_deg=None, H=128, W=2048):
+    """SemanticTHAB.__getitem__ (src/dataset/dataloader_semantic_THAB.py:28-84): organised cloud, flip before
+    the yaw, the yaw as np.roll by round(angle / (2 pi) * W) columns plus rotate_z, float64 range."""
+    sem = lut[(raw_label & 0xFFFF).astype(np.int64)].astype(np.int64).reshape(H, W, 1)
+    img = np.concatenate((xyzi.reshape(H, W, 4), sem), axis=-1)                  # float64
+    if flip:
+        img = img[:, ::-1, :]
+        img[..., 1] = -img[..., 1]
+    if yaw_deg is not None:
+        img = np.roll(img, int(round((yaw_deg / (2 * np.pi)) * W)), axis=1)
+        img[..., 0:3] = rotate_z(img[..., 0:3].reshape(-1, 3), yaw_deg).reshape(img[..., 0:3].shape)
+    xyz = img[..., 0:3]
+    rng = np.linalg.norm(xyz, axis=-1)
+    normals = build_normal_xyz(xyz)
+    return (rng[..., None].transpose(2, 0, 1).astype("float32"), img[..., 3][..., None].transpose(2, 0, 1).astype("float32"),
+            xyz.transpose(2, 0, 1).astype("float32"), normals.transpose(2, 0, 1).astype("float32"),
+            img[..., 4:5].transpose(2, 0, 1).astype("int64"))

@@ -104,7 +104,83 @@ __global__ void __launch_bounds__(FR_THREADS) frame_normals_kernel(const __grid_
     }
 }
 
+// ---- organised clouds (Ouster / SemanticTHAB): the sensor already delivers H x W points, pixel = point -----------
+// Replaces src/dataset/dataloader_semantic_THAB.py:35-66: label remap, reshape to (H,W,.), optional flip
+// (columns reversed, y negated), optional yaw as an image roll (rotate_equirectangular_image,
+// src/dataset/utils.py:21-28) plus rotate_z on the coordinates, range = ||xyz|| in float64 (the THAB image is
+// float64, unlike the projected loaders), cast to float32.
+struct OrgParams {
+    const float4* xyzi;        // [B*HW]
+    const unsigned* raw;       // [B*HW] or NULL
+    const int* lut;            // [65536] or NULL
+    int B, H, W;
+    unsigned long long flip_bits[4];
+    const int* shift;          // [B] column roll per scan (device) or NULL
+    const double* yaw;         // [B,2] cos, sin (device) or NULL
+    float* img;                // [B,6,HW]
+    int* missing;              // [B] or NULL
+};
+
+__global__ void __launch_bounds__(FR_THREADS) organized_planes_kernel(const __grid_constant__ OrgParams p) {
+    const int b = blockIdx.y;
+    const long long HW = (long long)p.H * p.W;
+    const bool flip = (p.flip_bits[b >> 6] >> (b & 63)) & 1ull;
+    const int shift = p.shift ? p.shift[b] : 0;
+    int miss = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / p.W), x = (int)(i - (long long)y * p.W);
+        int xs = ((x - shift) % p.W + p.W) % p.W;           // np.roll(img, shift, axis=1): out[x] = in[x - shift]
+        if (flip) xs = p.W - 1 - xs;                          // the flip is applied before the roll
+        const long long src = (long long)b * HW + (long long)y * p.W + xs;
+        const float4 v = __ldg(p.xyzi + src);
+        double X = (double)v.x, Y = flip ? -(double)v.y : (double)v.y, Z = (double)v.z;
+        if (p.yaw) {
+            const double c = p.yaw[2 * b], s = p.yaw[2 * b + 1];
+            const double xr = __dadd_rn(__dmul_rn(X, c), __dmul_rn(Y, s));
+            const double yr = __dadd_rn(__dmul_rn(X, -s), __dmul_rn(Y, c));
+            X = xr; Y = yr;
+        }
+        float lab = 0.f;
+        if (p.raw) {
+            const unsigned id = __ldg(p.raw + src) & 0xffffu;
+            const int t = p.lut ? __ldg(p.lut + id) : (int)id;
+            if (t < 0) ++miss;
+            lab = (float)t;
+        }
+        const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(X, X), __dmul_rn(Y, Y)), __dmul_rn(Z, Z)));
+        float* o = p.img + (long long)b * 6 * HW + i;
+        o[0] = (float)X; o[HW] = (float)Y; o[2 * HW] = (float)Z; o[3 * HW] = (float)r; o[4 * HW] = v.w; o[5 * HW] = lab;
+    }
+    miss = __reduce_add_sync(0xffffffffu, miss);
+    if ((threadIdx.x & 31) == 0 && miss && p.missing) atomicAdd(&p.missing[b], miss);
+}
+
 }  // namespace slu
+
+extern "C" int slu_organized_planes(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
+                                    int B, int H, int W, const uint8_t* h_flip, const int32_t* d_col_shift,
+                                    const double* d_yaw_cs, float* d_img, int32_t* d_missing, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_xyzi || !d_img) return fail(SLU_E_ARG, "d_xyzi / d_img is NULL");
+    if (B < 1 || B > 256 || H < 1 || W < 1) return fail(SLU_E_RANGE, "B=%d H=%d W=%d unsupported", B, H, W);
+    if ((reinterpret_cast<uintptr_t>(d_xyzi) & 15) != 0) return fail(SLU_E_ALIGN, "d_xyzi not 16-byte aligned");
+    OrgParams p{};
+    p.xyzi = reinterpret_cast<const float4*>(d_xyzi); p.raw = d_raw_label; p.lut = d_lut;
+    p.B = B; p.H = H; p.W = W;
+    for (int b = 0; b < B && h_flip; ++b)
+        if (h_flip[b]) p.flip_bits[b >> 6] |= 1ull << (b & 63);
+    p.shift = d_col_shift; p.yaw = d_yaw_cs; p.img = d_img; p.missing = d_missing;
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d_missing) SLU_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int32_t) * B, st));
+    long long gx = ((long long)H * W + FR_THREADS - 1) / FR_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;
+    if (gx > cap) gx = cap;
+    organized_planes_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("organized_planes_kernel");
+    return 0;
+}
 
 extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
                                  const uint8_t* h_flip, float norm_factor,

@@ -20,6 +20,10 @@ from .definitions import build_id_lut, id_map
 
 
 class SemanticKitti(Dataset):
+    THETA_RANGE = None            # per-scan theta min/max (dataloader_semantic_KITTI.py:58)
+    RESIZE_TO = (128, 2048)       # cv2.resize(..., (2048,128)) at :62
+    LABEL_MAP = id_map
+
     def __init__(self, data_path, rotate=False, flip=False, resolution=(2048, 128), projection=(64, 2048), resize=True,
                  *, device=None, return_device: bool = False, label_map=None):
         self.data_path = data_path
@@ -30,7 +34,7 @@ class SemanticKitti(Dataset):
         self.resize = resize
         self.return_device = return_device
         self._device = device
-        self._lut_host = build_id_lut(id_map if label_map is None else label_map)
+        self._lut_host = build_id_lut(self.LABEL_MAP if label_map is None else label_map)
         self._lut = None
 
     def __len__(self):
@@ -58,19 +62,25 @@ class SemanticKitti(Dataset):
         xyzi = torch.from_numpy(np.ascontiguousarray(np.concatenate([s[0] for s in scans]))).to(dev, non_blocking=True)
         raw = torch.from_numpy(np.ascontiguousarray(np.concatenate([s[1] for s in scans])).view(np.int32)).to(dev, non_blocking=True)
         proj = ops.project_batch(xyzi, raw, offs, self.projection[0], self.projection[1], lut=self._lut, yaw_deg=yaw_deg,
-                                 want_label=False)
+                                 theta_range=self.THETA_RANGE, want_label=False)
         missing = proj["diag"][:, 0]
-        out = ops.frame_tensors(proj["img"], out_hw=(128, 2048) if self.resize else None, flip=flip)
+        out = ops.frame_tensors(proj["img"], out_hw=self.RESIZE_TO if self.resize else None, flip=flip)
         out["pix"], out["offsets"], out["missing_label_ids"] = proj["pix"], offs, missing
+        return self._finish(out)
+
+    def _finish(self, out):
         return out
+
+    def _draw_augmentation(self):
+        """(yaw in degrees or None, flip) drawn from numpy's global RNG in the reference's order (:53, :71)."""
+        yaw = float(np.random.randint(-180, 180)) if self.rotate else None
+        return yaw, bool(self.flip and np.random.rand() < 0.5)
 
     # -- Dataset -----------------------------------------------------------------------------------
     def __getitem__(self, idx):
         frame_path, label_path = self.data_path[idx]
         xyzi, label = self.read_scan(frame_path, label_path)
-        # the reference draws the augmentation parameters from numpy's global RNG in this order (:53, :71)
-        yaw = float(np.random.randint(-180, 180)) if self.rotate else None
-        do_flip = bool(self.flip and np.random.rand() < 0.5)
+        yaw, do_flip = self._draw_augmentation()
         out = self.device_batch([(xyzi, label)], yaw_deg=None if yaw is None else [yaw], flip=[do_flip])
         if int(out["missing_label_ids"][0]) != 0:
             raise KeyError("scan %s contains semantic ids that are not in the label map" % (label_path,))   # id_map[l] at :47

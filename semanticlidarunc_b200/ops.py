@@ -346,6 +346,36 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
     return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag}
 
 
+def organized_planes(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], H: int, W: int, *, lut: Optional[torch.Tensor] = None,
+                     flip=None, col_shift=None, yaw_deg=None) -> dict:
+    """Organised clouds (slu_organized_planes): xyzi [B*H*W,4] float32 -> img [B,6,H,W] planes, missing [B]."""
+    _lib.require_cuda()
+    xyzi = _lib.as_buffer(xyzi, torch.float32, "xyzi").reshape(-1, 4)
+    if xyzi.size(0) % (H * W) != 0:
+        raise ValueError("xyzi must hold a whole number of H*W clouds")
+    B = xyzi.size(0) // (H * W)
+    dev = xyzi.device
+    if raw_label is not None:
+        raw_label = raw_label.contiguous()
+    if lut is not None:
+        lut = _lib.as_buffer(lut, torch.int32, "lut")
+    h_flip = None
+    if flip is not None:
+        f = np.ascontiguousarray(np.broadcast_to(np.asarray(flip, dtype=np.uint8), (B,)))
+        h_flip = f.ctypes.data_as(_lib.C.c_void_p)
+    shift = None if col_shift is None else torch.as_tensor(np.broadcast_to(np.asarray(col_shift, dtype=np.int32), (B,)).copy()).to(dev)
+    yaw = None
+    if yaw_deg is not None:
+        a = np.radians(np.broadcast_to(np.asarray(yaw_deg, dtype=np.float64), (B,)))
+        yaw = torch.from_numpy(np.stack([np.cos(a), np.sin(a)], axis=1).copy()).to(dev)
+    img = torch.empty((B, 6, H, W), dtype=torch.float32, device=dev)
+    missing = torch.empty((B,), dtype=torch.int32, device=dev)
+    rc = _lib.lib().slu_organized_planes(_lib.ptr(xyzi), _lib.ptr(raw_label), _lib.ptr(lut), B, H, W, h_flip, _lib.ptr(shift),
+                                         _lib.ptr(yaw), _lib.ptr(img), _lib.ptr(missing), _lib.stream_ptr())
+    _lib.check(rc, "slu_organized_planes")
+    return {"img": img, "missing": missing}
+
+
 def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True) -> dict:
     """Loader glue on the device (slu_frame_tensors): img [B,6,H,W] planes -> the loaders' five tensors,
     stacked over B: range [B,1,h,w], reflectivity [B,1,h,w], xyz [B,3,h,w], normals [B,3,h,w], semantics

@@ -124,3 +124,37 @@ def test_unknown_label_id_raises_like_reference(cuda):
         ds = SemanticKitti(write_pair(d, xyzi, raw), projection=(16, 256), resize=False)
         with pytest.raises(KeyError):
             ds[0]
+
+
+def test_cudal_getitem_vs_reference(cuda, golden):
+    from semanticlidarunc_b200.dataset.dataloader_semantic_CUDAL import SemanticCUDAL
+    g = golden("other_loaders.npz")
+    with tempfile.TemporaryDirectory() as d:
+        ds = SemanticCUDAL(write_pair(d, g["cudal/xyzi"], g["cudal/raw"]), projection=(32, 256), resize=True)
+        rng, refl, xyz, normals, sem = (t.numpy() for t in ds[0])
+    for a, k in ((rng, "range"), (refl, "reflectivity"), (xyz, "xyz"), (sem, "semantics")):
+        assert sha(a) == bytes(g["cudal/" + k + "_sha"]).hex(), k
+    assert refl.max() <= 1.0 and 12 in np.unique(sem)
+    m = normals_condition_mask(xyz)[::4, ::16]
+    assert np.abs(normals[:, ::4, ::16].astype(np.float64) - g["cudal/normals_sub"])[:, m].max() <= 5e-5
+
+
+def test_thab_organised_cloud_vs_reference(cuda, golden):
+    from semanticlidarunc_b200.dataset.dataloader_semantic_THAB import SemanticTHAB
+    g = golden("other_loaders.npz")
+    xyzi, raw = synth.synth_scan(int(g["thab/seed"]), "os1-128")
+    with tempfile.TemporaryDirectory() as d:
+        paths = write_pair(d, xyzi, raw)
+        rng, refl, xyz, normals, sem = (t.numpy() for t in SemanticTHAB(paths)[0])
+        for a, k in ((rng, "range"), (refl, "reflectivity"), (xyz, "xyz"), (sem, "semantics")):
+            assert sha(a) == bytes(g["thab_plain/" + k + "_sha"]).hex(), k
+        m = normals_condition_mask(xyz)[::4, ::16]
+        assert m.mean() > 0.9
+        assert np.abs(normals[:, ::4, ::16].astype(np.float64) - g["thab_plain/normals_sub"])[:, m].max() <= 5e-5
+        # flip + yaw with the reference's RNG protocol (coin first, then the angle)
+        np.random.seed(int(g["thab_aug/np_seed"]))
+        rng, refl, xyz, normals, sem = (t.numpy() for t in SemanticTHAB(paths, rotate=True, flip=True)[0])
+    assert sha(sem) == bytes(g["thab_aug/semantics_sha"]).hex() and sha(refl) == bytes(g["thab_aug/reflectivity_sha"]).hex()
+    # rotated coordinates: np.dot's float64 accumulation is BLAS-specific, so float32(xyz) may differ in the last bit
+    assert np.abs(xyz[:, ::4, ::16] - g["thab_aug/xyz_sub"]).max() <= 1e-5
+    assert np.abs(rng[:, ::4, ::16] - g["thab_aug/range_sub"]).max() <= 1e-5

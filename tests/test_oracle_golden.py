@@ -188,3 +188,20 @@ def test_auroc_and_binned_accuracy_oracle_vs_golden(golden):
     for nb in (10, 20):
         n, acc = om.binned_accuracy(ov, ~err, nb)
         assert np.array_equal(n, g[f"ua/n_{nb}"]) and np.allclose(acc, g[f"ua/acc_{nb}"], equal_nan=True)
+
+
+def test_cudal_and_thab_items_oracle_vs_golden(golden):
+    import hashlib
+    from semanticlidarunc_b200.dataset.dataloader_semantic_CUDAL import id_map as cudal_map
+    g = golden("other_loaders.npz")
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    names = ("range", "reflectivity", "xyz", "normals", "semantics")
+    r = oproj.kitti_item(g["cudal/xyzi"], g["cudal/raw"], build_id_lut(cudal_map), projection=(32, 256), resize=True,
+                         theta_range=[-np.pi / 8, np.pi / 8], normalise_reflectivity=True)
+    for k, a in zip(names, r):
+        assert sha(a) == bytes(g[f"cudal/{k}_sha"]).hex(), k
+    xyzi, raw = synth.synth_scan(int(g["thab/seed"]), "os1-128")
+    for tag, kw in (("thab_plain", {}), ("thab_aug", {"flip": True, "yaw_deg": int(g["thab_aug/angle"])})):
+        r = oproj.thab_item(xyzi, raw, build_id_lut(), **kw)
+        for k, a in zip(names, r):
+            assert sha(a) == bytes(g[f"{tag}/{k}_sha"]).hex(), (tag, k)
