@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
 // kernels (tests/test_gpu_project.py runs both against the reference's golden vectors).
 // ====================================================================================================
 constexpr double ANGLE_MARGIN = 8.0e-6;     // rad; >= 7x the fp32 angle error bound
+constexpr int DEFER_CAP = 1024;             // per-block queue of near-edge points (overflow is handled inline)
 
 __device__ __forceinline__ double exact_phi(const Pt q) { return atan2(q.y, q.x); }
 __device__ __forceinline__ double exact_theta(const Pt q) {
@@ -273,13 +274,28 @@ __device__ __forceinline__ double exact_theta(const Pt q) {
     return __dadd_rn(-atan2(rho, q.z), HALF_PI);
 }
 
-// certified bin from an fp32 angle: returns cnt = #{edges <= v} or -1 if v is within the margin of an edge
-__device__ __forceinline__ int fast_count_le(double start, double step, double inv_step, int num, float a32) {
-    if (!(step > 0.0) || !(fabsf(a32) <= 4.0f)) return -1;
-    const double t = ((double)a32 - start) * inv_step;
-    const double fl = floor(t);
-    const double lo = (t - fl) * step, hi = (fl + 1.0 - t) * step;
-    if (!(lo > ANGLE_MARGIN && hi > ANGLE_MARGIN) || fl < 0.0 || fl > (double)(num - 2)) return -1;
+// certified bin from an fp32 angle, in fp32 (fp64 conversions and roundings run on a slow pipe): returns
+// cnt = #{edges <= v}, or -1 if v is within the margin of an edge.  t = (a - start)/step carries a relative
+// error of ~2e-7, i.e. < 5e-4 bins at 2048 bins; the margin in bin units is widened by 1e-3 to cover it.
+struct FastEdges { float c0, inv_step, margin_bins, last; };
+
+__device__ __forceinline__ FastEdges make_fast_edges(const Edges& e) {
+    FastEdges f;
+    const bool ok = e.step > 0.0 && e.num >= 2;
+    const double inv = ok ? 1.0 / e.step : 0.0;
+    f.inv_step = (float)inv;
+    f.c0 = (float)(-e.start * inv);
+    f.margin_bins = ok ? (float)(ANGLE_MARGIN * inv) + 1.0e-3f : 2.0f;     // 2 > 0.5: nothing passes when degenerate
+    f.last = (float)(e.num - 2);
+    return f;
+}
+
+__device__ __forceinline__ int fast_count_le(const FastEdges& f, float a32) {
+    if (!(fabsf(a32) <= 4.0f)) return -1;
+    const float t = fmaf(a32, f.inv_step, f.c0);
+    const float fl = floorf(t);
+    const float lo = t - fl;
+    if (!(lo > f.margin_bins && lo < 1.0f - f.margin_bins) || fl < 0.0f || fl > f.last) return -1;
     return (int)fl + 1;
 }
 
@@ -296,7 +312,11 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         p.diag[2 * b] = 0; p.diag[2 * b + 1] = 0;
     }
     const Edges ew = make_edges(-PI, PI, p.W);
-    const double inv_step_w = ew.step > 0.0 ? 1.0 / ew.step : 0.0;
+    const FastEdges fw = make_fast_edges(ew);
+    __shared__ int s_q[DEFER_CAP];
+    __shared__ int s_qn;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
     float tmin = INFINITY, tmax = -INFINITY;
     int missing = 0, near_cnt = 0;
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
@@ -309,8 +329,14 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
         const float phi32 = atan2f(v.y, v.x);
         const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
-        int cnt_w = fast_count_le(ew.start, ew.step, inv_step_w, ew.num, phi32);
+        p.theta32[n] = th32;
+        if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
+        int cnt_w = fast_count_le(fw, phi32);
         if (cnt_w < 0) {
+            // near an edge: queue the point; the fp64 path runs once per block on the packed queue instead of
+            // once per warp that happens to contain such a point
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
             bool near;
             cnt_w = count_le(ew, exact_phi(q), near);
             if (near) ++near_cnt;
@@ -318,8 +344,16 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         int c = (p.W - 1 - cnt_w) % p.W;
         if (c < 0) c += p.W;
         p.col[n] = c;
-        p.theta32[n] = th32;
-        if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
+        const long long n = n0 + s_q[i];
+        bool near;
+        const int cnt_w = count_le(ew, exact_phi(load_pt(p, b, __ldg(p.xyzi + n))), near);
+        if (near) ++near_cnt;
+        int c = (p.W - 1 - cnt_w) % p.W;
+        if (c < 0) c += p.W;
+        p.col[n] = c;
     }
     __shared__ float s_min[PT_THREADS / 32], s_max[PT_THREADS / 32];
     __shared__ int s_miss[PT_THREADS / 32], s_near[PT_THREADS / 32];
@@ -396,23 +430,49 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     double lo, hi;
     scan_theta_range(p, b, lo, hi);
     const Edges eh = make_edges(lo, hi, p.H);
-    const double inv_step_h = eh.step > 0.0 ? 1.0 / eh.step : 0.0;
+    const FastEdges fh = make_fast_edges(eh);
+    __shared__ int s_q[DEFER_CAP];
+    __shared__ int s_qn;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
     int near_cnt = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (p.theta_out) { p.theta_out[2 * b] = lo; p.theta_out[2 * b + 1] = hi; }
+    if (blockIdx.x == 0) {
+        // fold the angle kernel's per-block diagnostics into the scan's counters (strided over the block's
+        // threads: a single thread walking gx slots serially would be the longest chain in this kernel)
+        if (threadIdx.x == 0 && p.theta_out) { p.theta_out[2 * b] = lo; p.theta_out[2 * b + 1] = hi; }
         int missing = 0;
-        for (int i = 0; i < p.gx; ++i) { missing += p.part_diag[2 * ((long long)b * p.gx + i)]; near_cnt += p.part_diag[2 * ((long long)b * p.gx + i) + 1]; }
-        if (missing) atomicAdd(&p.diag[2 * b], missing);
+        for (int i = threadIdx.x; i < p.gx; i += blockDim.x) {
+            missing += p.part_diag[2 * ((long long)b * p.gx + i)];
+            near_cnt += p.part_diag[2 * ((long long)b * p.gx + i) + 1];
+        }
+        missing = __reduce_add_sync(0xffffffffu, missing);
+        if ((threadIdx.x & 31) == 0 && missing) atomicAdd(&p.diag[2 * b], missing);
     }
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        int cnt_h = fast_count_le(eh.start, eh.step, inv_step_h, eh.num, p.theta32[n]);
+        int cnt_h = fast_count_le(fh, p.theta32[n]);
         if (cnt_h < 0) {
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
             bool near;
             const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
             cnt_h = count_le(eh, th, near);
             if (near && !p.use_range) near = !(th == lo || th == hi);
             if (near) ++near_cnt;
         }
+        int r = (p.H - 1 - cnt_h) % p.H;
+        if (r < 0) r += p.H;
+        const int px = r * p.W + p.col[n];
+        p.pix[n] = px;
+        atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
+        const long long n = n0 + s_q[i];
+        bool near;
+        const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
+        const int cnt_h = count_le(eh, th, near);
+        if (near && !p.use_range) near = !(th == lo || th == hi);
+        if (near) ++near_cnt;
         int r = (p.H - 1 - cnt_h) % p.H;
         if (r < 0) r += p.H;
         const int px = r * p.W + p.col[n];
