@@ -153,7 +153,8 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": "reduce_staged_kernel<20,logits>", "achieved": round(achieved, 1),
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kernel_ms, 4), "traffic": None,
-                "kernel_share_of_step": round(kernel_ms / (ms / args.steps), 4)}
+                "kernel_share_of_step": round(kernel_ms / (ms / args.steps), 4),
+                "frac_of_8TBps_datasheet": round(achieved / 8000.0, 4)}
     tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tr):
         with open(tr) as f:
