@@ -154,6 +154,19 @@ int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, c
                               float temperature, float eps_alpha, float eps_mse, float eps_kl,
                               float w_mse, float w_kl, double* d_sums, float* d_grad_outputs, slu_stream_t stream);
 
+/* Alternative data-fit terms, one per call, forward + analytic backward.
+ * Replaces: NLLDirichletCategorical (src/losses/dirichlet_losses.py:73-119), DigammaDirichletCE (:122-167),
+ *           BrierDirichlet (:174-220; s_ref < 0 means "use alpha0").
+ *   d_sums [2] float64, ADDED to: sum of per-pixel values | number of valid pixels;  d_grad [B,C,HW] or NULL
+ *   holds d(per-pixel value)/d(alpha), 0 on masked pixels; the caller divides by max(n_valid,1).
+ */
+#define SLU_TERM_NLL        2
+#define SLU_TERM_DIGAMMA_CE 3
+#define SLU_TERM_BRIER      4
+int slu_dirichlet_term(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
+                       int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                       int term, float eps, float s_ref, double* d_sums, float* d_grad, slu_stream_t stream);
+
 /* Diagnostic: d_out[3i..3i+2] = lgamma, digamma, trigamma of d_in[i] (> 0) as the loss kernels evaluate them. */
 int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_stream_t stream);
 

@@ -350,7 +350,7 @@ def gen_metrics():
 
 # ---------------------------------------------------------------- losses
 def gen_losses():
-    from losses.dirichlet_losses import DirichletMSELoss
+    from losses.dirichlet_losses import BrierDirichlet, DigammaDirichletCE, DirichletMSELoss, NLLDirichletCategorical
     from losses.regularizers import KL_offClasses_to_uniform
 
     g = torch.Generator().manual_seed(404)
@@ -358,7 +358,9 @@ def gen_losses():
     alpha = (torch.nn.functional.softplus(torch.randn((B, C, H, W), generator=g) * 3.0) + 1.0)
     target = torch.randint(0, C, (B, H, W), generator=g)
     out = {"alpha": alpha.numpy(), "target": target.numpy()}
-    for name, mod in (("mse", DirichletMSELoss(ignore_index=0)), ("kl", KL_offClasses_to_uniform(ignore_index=0))):
+    for name, mod in (("mse", DirichletMSELoss(ignore_index=0)), ("kl", KL_offClasses_to_uniform(ignore_index=0)),
+                      ("nll", NLLDirichletCategorical(ignore_index=0)), ("dce", DigammaDirichletCE(ignore_index=0)),
+                      ("brier", BrierDirichlet(ignore_index=0)), ("brier_sref", BrierDirichlet(ignore_index=0, s_ref=30.0))):
         a = alpha.clone().requires_grad_(True)
         loss = mod(a, target)
         (grad,) = torch.autograd.grad(loss, a)

@@ -67,3 +67,51 @@ def kl_offclasses_to_uniform(alpha: torch.Tensor, target: torch.Tensor, ignore_i
     term1 = torch.lgamma(s) - torch.lgamma(a).sum(dim=1, keepdim=True)
     term2 = ((a - 1.0) * (torch.digamma(a) - torch.digamma(s))).sum(dim=1, keepdim=True)
     return (term1 + term2).squeeze(1).mean()
+
+
+def _masked_mean(per_pix, valid):
+    w = valid.float().to(per_pix.dtype)
+    return (per_pix * w).sum() / w.sum().clamp_min(1.0)
+
+
+def nll_dirichlet_categorical(alpha, target, ignore_index=None, eps: float = 1e-12):
+    """src/losses/dirichlet_losses.py:73-119."""
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    target = target.long()
+    valid = valid_mask(target, ignore_index)
+    if valid.sum() == 0:
+        return alpha.sum() * 0.0
+    a0 = alpha.sum(dim=1)
+    ay = alpha.gather(1, target.unsqueeze(1)).squeeze(1)
+    return _masked_mean(-(torch.log(ay + eps) - torch.log(a0 + eps)), valid)
+
+
+def digamma_dirichlet_ce(alpha, target, ignore_index=None):
+    """src/losses/dirichlet_losses.py:122-167."""
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    target = target.long()
+    valid = valid_mask(target, ignore_index)
+    if valid.sum() == 0:
+        return alpha.sum() * 0.0
+    a0 = alpha.sum(dim=1)
+    ay = alpha.gather(1, target.unsqueeze(1)).squeeze(1)
+    return _masked_mean(torch.digamma(a0) - torch.digamma(ay), valid)
+
+
+def brier_dirichlet(alpha, target, ignore_index=None, s_ref=None, eps: float = 1e-12):
+    """src/losses/dirichlet_losses.py:174-220."""
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    target = target.long()
+    valid = valid_mask(target, ignore_index)
+    if valid.sum() == 0:
+        return alpha.sum() * 0.0
+    a0 = alpha.sum(dim=1, keepdim=True)
+    p_hat = alpha / (a0 + eps)
+    sum_p2 = (p_hat * p_hat).sum(dim=1, keepdim=True)
+    s = a0 if s_ref is None else torch.as_tensor(float(s_ref), dtype=alpha.dtype)
+    sum_ep2 = (s * sum_p2 + 1.0) / (s + 1.0)
+    ep_y = p_hat.gather(1, target.unsqueeze(1))
+    return _masked_mean((sum_ep2 - 2.0 * ep_y + 1.0).squeeze(1), valid)

@@ -342,6 +342,134 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
     return 0;
 }
 
+
+// =====================================================================================================
+// Single-term kernel for the alternative data-fit terms.  Per pixel, with a0 = sum(alpha),
+// ay = alpha[target]:
+//   SLU_TERM_NLL        NLLDirichletCategorical  src/losses/dirichlet_losses.py:73-119
+//        L = log(a0 + e) - log(ay + e)                   dL/da_j = 1/(a0+e) - [j=y]/(ay+e)
+//   SLU_TERM_DIGAMMA_CE DigammaDirichletCE       :122-167
+//        L = psi(a0) - psi(ay)                           dL/da_j = psi'(a0) - [j=y] psi'(ay)
+//   SLU_TERM_BRIER      BrierDirichlet           :174-220   (D = a0 + e, p = alpha/D, S2 = sum p^2,
+//        s = a0 or the constant s_ref)  L = (s S2 + 1)/(s + 1) - 2 p_y + 1
+//        dS2/da_j = 2 alpha_j/D^2 - 2 S2/D;  dp_y/da_j = [j=y]/D - alpha_y/D^2
+// =====================================================================================================
+struct TermParams {
+    const float* alpha;
+    const long long* target;
+    const unsigned char* keep;
+    int B, C;
+    long long HW, n_px;
+    long long ignore[MAX_IGNORE];
+    int n_ignore;
+    int term;
+    float eps, s_ref;              // s_ref < 0: use a0
+    double* sums;                  // [2] sum of per-pixel values | n_valid
+    float* grad;                   // [B,C,HW] or NULL
+};
+
+template <int CP>
+__global__ void __launch_bounds__(LOSS_THREADS) dirichlet_term_kernel(const __grid_constant__ TermParams p) {
+    const int tid = threadIdx.x;
+    double acc = 0.0;
+    unsigned n_valid = 0;
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long g = ch * LOSS_THREADS + tid;
+        if (g >= p.n_px) continue;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const long long tgt = p.target[g];
+        bool valid;
+        if (p.keep) {
+            valid = p.keep[g] != 0;
+        } else {
+            valid = true;
+#pragma unroll
+            for (int i = 0; i < MAX_IGNORE; ++i)
+                if (i < p.n_ignore && tgt == p.ignore[i]) valid = false;
+        }
+        const float* base = p.alpha + ((long long)b * p.C) * p.HW + px;
+        float* go = p.grad ? p.grad + ((long long)b * p.C) * p.HW + px : nullptr;
+        if (!valid) {
+            if (go) for (int c = 0; c < p.C; ++c) go[(long long)c * p.HW] = 0.f;
+            continue;
+        }
+        ++n_valid;
+        const int y = (int)tgt;
+        float a[CP];
+        float a0 = 0.f, ay = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            a[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
+            a0 += a[c];
+            if (c == y) ay = a[c];
+        }
+        float gA = 0.f, gB = 0.f, gC = 0.f, val = 0.f;      // dL/da_j = gA + gB [j=y] + gC a_j
+        if (p.term == SLU_TERM_NLL) {
+            val = logf(a0 + p.eps) - logf(ay + p.eps);
+            gA = 1.0f / (a0 + p.eps);
+            gB = -1.0f / (ay + p.eps);
+        } else if (p.term == SLU_TERM_DIGAMMA_CE) {
+            val = digamma_pos(a0) - digamma_pos(ay);
+            gA = trigamma_pos(a0);
+            gB = -trigamma_pos(ay);
+        } else {   // SLU_TERM_BRIER
+            const float D = a0 + p.eps, invD = 1.0f / D;
+            float S2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) { const float pc = a[c] * invD; S2 = fmaf(pc, pc, S2); }
+            const float py = ay * invD;
+            const float dS2_A = -2.0f * S2 * invD, dS2_C = 2.0f * invD * invD;      // dS2/da_j = dS2_A + dS2_C a_j
+            if (p.s_ref < 0.f) {
+                const float q = 1.0f / (a0 + 1.0f);
+                val = (a0 * S2 + 1.0f) * q - 2.0f * py + 1.0f;
+                gA = (S2 - 1.0f) * q * q + a0 * q * dS2_A;
+                gC = a0 * q * dS2_C;
+            } else {
+                const float q = p.s_ref / (p.s_ref + 1.0f);
+                val = (p.s_ref * S2 + 1.0f) / (p.s_ref + 1.0f) - 2.0f * py + 1.0f;
+                gA = q * dS2_A;
+                gC = q * dS2_C;
+            }
+            gA += 2.0f * ay * invD * invD;
+            gB = -2.0f * invD;
+        }
+        acc += (double)val;
+        if (go) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (c < p.C) go[(long long)c * p.HW] = fmaf(gC, a[c], gA + (c == y ? gB : 0.f));
+        }
+    }
+    __shared__ double s_v[LOSS_THREADS / 32];
+    __shared__ unsigned s_n[LOSS_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    }
+    if ((tid & 31) == 0) { s_v[tid >> 5] = acc; s_n[tid >> 5] = n_valid; }
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0, n = 0.0;
+        for (int i = 0; i < LOSS_THREADS / 32; ++i) { v += s_v[i]; n += (double)s_n[i]; }
+        atomicAdd(&p.sums[0], v);
+        atomicAdd(&p.sums[1], n);
+    }
+}
+
+template <int CP>
+static int launch_term(const TermParams& p, cudaStream_t st) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    const long long cap = 6LL * sms;
+    dirichlet_term_kernel<CP><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
+    SLU_LAUNCH_CHECK("dirichlet_term_kernel");
+    return 0;
+}
+
 // diagnostic: out[3i..3i+2] = lgamma, digamma, trigamma of in[i] through ldt_pos (accuracy tests)
 __global__ void special_eval_kernel(const float* in, long long n, float* out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,6 +480,34 @@ __global__ void special_eval_kernel(const float* in, long long n, float* out) {
 }
 
 }  // namespace slu
+extern "C" int slu_dirichlet_term(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
+                                  int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                                  int term, float eps, float s_ref, double* d_sums, float* d_grad, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_alpha || !d_target || !d_sums) return fail(SLU_E_ARG, "d_alpha / d_target / d_sums is NULL");
+    if (B < 1 || HW < 1) return fail(SLU_E_ARG, "B=%d HW=%lld must be >= 1", B, (long long)HW);
+    if (C < 2 || C > SLU_MAX_CLASSES) return fail(SLU_E_RANGE, "C=%d outside [2,%d]", C, SLU_MAX_CLASSES);
+    if (n_ignore < 0 || n_ignore > MAX_IGNORE || (n_ignore > 0 && !h_ignore)) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,%d]", n_ignore, MAX_IGNORE);
+    if (term != SLU_TERM_NLL && term != SLU_TERM_DIGAMMA_CE && term != SLU_TERM_BRIER) return fail(SLU_E_ARG, "unknown term %d", term);
+    TermParams p{};
+    p.alpha = d_alpha; p.target = reinterpret_cast<const long long*>(d_target); p.keep = d_keep_mask;
+    p.B = B; p.C = C; p.HW = HW; p.n_px = (long long)B * HW;
+    for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
+    p.n_ignore = n_ignore; p.term = term; p.eps = eps; p.s_ref = s_ref;
+    p.sums = d_sums; p.grad = d_grad;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch ((C + 3) / 4 * 4) {
+        case 4: return launch_term<4>(p, st);
+        case 8: return launch_term<8>(p, st);
+        case 12: return launch_term<12>(p, st);
+        case 16: return launch_term<16>(p, st);
+        case 20: return launch_term<20>(p, st);
+        case 24: return launch_term<24>(p, st);
+        case 28: return launch_term<28>(p, st);
+        default: return launch_term<32>(p, st);
+    }
+}
+
 extern "C" int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_stream_t stream) {
     using namespace slu;
     if (!d_in || !d_out || n < 1) return fail(SLU_E_ARG, "slu_diag_special: bad arguments");

@@ -32,3 +32,25 @@ class _DirichletTerm(torch.autograd.Function):
         g, n = ctx.saved_tensors
         scale = (grad_out.double() / n).to(g.dtype)
         return g * scale, None, None, None, None
+
+
+class _DirichletSingleTerm(torch.autograd.Function):
+    """NLL / digamma-CE / Brier (ops.TERM_*): one kernel launch, analytic gradient saved for backward."""
+
+    @staticmethod
+    def forward(ctx, alpha, target, term: int, ignore_index, eps: float, s_ref):
+        ids, keep = split_ignore(ignore_index)
+        if len(ids) > MAX_IDS:
+            keep = ~torch.isin(target, torch.as_tensor(ids, device=target.device, dtype=target.dtype))
+            ids = ()
+        r = ops.dirichlet_term(alpha.detach(), target, term, ignore=ids, keep_mask=keep, eps=eps, s_ref=s_ref,
+                               want_grad=ctx.needs_input_grad[0])
+        n = r["sums"][1].clamp_min(1.0)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(r["grad"], n)
+        return (r["sums"][0] / n).to(alpha.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g, n = ctx.saved_tensors
+        return g * (grad_out.double() / n).to(g.dtype), None, None, None, None, None

@@ -1,9 +1,9 @@
 """`DirichletMSELoss` with the reference's interface (src/losses/dirichlet_losses.py:317-385), computed
 by libslu's fused forward+backward kernel (csrc/slu_loss.cu).  `_valid_mask` mirrors :15-70.
 
-The other Dirichlet data-fit terms of that file (NLLDirichletCategorical :73, DigammaDirichletCE :122,
-BrierDirichlet :174, ComplementKLUniform :228) have weight 0 in every shipped config
-(src/configs/SemanticKitti_default.yaml:50-62) and are next-round work.
+`NLLDirichletCategorical` (:73-119), `DigammaDirichletCE` (:122-167) and `BrierDirichlet` (:174-220) -- weight
+0 in every shipped config (src/configs/SemanticKitti_default.yaml:50-62) -- run on the single-term kernel
+(slu_dirichlet_term).  `ComplementKLUniform` (:228-314) is not on the device path yet.
 """
 from __future__ import annotations
 
@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from ._function import _DirichletTerm
+from .. import ops
+from ._function import _DirichletSingleTerm, _DirichletTerm
 from ._mask import _valid_mask  # noqa: F401  (re-exported, the reference Trainer imports it from here)
 
 
@@ -31,3 +32,46 @@ class DirichletMSELoss(nn.Module):
         if alpha.shape[1] <= 2:                       # the reference returns an exact zero here (:352-353)
             return alpha.sum() * 0.0
         return _DirichletTerm.apply(alpha, target, 0, self.ignore_index, self.eps)
+
+
+def _prep(target: torch.Tensor) -> torch.Tensor:
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    return target.long()
+
+
+class NLLDirichletCategorical(nn.Module):
+    """-log E[p_y] = log(alpha0 + eps) - log(alpha_y + eps), mean over valid pixels (:73-119)."""
+
+    def __init__(self, ignore_index: Optional[int] = None, eps: float = 1e-12):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.eps = eps
+
+    def forward(self, alpha: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _DirichletSingleTerm.apply(alpha, _prep(target), ops.TERM_NLL, self.ignore_index, self.eps, None)
+
+
+class DigammaDirichletCE(nn.Module):
+    """E[-log p_y] = psi(alpha0) - psi(alpha_y), mean over valid pixels (:122-167)."""
+
+    def __init__(self, ignore_index: Optional[int] = None, eps: float = 1e-8):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.eps = eps
+
+    def forward(self, alpha: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _DirichletSingleTerm.apply(alpha, _prep(target), ops.TERM_DIGAMMA_CE, self.ignore_index, self.eps, None)
+
+
+class BrierDirichlet(nn.Module):
+    """Expected Brier score under the Dirichlet predictive distribution (:174-220)."""
+
+    def __init__(self, ignore_index: Optional[int] = None, s_ref: Optional[float] = None, eps: float = 1e-12):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.s_ref = s_ref
+        self.eps = eps
+
+    def forward(self, alpha: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return _DirichletSingleTerm.apply(alpha, _prep(target), ops.TERM_BRIER, self.ignore_index, self.eps, self.s_ref)

@@ -173,6 +173,33 @@ def dirichlet_loss(alpha: torch.Tensor, target: torch.Tensor, *, ignore=(), keep
     return {"sums": sums, "grad_mse": g_mse, "grad_kl": g_kl}
 
 
+TERM_NLL, TERM_DIGAMMA_CE, TERM_BRIER = 2, 3, 4
+
+
+def dirichlet_term(alpha: torch.Tensor, target: torch.Tensor, term: int, *, ignore=(), keep_mask: Optional[torch.Tensor] = None,
+                   eps: float = 1e-12, s_ref: Optional[float] = None, want_grad: bool = True) -> dict:
+    """One alternative data-fit term (slu_dirichlet_term): sums float64[2] (sum | n_valid) and grad [B,C,H,W]."""
+    _lib.require_cuda()
+    alpha = _lib.as_buffer(alpha, torch.float32, "alpha")
+    B, Cc, H, W = alpha.shape
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    if tuple(target.shape) != (B, H, W):
+        raise ValueError(f"target shape {tuple(target.shape)} != {(B, H, W)}")
+    target = _lib.as_buffer(target.to(alpha.device), torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask.to(alpha.device), torch.bool, "keep_mask")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    sums = torch.zeros(2, dtype=torch.float64, device=alpha.device)
+    grad = torch.empty_like(alpha) if want_grad else None
+    rc = _lib.lib().slu_dirichlet_term(_lib.ptr(alpha), _lib.ptr(target), _lib.ptr(keep_mask), B, Cc, H * W, h_ign, len(ign),
+                                       int(term), float(eps), -1.0 if s_ref is None else float(s_ref), _lib.ptr(sums),
+                                       _lib.ptr(grad), _lib.stream_ptr())
+    _lib.check(rc, "slu_dirichlet_term")
+    return {"sums": sums, "grad": grad}
+
+
 def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse: float = 1.0, w_kl: float = 0.05,
                           ignore=(), keep_mask: Optional[torch.Tensor] = None, temperature: float = 1.0,
                           eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True) -> dict:

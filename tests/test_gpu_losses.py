@@ -112,3 +112,40 @@ def test_fused_loss_from_head_outputs_vs_oracle_chain(cuda, shape, ignore):
     ok, aerr, rerr = rel_close(o.grad.cpu().numpy(), g_ref.numpy(), 1e-5, 2e-6 * float(g_ref.abs().max()))
     assert ok, f"grad: abs {aerr:.3e} rel {rerr:.3e} (max |g| {float(g_ref.abs().max()):.3e})"
     assert not mse.requires_grad and not kl.requires_grad
+
+
+@pytest.mark.parametrize("name", ["nll", "dce", "brier", "brier_sref"])
+def test_alternative_data_fit_terms_vs_reference_golden(cuda, golden, name):
+    from semanticlidarunc_b200.losses.dirichlet_losses import BrierDirichlet, DigammaDirichletCE, NLLDirichletCategorical
+    mods = {"nll": NLLDirichletCategorical(ignore_index=0), "dce": DigammaDirichletCE(ignore_index=0),
+            "brier": BrierDirichlet(ignore_index=0), "brier_sref": BrierDirichlet(ignore_index=0, s_ref=30.0)}
+    g = golden("losses.npz")
+    a = torch.from_numpy(g["alpha"]).to(cuda).requires_grad_(True)
+    t = torch.from_numpy(g["target"]).to(cuda)
+    loss = mods[name](a, t)
+    (grad,) = torch.autograd.grad(loss, a)
+    ref = float(g[name + "/loss"])
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref) + 1e-9, (float(loss.detach()), ref)
+    ok, aerr, rerr = rel_close(grad.cpu().numpy(), g[name + "/grad"], 1e-5, 2e-6 * float(np.abs(g[name + "/grad"]).max()))
+    assert ok, f"{name} grad: abs {aerr:.3e} rel {rerr:.3e}"
+
+
+def test_alternative_terms_vs_fp64_autograd_with_masks(cuda):
+    import functools
+    from semanticlidarunc_b200.losses.dirichlet_losses import BrierDirichlet, DigammaDirichletCE, NLLDirichletCategorical
+    gen = torch.Generator().manual_seed(8)
+    alpha = torch.nn.functional.softplus(torch.randn((2, 13, 6, 70), generator=gen) * 3.0) + 1.0
+    target = torch.randint(0, 13, (2, 6, 70), generator=gen)
+    keep = torch.rand((2, 6, 70), generator=gen) > 0.25
+    for ign, ign_dev in (((0, 4), (0, 4)), (keep, keep.to(cuda))):
+        for fn, mod in ((ol.nll_dirichlet_categorical, NLLDirichletCategorical), (ol.digamma_dirichlet_ce, DigammaDirichletCE),
+                        (ol.brier_dirichlet, BrierDirichlet)):
+            a_ref = alpha.clone().double().requires_grad_(True)
+            l_ref = fn(a_ref, target, ignore_index=ign)
+            (g_ref,) = torch.autograd.grad(l_ref, a_ref)
+            a = alpha.clone().to(cuda).requires_grad_(True)
+            l = mod(ignore_index=ign_dev)(a, target.to(cuda))
+            l.backward()
+            assert abs(float(l.detach()) - float(l_ref.detach())) <= 1e-5 * abs(float(l_ref.detach())) + 1e-9, mod.__name__
+            ok, aerr, rerr = rel_close(a.grad.cpu().numpy(), g_ref.numpy(), 1e-5, 2e-6 * float(g_ref.abs().max()))
+            assert ok, f"{mod.__name__} grad: abs {aerr:.3e} rel {rerr:.3e}"

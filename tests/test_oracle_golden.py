@@ -99,7 +99,10 @@ def test_metrics_oracle_vs_golden(golden):
 def test_losses_oracle_vs_golden(golden):
     g = golden("losses.npz")
     target = torch.from_numpy(g["target"])
-    for name, fn in (("mse", ol.dirichlet_mse), ("kl", ol.kl_offclasses_to_uniform)):
+    import functools
+    for name, fn in (("mse", ol.dirichlet_mse), ("kl", ol.kl_offclasses_to_uniform), ("nll", ol.nll_dirichlet_categorical),
+                     ("dce", ol.digamma_dirichlet_ce), ("brier", ol.brier_dirichlet),
+                     ("brier_sref", functools.partial(ol.brier_dirichlet, s_ref=30.0))):
         a = torch.from_numpy(g["alpha"]).clone().requires_grad_(True)
         loss = fn(a, target, ignore_index=0)
         (grad,) = torch.autograd.grad(loss, a)
