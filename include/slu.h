@@ -196,6 +196,12 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
 int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
                    int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream);
 
+/* Per-class score histogram: replaces the per-class host arrays of UncertaintyPerClassAggregator.update
+ * (src/models/evaluator.py:211-262).  d_hist [C, n_score_bins] int64 and d_sum_fx [C] int64 (sum of scores in
+ * units of 2^-32, non-negative scores) are ADDED to; labels outside [0,C) and NaN scores are skipped. */
+int slu_class_score_hist(const float* d_score, const int64_t* d_labels, int64_t n, int C, int n_score_bins,
+                         int64_t* d_hist, int64_t* d_sum_fx, slu_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 1: spherical range-image projection with a nearest-range depth test, batched.
  * Replaces: spherical_projection (src/dataset/utils.py:288-349) + to_deflection_coordinates

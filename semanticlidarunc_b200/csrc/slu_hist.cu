@@ -120,7 +120,43 @@ __global__ void __launch_bounds__(HIST_THREADS) score_hist_kernel(const float* _
     }
 }
 
+// ---- per-class score histogram: UncertaintyPerClassAggregator (src/models/evaluator.py:191-262) --------------------
+// The reference keeps, per class, every pixel's uncertainty on the host (for box / ridgeline plots and the per-class mean).
+// Here: hist[label][floor(clamp(score,0,1) * M)] += 1 and an exact per-class sum in 2^-32 fixed point.
+__global__ void __launch_bounds__(HIST_THREADS) class_score_hist_kernel(const float* __restrict__ score, const long long* __restrict__ labels,
+                                                                        long long n, int C, int M, unsigned long long* __restrict__ hist,
+                                                                        unsigned long long* __restrict__ sum_fx) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long lb = __ldg(labels + i);
+        const float s = __ldg(score + i);
+        if (lb < 0 || lb >= C || s != s) continue;
+        int bin = (int)((double)fminf(fmaxf(s, 0.f), 1.f) * (double)M);
+        bin = bin > M - 1 ? M - 1 : bin;
+        atomicAdd(&hist[lb * M + bin], 1ull);
+        atomicAdd(&sum_fx[lb], __double2ull_rn((double)s * 4294967296.0));      // unclamped value, as the reference stores it
+    }
+}
+
 }  // namespace slu
+
+extern "C" int slu_class_score_hist(const float* d_score, const int64_t* d_labels, int64_t n, int C, int n_score_bins,
+                                    int64_t* d_hist, int64_t* d_sum_fx, slu_stream_t stream) {
+    using namespace slu;
+    if (n < 0) return fail(SLU_E_ARG, "n < 0");
+    if (n == 0) return 0;
+    if (!d_score || !d_labels || !d_hist || !d_sum_fx) return fail(SLU_E_ARG, "NULL pointer");
+    if (C < 1 || C > 4096 || n_score_bins < 1 || n_score_bins > (1 << 20)) return fail(SLU_E_RANGE, "C=%d / n_score_bins=%d unsupported", C, n_score_bins);
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long want = (n + HIST_THREADS - 1) / HIST_THREADS;
+    const long long cap = 8LL * sms;
+    class_score_hist_kernel<<<(unsigned)(want < cap ? want : cap), HIST_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_score, reinterpret_cast<const long long*>(d_labels), n, C, n_score_bins,
+        reinterpret_cast<unsigned long long*>(d_hist), reinterpret_cast<unsigned long long*>(d_sum_fx));
+    SLU_LAUNCH_CHECK("class_score_hist_kernel");
+    return 0;
+}
 
 extern "C" int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
                               int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream) {

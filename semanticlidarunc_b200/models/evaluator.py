@@ -151,3 +151,75 @@ class UncertaintyAccuracyAggregator:
         labels = [f"[{l:.2f}, {hh:.2f})" if i < len(lows) - 1 else f"[{l:.2f}, {hh:.2f}]" for i, (l, hh) in enumerate(zip(lows, highs))]
         return pd.DataFrame({"low": lows, "high": highs, "label": labels, "n": n.astype(int),
                              "pct": 100.0 * n / max(1.0, n.sum()), "accuracy": acc})
+
+
+class UncertaintyPerClassAggregator:
+    """Per-class uncertainty statistics with the reference's interface (src/models/evaluator.py:191-281):
+    `update(labels, uncertainty)`, `reset()`, `as_dataframe(class_names, ignore_ids)`, `_seen_counts`.
+    State is a device histogram [C, 2048] plus an exact per-class sum, so the per-class mean (what
+    plot_iou_sorted_by_uncertainty uses, :559-563) is exact and the distribution plots see 2048-bin densities.
+    `as_dataframe` expands the histogram to bin-centre samples (at most `max_rows_per_class` per class, in
+    proportion); `class_stats()` gives count / mean / quartiles directly.  `max_per_class` is accepted and ignored."""
+
+    def __init__(self, num_classes: int, max_per_class: int | None = None, seed: int = 0, n_score_bins: int = 2048,
+                 max_rows_per_class: int = 200_000):
+        self.num_classes = int(num_classes)
+        self.max_per_class = max_per_class
+        self.n_score_bins = int(n_score_bins)
+        self.max_rows_per_class = int(max_rows_per_class)
+        self._hist = None
+        self._sum = None
+
+    def reset(self):
+        if self._hist is not None:
+            self._hist.zero_()
+            self._sum.zero_()
+
+    @property
+    def _seen_counts(self):
+        if self._hist is None:
+            return [0] * self.num_classes
+        return [int(v) for v in self._hist.sum(dim=1).cpu()]
+
+    @torch.no_grad()
+    def update(self, labels: torch.Tensor, uncertainty: torch.Tensor):
+        assert labels.shape == uncertainty.shape, "labels and uncertainty must have same shape"
+        dev = uncertainty.device if uncertainty.is_cuda else _lib.require_cuda()
+        if self._hist is None:
+            self._hist = torch.zeros((self.num_classes, self.n_score_bins), dtype=torch.int64, device=dev)
+            self._sum = torch.zeros((self.num_classes,), dtype=torch.int64, device=dev)
+        ops.class_score_hist(uncertainty.detach().to(dev), labels.detach().to(dev), self._hist, self._sum)
+
+    def class_stats(self) -> pd.DataFrame:
+        cols = ["class_id", "n", "mean", "q25", "median", "q75"]
+        if self._hist is None:
+            return pd.DataFrame(columns=cols)
+        h = self._hist.cpu().numpy().astype(np.float64)
+        sums = self._sum.cpu().numpy().astype(np.float64) / 4294967296.0
+        centres = (np.arange(self.n_score_bins) + 0.5) / self.n_score_bins
+        rows = []
+        for c in range(self.num_classes):
+            n = h[c].sum()
+            if n == 0:
+                continue
+            cdf = np.cumsum(h[c]) / n
+            q = [float(centres[min(np.searchsorted(cdf, t), self.n_score_bins - 1)]) for t in (0.25, 0.5, 0.75)]
+            rows.append({"class_id": c, "n": int(n), "mean": float(sums[c] / n), "q25": q[0], "median": q[1], "q75": q[2]})
+        return pd.DataFrame(rows, columns=cols)
+
+    def as_dataframe(self, class_names, ignore_ids=()):
+        """Long DataFrame with columns class_id, class, uncertainty (bin-centre samples of the histogram)."""
+        if self._hist is None:
+            return pd.DataFrame(columns=["class_id", "class", "uncertainty"])
+        h = self._hist.cpu().numpy()
+        centres = ((np.arange(self.n_score_bins) + 0.5) / self.n_score_bins).astype(np.float32)
+        rows, skip = [], set(ignore_ids)
+        for c in range(self.num_classes):
+            n = int(h[c].sum())
+            if c in skip or n == 0:
+                continue
+            reps = h[c] if n <= self.max_rows_per_class else np.round(h[c] * (self.max_rows_per_class / n)).astype(np.int64)
+            rows.append(pd.DataFrame({"class_id": c, "class": class_names[c], "uncertainty": np.repeat(centres, reps)}))
+        if not rows:
+            return pd.DataFrame(columns=["class_id", "class", "uncertainty"])
+        return pd.concat(rows, ignore_index=True)

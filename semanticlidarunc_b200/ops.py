@@ -287,6 +287,18 @@ def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hi
     _lib.check(rc, "slu_score_hist")
 
 
+def class_score_hist(score: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, sum_fx: torch.Tensor) -> None:
+    """Accumulate scores per label class (slu_class_score_hist): hist [C,M] int64, sum_fx [C] int64 (2^-32 units)."""
+    _lib.require_cuda()
+    score = _lib.as_buffer(score, torch.float32, "score").reshape(-1)
+    labels = _lib.as_buffer(labels, torch.int64, "labels").reshape(-1)
+    if score.numel() != labels.numel():
+        raise ValueError("score and labels differ in size")
+    rc = _lib.lib().slu_class_score_hist(_lib.ptr(score), _lib.ptr(labels), score.numel(), hist.size(0), hist.size(1),
+                                         _lib.ptr(hist), _lib.ptr(sum_fx), _lib.stream_ptr())
+    _lib.check(rc, "slu_class_score_hist")
+
+
 def _offsets_array(offsets):
     off = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
     return off, off.ctypes.data_as(_lib.C.c_void_p)

@@ -149,3 +149,62 @@ def test_whole_mc_block_updates_every_aggregator(cuda):
     df = ua.binned_accuracy(num_bins=10)
     assert abs(df["n"].to_numpy() - n).sum() <= 4          # a pixel within 1e-6 of a coarse edge may move
     assert int(iou.confmat.sum()) == lab.numel() and ece._seen == int(valid.sum())
+
+
+def test_uncertainty_per_class_aggregator(cuda):
+    """Per-class mean is exact (what the reference's plot_iou_sorted_by_uncertainty consumes), quartiles and the
+    expanded dataframe agree with the reference's per-pixel arrays to one histogram bin (1/2048)."""
+    from semanticlidarunc_b200.models.evaluator import UncertaintyPerClassAggregator
+    g = torch.Generator().manual_seed(3)
+    C = 20
+    labels = torch.randint(-1, C + 1, (3, 16, 256), generator=g)
+    unc = torch.rand((3, 16, 256), generator=g) ** 2
+    agg = UncertaintyPerClassAggregator(C)
+    agg.update(labels[:1], unc[:1])
+    agg.update(labels[1:].to(cuda), unc[1:].to(cuda))
+    st = agg.class_stats().set_index("class_id")
+    names = [str(i) for i in range(C)]
+    df = agg.as_dataframe(names, ignore_ids=(0,))
+    assert 0 not in set(df["class_id"]) and set(df["class_id"]) == set(range(1, C))
+    for c in range(C):
+        v = unc[labels == c].double().numpy()
+        assert agg._seen_counts[c] == v.size == int(st.loc[c, "n"])
+        assert abs(st.loc[c, "mean"] - v.mean()) < 1e-7
+        assert abs(st.loc[c, "median"] - np.median(v)) < 0.01      # ~550 samples per class: neighbouring samples are ~0.004 apart
+        if c:
+            assert abs(df[df["class_id"] == c]["uncertainty"].mean() - v.mean()) < 1.0 / 2048
+    agg.reset()
+    assert sum(agg._seen_counts) == 0
+
+
+def test_summary_cache_round_trip(cuda, tmp_path):
+    from semanticlidarunc_b200 import synth
+    from semanticlidarunc_b200.metrics.auroc import AUROCAggregator
+    from semanticlidarunc_b200.models.evaluator import UncertaintyAccuracyAggregator, UncertaintyPerClassAggregator
+    from semanticlidarunc_b200.models.summary_cache import load_summary, save_summary
+    from semanticlidarunc_b200.utils.mc_dropout import mc_reduce_from_logits
+    C = 20
+
+    def fresh():
+        return dict(iou_evaluator=IoUEvaluator(C), ece_eval=ECEAggregator(n_bins=15, mode="probs", ignore_index=0),
+                    auroc_eval=AUROCAggregator(mode="probs", ignore_index=0), auroc_eval_mi=AUROCAggregator(mode="probs", score="mi_norm", ignore_index=0),
+                    ua_agg=UncertaintyAccuracyAggregator(), unc_agg=UncertaintyPerClassAggregator(C))
+    a = fresh()
+    x, lab = synth.synth_mc_logits(31, 4, 1, C, 16, 256)
+    out = mc_reduce_from_logits(x.to(cuda), lab.to(cuda), **{k: v for k, v in a.items() if k != "unc_agg"})
+    a["unc_agg"].update(lab.to(cuda), out["H_norm"])
+    path = str(tmp_path / "summary_epoch_000001.pt")
+    save_summary(path, {"epoch_name": "000001", "num_frames": 1}, **a)
+    b = fresh()
+    cache = load_summary(path, **b)
+    assert cache["meta"]["num_frames"] == 1
+    assert torch.equal(a["iou_evaluator"].confmat, b["iou_evaluator"].confmat)
+    assert a["ece_eval"].compute()[0] == b["ece_eval"].compute()[0]
+    assert a["auroc_eval"].compute()[0] == b["auroc_eval"].compute()[0]
+    assert a["auroc_eval_mi"].compute()[0] == b["auroc_eval_mi"].compute()[0]
+    assert a["ua_agg"].binned_accuracy(10).equals(b["ua_agg"].binned_accuracy(10))
+    assert a["unc_agg"].class_stats().equals(b["unc_agg"].class_stats())
+    import pytest as _pt
+    with _pt.raises(KeyError):
+        from semanticlidarunc_b200.models.summary_cache import restore_summary
+        restore_summary({"meta": {}}, iou_evaluator=IoUEvaluator(C))
