@@ -141,18 +141,40 @@ def get_eu_minus_au_fraction(alpha, eps=None, min_h=None):
 
 @torch.no_grad()
 def evidential_reduce_from_outputs(outputs, labels=None, *, num_classes=None, iou_evaluator=None, ece_eval=None,
+                                   auroc_eval=None, auroc_eval_mi=None, ua_agg=None, unc_agg=None, ua_ignore_ids=(0,),
                                    want=("pred", "conf", "H", "AU", "EU", "MI")):
-    """The whole single-pass Dirichlet branch of Tester.test_epoch (src/models/tester.py:484-512) in one
+    """The whole single-pass Dirichlet branch of Tester.test_epoch (src/models/tester.py:484-516) in one
     kernel: head output [B,C+1,H,W] -> pred, H_norm, AU, EU, MI_norm (+ alpha if asked) and the
-    IoUEvaluator / ECEAggregator(mode='alpha') updates."""
+    IoUEvaluator / ECEAggregator(mode='alpha') updates; the AUROC (entropy and Dirichlet-MI scores, :510-512),
+    accuracy-vs-uncertainty (:502-508) and per-class uncertainty (:516) aggregators are then fed from the small
+    per-pixel maps, so alpha [B,C,H,W] is never materialised."""
     x = _cuda(outputs)
     if num_classes is not None and num_classes + 1 != x.shape[1]:
         x = x[:, : num_classes + 1].contiguous()
     confmat = iou_evaluator._accumulator(x.device) if iou_evaluator is not None else None
     bins = ece_eval._accumulator(x.device) if ece_eval is not None else None
-    return ops.evidential_reduce(x, None if labels is None else _cuda(labels), from_outputs=True,
-                                 temperature=get_alpha_temperature(), eps=get_eps_value(),
-                                 eps_metrics=ece_eval.eps if ece_eval is not None else 1e-12,
-                                 ignore_index=ece_eval.ignore_index if ece_eval is not None else None,
-                                 edges=ece_eval._edges if ece_eval is not None else None,
-                                 confmat=confmat, ece_bins=bins, want=want)
+    need = set(want)
+    if auroc_eval is not None or ua_agg is not None or unc_agg is not None:
+        need |= {"pred", "H"}
+    if auroc_eval_mi is not None:
+        need |= {"pred", "MI"}
+    lab = None if labels is None else _cuda(labels)
+    out = ops.evidential_reduce(x, lab, from_outputs=True,
+                                temperature=get_alpha_temperature(), eps=get_eps_value(),
+                                eps_metrics=ece_eval.eps if ece_eval is not None else 1e-12,
+                                ignore_index=ece_eval.ignore_index if ece_eval is not None else None,
+                                edges=ece_eval._edges if ece_eval is not None else None,
+                                confmat=confmat, ece_bins=bins, want=tuple(need))
+    if lab is not None:
+        lab3 = lab[:, 0] if lab.dim() == 4 else lab
+        # note: the reference's AUROC 'entropy_norm' score in alpha mode clamps p at 1e-12 (auroc.py:48-53) where
+        # probability_helper adds 1e-8 inside the log; both give the same ranking up to ~1e-7 in the score
+        if auroc_eval is not None:
+            auroc_eval.add_maps(out["H"], out["pred"], lab3)
+        if auroc_eval_mi is not None:
+            auroc_eval_mi.add_maps(out["MI"], out["pred"], lab3)
+        if ua_agg is not None:
+            ua_agg.update(labels=lab3, preds=out["pred"], uncertainty=out["H"], ignore_ids=ua_ignore_ids)
+        if unc_agg is not None:
+            unc_agg.update(lab3, out["H"])
+    return out

@@ -32,7 +32,7 @@ def mc_mutual_information_norm(probs: torch.Tensor, eps: float = 1e-12) -> torch
 @torch.no_grad()
 def mc_reduce_from_logits(mc_logits: torch.Tensor, labels: torch.Tensor | None = None, *, eps: float = 1e-12,
                           ignore_index=None, iou_evaluator=None, ece_eval=None, auroc_eval=None, auroc_eval_mi=None,
-                          ua_agg=None, ua_ignore_ids=(0,), want=("pred", "conf", "H_norm", "MI_norm")) -> dict:
+                          ua_agg=None, unc_agg=None, ua_ignore_ids=(0,), want=("pred", "conf", "H_norm", "MI_norm")) -> dict:
     """The whole MC block of Tester.test_epoch (tester.py:412-471) in one pass over the logits.
 
     mc_logits [T,B,C,H,W] straight from `mc_forward`; returns pred / conf / H_norm / MI_norm (and
@@ -47,7 +47,7 @@ def mc_reduce_from_logits(mc_logits: torch.Tensor, labels: torch.Tensor | None =
     if ece_eval is not None and ignore_index is None:
         ignore_index = ece_eval.ignore_index
     need = set(want)
-    if auroc_eval is not None or ua_agg is not None:
+    if auroc_eval is not None or ua_agg is not None or unc_agg is not None:
         need |= {"pred", "H_norm"}
     if auroc_eval_mi is not None:
         need |= {"pred", "MI_norm"}
@@ -61,4 +61,6 @@ def mc_reduce_from_logits(mc_logits: torch.Tensor, labels: torch.Tensor | None =
             auroc_eval_mi.add_maps(out["MI_norm"], out["pred"], lab)
         if ua_agg is not None:
             ua_agg.update(labels=lab, preds=out["pred"], uncertainty=out["H_norm"], ignore_ids=ua_ignore_ids)
+        if unc_agg is not None:
+            unc_agg.update(lab, out["H_norm"])          # tester.py:516
     return out
