@@ -257,11 +257,14 @@ int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
  *   h_flip [B] host bytes (1 = mirror columns and negate y) or NULL;  norm_factor: Scharr scale is 1/norm_factor
  *   outputs (each may be NULL): d_range [B,1,Hd*Wd], d_refl [B,1,..], d_xyz [B,3,..], d_normals [B,3,..]
  *   (needs d_xyz), d_sem [B,1,..] int64 -- the five tensors Dataset.__getitem__ returns, stacked over B.
+ *   d_rowmap [B, Hs+1] int32 workspace or NULL: when given, image rows without any return are dropped before the
+ *   resize (src/dataset/dataloader_semantic_WADS.py:125); rowmap[b][0] returns the number of rows kept.  With
+ *   resize_rows == 0 the output keeps Hs rows, of which the first rowmap[b][0] are valid and the rest zero.
  */
 int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
                       const uint8_t* h_flip, float norm_factor,
                       float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
-                      slu_stream_t stream);
+                      int32_t* d_rowmap, int resize_rows, slu_stream_t stream);
 
 /* Organised clouds (Ouster / SemanticTHAB: the sensor delivers H x W points, pixel n = point n, no projection;
  * src/inference_ouster.py:59-62, documentation/dataset.md:109).

@@ -223,6 +223,32 @@ def gen_other_loaders():
         subs([t.numpy() for t in SemanticTHAB([(fb, fl)], rotate=True, flip=True)[0]], "thab_aug", out)
         out["thab_aug/angle"] = np.array(angle)
         out["thab_aug/np_seed"] = np.array(seed)
+    # WADS: +-pi/2 elevation range, empty rows dropped, 64x1024 target; STF: 5-column file, clip, identity labels
+    from dataset.dataloader_semantic_STF import SemanticSTF
+    from dataset.dataloader_semantic_WADS import SemanticWADS
+    xyzi, raw = synth.synth_scan(25, "tiny")
+    raw = raw.copy()
+    raw[:40] = (raw[:40] & np.uint32(0xFFFF0000)) | np.uint32(110)
+    out["wads/xyzi"], out["wads/raw"] = xyzi, raw
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "0.bin"), os.path.join(d, "0.label")
+        xyzi.tofile(fb); raw.tofile(fl)
+        subs([t.numpy() for t in SemanticWADS([(fb, fl)], projection=(64, 256), resize=True)[0]], "wads", out)
+        r = [t.numpy() for t in SemanticWADS([(fb, fl)], projection=(64, 256), resize=False)[0]]
+        out["wads_native/shape"] = np.array(r[2].shape)
+        for k, a in zip(("range", "reflectivity", "xyz", "normals", "semantics"), r):
+            out[f"wads_native/{k}"] = a
+    rng = np.random.default_rng(26)
+    xyzi, _ = synth.synth_scan(26, "tiny")
+    xyzi = xyzi.copy()
+    xyzi[:300, :3] *= 0.02                                                   # inside the 1.8 m sensor clip
+    five = np.concatenate([xyzi[:, :3], xyzi[:, 3:4] * 255.0, rng.random((xyzi.shape[0], 1))], axis=1).astype(np.float32)
+    lab = rng.integers(0, 22, xyzi.shape[0]).astype(np.uint32)
+    out["stf/five"], out["stf/label"] = five, lab
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "0.bin"), os.path.join(d, "0.label")
+        five.tofile(fb); lab.tofile(fl)
+        subs([t.numpy() for t in SemanticSTF([(fb, fl)], projection=(16, 256), resize=True, remap_adverse_label=True, clip=True)[0]], "stf", out)
     np.savez_compressed(os.path.join(GOLD, "other_loaders.npz"), **out)
 
 

@@ -157,18 +157,21 @@ def build_normal_xyz(xyz, norm_factor=0.25):
 
 
 def kitti_item(xyzi, raw_label, lut, projection=(64, 2048), resize=True, flip=False, yaw_deg=None,
-               theta_range=None, normalise_reflectivity=False):
+               theta_range=None, normalise_reflectivity=False, drop_empty_rows=False, resize_to=(2048, 128)):
     """SemanticKitti.__getitem__ (src/dataset/dataloader_semantic_KITTI.py:31-99) with the random draws
     (yaw angle :53, flip coin :71) passed in.  Returns the five arrays in the reference's order/dtypes.
-    theta_range / normalise_reflectivity give SemanticCUDAL.__getitem__ (dataloader_semantic_CUDAL.py:70-125)."""
+    theta_range / normalise_reflectivity give SemanticCUDAL.__getitem__ (dataloader_semantic_CUDAL.py:70-125);
+    drop_empty_rows / resize_to=(1024, 64) give SemanticWADS.__getitem__ (dataloader_semantic_WADS.py:96-155)."""
     import cv2
     sem = lut[(raw_label & 0xFFFF).astype(np.int64)].astype(np.int64)
     pc = np.concatenate([xyzi, sem[..., np.newaxis]], axis=-1)
     if yaw_deg is not None:
         pc[..., 0:3] = rotate_z(pc[..., 0:3].reshape(-1, 3), float(yaw_deg))
     img, _, _, _ = spherical_projection(pc, projection[0], projection[1], theta_range=theta_range)
+    if drop_empty_rows:
+        img = img[~np.all(np.linalg.norm(img, axis=-1) == 0, axis=1)]            # WADS :125
     if resize:
-        img = cv2.resize(img, (2048, 128), interpolation=cv2.INTER_NEAREST)
+        img = cv2.resize(img, tuple(resize_to), interpolation=cv2.INTER_NEAREST)
     if flip:
         img = img[:, ::-1, :]
         img[..., 1] *= -1

@@ -45,7 +45,7 @@ SIGNATURES = {
                                _p, _p, _p, _p, _p, _p, _p]),
     "slu_project_points": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p]),
     "slu_organized_planes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
-    "slu_frame_tensors": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p]),
+    "slu_frame_tensors": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _i, _p]),
     "slu_backproject": (_i, [_p, _p, _p, _i64, _i, _i64, _p, _p]),
     "slu_diag_read_stream": (_i, [_p, _i64, _p, _p]),
 }

@@ -26,6 +26,8 @@ struct FrameParams {
     double ify, ifx;         // OpenCV's inverse scale factors
     unsigned long long flip_bits[4];   // bit b = flip scan b (B <= 256)
     float tap_c, tap_s;      // Scharr smoothing taps (10, 3) * scale
+    const int* rowmap;       // [B, Hs+1]: count, then the source rows kept (drop_empty_rows) or NULL
+    int keep_native_h;       // no resize requested: output row r <- kept row r, rows beyond the count are zero
     float* range;            // [B,1,Hd*Wd]
     float* refl;             // [B,1,Hd*Wd]
     float* xyz;              // [B,3,Hd*Wd]
@@ -38,25 +40,59 @@ __global__ void __launch_bounds__(FR_THREADS) frame_resample_kernel(const __grid
     const long long HWs = (long long)p.Hs * p.Ws, HWd = (long long)p.Hd * p.Wd;
     const bool flip = (p.flip_bits[b >> 6] >> (b & 63)) & 1ull;
     const float* src = p.img + (long long)b * 6 * HWs;
+    // WADS drops image rows without any return before resizing (dataloader_semantic_WADS.py:125): the
+    // source height is then the per-scan count of kept rows and source rows go through the row map
+    const int* rmap = p.rowmap ? p.rowmap + (long long)b * (p.Hs + 1) : nullptr;
+    const int hs_eff = rmap ? rmap[0] : p.Hs;
+    const int hd_eff = p.keep_native_h ? hs_eff : p.Hd;
+    const double ify = rmap ? (hs_eff > 0 ? 1.0 / ((double)hd_eff / (double)hs_eff) : 0.0) : p.ify;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HWd; i += (long long)gridDim.x * blockDim.x) {
         const int yd = (int)(i / p.Wd);
         int xd = (int)(i - (long long)yd * p.Wd);
         if (flip) xd = p.Wd - 1 - xd;                                   // resized[:, ::-1]
-        int ys = (int)floor((double)yd * p.ify), xs = (int)floor((double)xd * p.ifx);
-        ys = ys < p.Hs - 1 ? ys : p.Hs - 1;
+        int ys = (int)floor((double)yd * ify), xs = (int)floor((double)xd * p.ifx);
+        ys = ys < hs_eff - 1 ? ys : hs_eff - 1;
         xs = xs < p.Ws - 1 ? xs : p.Ws - 1;
-        const long long s = (long long)ys * p.Ws + xs;
-        const float x = src[s], z = src[2 * HWs + s];
-        float y = src[HWs + s];
+        const bool empty = hs_eff <= 0 || yd >= hd_eff;
+        if (rmap && !empty) ys = rmap[1 + ys];
+        const long long s = empty ? 0 : (long long)ys * p.Ws + xs;
+        const float x = empty ? 0.f : src[s], z = empty ? 0.f : src[2 * HWs + s];
+        float y = empty ? 0.f : src[HWs + s];
         if (flip) y = -y;                                               // :73
         const long long o = (long long)b * HWd + i;
         if (p.xyz) {
             float* q = p.xyz + (long long)b * 3 * HWd + i;
             q[0] = x; q[HWd] = y; q[2 * HWd] = z;
         }
-        if (p.range) p.range[o] = src[3 * HWs + s];
-        if (p.refl) p.refl[o] = src[4 * HWs + s];
-        if (p.sem) p.sem[o] = (long long)src[5 * HWs + s];
+        if (p.range) p.range[o] = empty ? 0.f : src[3 * HWs + s];
+        if (p.refl) p.refl[o] = empty ? 0.f : src[4 * HWs + s];
+        if (p.sem) p.sem[o] = empty ? 0ll : (long long)src[5 * HWs + s];
+    }
+}
+
+// rows with at least one non-zero x, y, z, intensity or label value (the reference tests the 5-channel norm)
+__global__ void __launch_bounds__(FR_THREADS) frame_rowmap_kernel(const float* __restrict__ img, int Hs, int Ws, int* __restrict__ rowmap) {
+    extern __shared__ int s_flag[];
+    const int b = blockIdx.x;
+    const long long HWs = (long long)Hs * Ws;
+    const float* src = img + (long long)b * 6 * HWs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int r = warp; r < Hs; r += nwarp) {
+        bool any = false;
+        for (int x = lane; x < Ws && !any; x += 32) {
+            const long long s = (long long)r * Ws + x;
+            any = src[s] != 0.f || src[HWs + s] != 0.f || src[2 * HWs + s] != 0.f || src[4 * HWs + s] != 0.f || src[5 * HWs + s] != 0.f;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (lane == 0) s_flag[r] = any ? 1 : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int* m = rowmap + (long long)b * (Hs + 1);
+        int n = 0;
+        for (int r = 0; r < Hs; ++r)
+            if (s_flag[r]) m[1 + n++] = r;
+        m[0] = n;
     }
 }
 
@@ -72,9 +108,12 @@ __global__ void __launch_bounds__(FR_THREADS) frame_normals_kernel(const __grid_
     const long long HW = (long long)p.Hd * p.Wd;
     const float* base = p.xyz + (long long)b * 3 * HW;
     float* out = p.normals + (long long)b * 3 * HW;
+    // with dropped rows and no resize the image really has rowmap[0] rows: reflect at that border
+    const int h_eff = (p.rowmap && p.keep_native_h) ? p.rowmap[(long long)b * (p.Hs + 1)] : p.Hd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
         const int y = (int)(i / p.Wd), x = (int)(i - (long long)y * p.Wd);
-        const int ym = reflect101(y - 1, p.Hd), yp = reflect101(y + 1, p.Hd);
+        if (y >= h_eff) { out[i] = 0.f; out[HW + i] = 0.f; out[2 * HW + i] = 0.f; continue; }
+        const int ym = reflect101(y - 1, h_eff), yp = reflect101(y + 1, h_eff);
         const int xm = reflect101(x - 1, p.Wd), xp = reflect101(x + 1, p.Wd);
         float gx[3], gy[3];                      // d/dx and d/dy of the planes x, y, z
 #pragma unroll
@@ -185,7 +224,7 @@ extern "C" int slu_organized_planes(const float* d_xyzi, const uint32_t* d_raw_l
 extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
                                  const uint8_t* h_flip, float norm_factor,
                                  float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
-                                 slu_stream_t stream) {
+                                 int32_t* d_rowmap, int resize_rows, slu_stream_t stream) {
     using namespace slu;
     if (!d_img) return fail(SLU_E_ARG, "d_img is NULL");
     if (B < 1 || B > 256) return fail(SLU_E_RANGE, "B=%d outside [1,256]", B);
@@ -202,8 +241,16 @@ extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int 
     p.tap_c = 10.0f * scale; p.tap_s = 3.0f * scale;
     p.range = d_range; p.refl = d_refl; p.xyz = d_xyz; p.normals = d_normals;
     p.sem = reinterpret_cast<long long*>(d_sem);
+    p.rowmap = d_rowmap;
+    p.keep_native_h = (d_rowmap && !resize_rows) ? 1 : 0;
+    if (p.keep_native_h && Hd != Hs) return fail(SLU_E_ARG, "without a row resize the output must have Hs rows");
+    if (d_rowmap && Hs > 8192) return fail(SLU_E_RANGE, "Hs=%d too large for row compaction", Hs);
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    if (d_rowmap) {
+        frame_rowmap_kernel<<<B, FR_THREADS, sizeof(int) * Hs, reinterpret_cast<cudaStream_t>(stream)>>>(d_img, Hs, Ws, d_rowmap);
+        SLU_LAUNCH_CHECK("frame_rowmap_kernel");
+    }
     const long long HWd = (long long)Hd * Wd;
     long long gx = (HWd + FR_THREADS - 1) / FR_THREADS;
     const long long cap = (8LL * sms + B - 1) / B;

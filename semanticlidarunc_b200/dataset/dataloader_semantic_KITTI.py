@@ -47,8 +47,7 @@ class SemanticKitti(Dataset):
             self._lut = torch.from_numpy(self._lut_host).to(dev)
         return dev
 
-    @staticmethod
-    def read_scan(frame_path, label_path):
+    def read_scan(self, frame_path, label_path):
         """The on-disk pair: float32 [N,4] x,y,z,intensity and uint32 [N] (semantic id | instance << 16)."""
         xyzi = np.fromfile(frame_path, dtype=np.float32).reshape(-1, 4)
         label = np.fromfile(label_path, dtype=np.uint32).reshape(-1)
@@ -64,9 +63,12 @@ class SemanticKitti(Dataset):
         proj = ops.project_batch(xyzi, raw, offs, self.projection[0], self.projection[1], lut=self._lut, yaw_deg=yaw_deg,
                                  theta_range=self.THETA_RANGE, want_label=False)
         missing = proj["diag"][:, 0]
-        out = ops.frame_tensors(proj["img"], out_hw=self.RESIZE_TO if self.resize else None, flip=flip)
+        out = self._frame(proj["img"], flip)
         out["pix"], out["offsets"], out["missing_label_ids"] = proj["pix"], offs, missing
         return self._finish(out)
+
+    def _frame(self, img, flip):
+        return ops.frame_tensors(img, out_hw=self.RESIZE_TO if self.resize else None, flip=flip)
 
     def _finish(self, out):
         return out

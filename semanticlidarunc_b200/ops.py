@@ -415,10 +415,12 @@ def organized_planes(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], H: i
     return {"img": img, "missing": missing}
 
 
-def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True) -> dict:
+def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True,
+                  drop_empty_rows: bool = False) -> dict:
     """Loader glue on the device (slu_frame_tensors): img [B,6,H,W] planes -> the loaders' five tensors,
     stacked over B: range [B,1,h,w], reflectivity [B,1,h,w], xyz [B,3,h,w], normals [B,3,h,w], semantics
-    [B,1,h,w] int64.  out_hw=(h,w) resizes with cv2's INTER_NEAREST rule; flip: per-scan booleans."""
+    [B,1,h,w] int64.  out_hw=(h,w) resizes with cv2's INTER_NEAREST rule; flip: per-scan booleans;
+    drop_empty_rows removes image rows without any return first (WADS) and adds "rows_kept" [B] int32."""
     _lib.require_cuda()
     img = _lib.as_buffer(img, torch.float32, "img")
     if img.dim() != 4 or img.size(1) != 6:
@@ -435,10 +437,14 @@ def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float 
            "xyz": torch.empty((B, 3, Hd, Wd), dtype=torch.float32, device=dev),
            "normals": torch.empty((B, 3, Hd, Wd), dtype=torch.float32, device=dev) if want_normals else None,
            "semantics": torch.empty((B, 1, Hd, Wd), dtype=torch.int64, device=dev)}
+    rowmap = torch.empty((B, Hs + 1), dtype=torch.int32, device=dev) if drop_empty_rows else None
     rc = _lib.lib().slu_frame_tensors(_lib.ptr(img), B, Hs, Ws, Hd, Wd, h_flip, float(norm_factor),
                                       _lib.ptr(out["range"]), _lib.ptr(out["reflectivity"]), _lib.ptr(out["xyz"]),
-                                      _lib.ptr(out["normals"]), _lib.ptr(out["semantics"]), _lib.stream_ptr())
+                                      _lib.ptr(out["normals"]), _lib.ptr(out["semantics"]), _lib.ptr(rowmap),
+                                      int(out_hw is not None), _lib.stream_ptr())
     _lib.check(rc, "slu_frame_tensors")
+    if drop_empty_rows:
+        out["rows_kept"] = rowmap[:, 0]
     return out
 
 

@@ -92,7 +92,7 @@ def test_frame_loss_evidential_hist_outputs_stay_in_bounds(cuda):
     flip = np.array([1, 0, 1], dtype=np.uint8)
     rc = _lib.lib().slu_frame_tensors(_lib.ptr(img), B, H, W, 9, 101, flip.ctypes.data_as(_lib.C.c_void_p), 0.25,
                                       _lib.ptr(o["range"].win), _lib.ptr(o["refl"].win), _lib.ptr(o["xyz"].win),
-                                      _lib.ptr(o["nrm"].win), _lib.ptr(o["sem"].win), _lib.stream_ptr())
+                                      _lib.ptr(o["nrm"].win), _lib.ptr(o["sem"].win), None, 1, _lib.stream_ptr())
     _lib.check(rc, "slu_frame_tensors")
     alpha = torch.rand((B, C, H, W), device=cuda) * 5 + 1
     tgt = torch.randint(0, C, (B, H, W), device=cuda)

@@ -158,3 +158,39 @@ def test_thab_organised_cloud_vs_reference(cuda, golden):
     # rotated coordinates: np.dot's float64 accumulation is BLAS-specific, so float32(xyz) may differ in the last bit
     assert np.abs(xyz[:, ::4, ::16] - g["thab_aug/xyz_sub"]).max() <= 1e-5
     assert np.abs(rng[:, ::4, ::16] - g["thab_aug/range_sub"]).max() <= 1e-5
+
+
+def test_wads_getitem_drops_empty_rows_like_reference(cuda, golden):
+    from semanticlidarunc_b200.dataset.dataloader_semantic_WADS import SemanticWADS
+    g = golden("other_loaders.npz")
+    with tempfile.TemporaryDirectory() as d:
+        paths = write_pair(d, g["wads/xyzi"], g["wads/raw"])
+        rng, refl, xyz, normals, sem = (t.numpy() for t in SemanticWADS(paths, projection=(64, 256), resize=True)[0])
+        assert xyz.shape == (3, 64, 1024) and 20 in np.unique(sem)
+        for a, k in ((rng, "range"), (refl, "reflectivity"), (xyz, "xyz"), (sem, "semantics")):
+            assert sha(a) == bytes(g["wads/" + k + "_sha"]).hex(), k
+        m = normals_condition_mask(xyz)[::4, ::16]
+        assert np.abs(normals[:, ::4, ::16].astype(np.float64) - g["wads/normals_sub"])[:, m].max() <= 5e-5
+        # without the resize the image keeps only the rows that received points (variable height)
+        rng, refl, xyz, normals, sem = (t.numpy() for t in SemanticWADS(paths, projection=(64, 256), resize=False)[0])
+    assert xyz.shape == tuple(g["wads_native/shape"])
+    for a, k in ((rng, "range"), (refl, "reflectivity"), (xyz, "xyz"), (sem, "semantics")):
+        assert np.array_equal(a, g["wads_native/" + k]), k
+    m = normals_condition_mask(xyz)
+    assert np.abs(normals.astype(np.float64) - g["wads_native/normals"])[:, m].max() <= 5e-5
+
+
+def test_stf_getitem_vs_reference(cuda, golden):
+    from semanticlidarunc_b200.dataset.dataloader_semantic_STF import SemanticSTF
+    g = golden("other_loaders.npz")
+    with tempfile.TemporaryDirectory() as d:
+        fb, fl = os.path.join(d, "0.bin"), os.path.join(d, "0.label")
+        g["stf/five"].tofile(fb)
+        g["stf/label"].tofile(fl)
+        ds = SemanticSTF([(fb, fl)], projection=(16, 256), resize=True, remap_adverse_label=True, clip=True)
+        rng, refl, xyz, normals, sem = (t.numpy() for t in ds[0])
+    for a, k in ((rng, "range"), (refl, "reflectivity"), (xyz, "xyz"), (sem, "semantics")):
+        assert sha(a) == bytes(g["stf/" + k + "_sha"]).hex(), k
+    assert 20 not in np.unique(sem) and 21 in np.unique(sem)
+    m = normals_condition_mask(xyz)[::4, ::16]
+    assert np.abs(normals[:, ::4, ::16].astype(np.float64) - g["stf/normals_sub"])[:, m].max() <= 5e-5

@@ -208,3 +208,18 @@ def test_cudal_and_thab_items_oracle_vs_golden(golden):
         r = oproj.thab_item(xyzi, raw, build_id_lut(), **kw)
         for k, a in zip(names, r):
             assert sha(a) == bytes(g[f"{tag}/{k}_sha"]).hex(), (tag, k)
+
+
+def test_wads_item_oracle_vs_golden(golden):
+    import hashlib
+    from semanticlidarunc_b200.dataset.dataloader_semantic_WADS import id_map as wads_map
+    g = golden("other_loaders.npz")
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    names = ("range", "reflectivity", "xyz", "normals", "semantics")
+    kw = dict(projection=(64, 256), theta_range=[-np.pi / 2, np.pi / 2], drop_empty_rows=True, resize_to=(1024, 64))
+    r = oproj.kitti_item(g["wads/xyzi"], g["wads/raw"], build_id_lut(wads_map), resize=True, **kw)
+    for k, a in zip(names, r):
+        assert sha(a) == bytes(g[f"wads/{k}_sha"]).hex(), k
+    r = oproj.kitti_item(g["wads/xyzi"], g["wads/raw"], build_id_lut(wads_map), resize=False, **kw)
+    for k, a in zip(names, r):
+        assert np.array_equal(a, g[f"wads_native/{k}"]), k
