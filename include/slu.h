@@ -167,6 +167,41 @@ int slu_dirichlet_term(const float* d_alpha, const int64_t* d_target, const uint
                        int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
                        int term, float eps, float s_ref, double* d_sums, float* d_grad, slu_stream_t stream);
 
+/* Remaining evidential terms / regularisers, one per call, forward + analytic backward.
+ * Replaces: ComplementKLUniform (src/losses/dirichlet_losses.py:228-314), WrongLowEvidence
+ *           (src/losses/regularizers.py:218-289), EvidenceRegBand (:116-147), EvidenceReg (:149-212),
+ *           KL_offClasses_to_uniform with_conf_weighting=True (:369-383).
+ *   h_params (host floats, n_params must match the term):
+ *     SLU_TERM_COMP_KL    7: gamma, tau, sigma, s_target (< 0 = none), normalize (0/1), eps, detach_uncert (0/1)
+ *     SLU_TERM_WRONG_LOW  4: s_low, margin, soft_margin_k, eps
+ *     SLU_TERM_EVID_BAND  2: s_target, band
+ *     SLU_TERM_EVID_REG   4: s_target, mode (0 log_squared | 1 one_sided | 2 l2), margin, scale_correct (0/1)
+ *     SLU_TERM_KL_CONF    2: gamma, eps
+ *   d_target may be NULL for EVID_BAND / EVID_REG (then every pixel is valid unless d_keep_mask says otherwise).
+ *   d_sums [2] float64, ADDED to: sum of per-pixel values | the term's denominator (valid pixels; sum of gates
+ *   for WRONG_LOW; sum of weights for KL_CONF);  d_grad [B,C,HW] or NULL = d(per-pixel value)/d(alpha), 0 on masked
+ *   pixels.  The caller divides by the reference's clamp of the denominator.
+ */
+#define SLU_TERM_COMP_KL    5
+#define SLU_TERM_WRONG_LOW  6
+#define SLU_TERM_EVID_BAND  7
+#define SLU_TERM_EVID_REG   8
+#define SLU_TERM_KL_CONF    9
+int slu_evidence_term(const float* d_alpha, const int64_t* d_target, const uint8_t* d_keep_mask,
+                      int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                      int term, const float* h_params, int n_params,
+                      double* d_sums, float* d_grad, slu_stream_t stream);
+
+/* LogitRegularizer (src/losses/regularizers.py:75-110): per element z^2, or relu(z - threshold)^2 when
+ * use_threshold != 0, over d_logits [B,Cz,HW] with a per-pixel validity mask (d_target / d_keep_mask may both
+ * be NULL = all valid).  d_sums [2] float64 ADDED to: sum over valid elements | number of valid PIXELS (the
+ * reference divides the element sum by the pixel count when a mask is given, by the element count otherwise).
+ * d_grad [B,Cz,HW] or NULL.
+ */
+int slu_logit_regularizer(const float* d_logits, const int64_t* d_target, const uint8_t* d_keep_mask,
+                          int B, int Cz, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                          int use_threshold, float threshold, double* d_sums, float* d_grad, slu_stream_t stream);
+
 /* Diagnostic: d_out[3i..3i+2] = lgamma, digamma, trigamma of d_in[i] (> 0) as the loss kernels evaluate them. */
 int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_stream_t stream);
 

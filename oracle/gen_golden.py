@@ -395,9 +395,60 @@ def gen_losses():
     np.savez_compressed(os.path.join(GOLD, "losses.npz"), **out)
 
 
+def gen_loss_terms():
+    """The remaining terms, run through the unmodified reference modules + autograd."""
+    from losses.dirichlet_losses import ComplementKLUniform
+    from losses.regularizers import (EvidenceReg, EvidenceRegBand, KL_offClasses_to_uniform, LogitRegularizer,
+                                     WrongLowEvidence)
+
+    g = torch.Generator().manual_seed(505)
+    B, C, H, W = 2, 20, 4, 32
+    alpha = (torch.nn.functional.softplus(torch.randn((B, C, H, W), generator=g) * 3.0) + 1.0)
+    target = torch.randint(0, C, (B, H, W), generator=g)
+    # make ~half of the pixels "correct" so WrongLowEvidence / the complement gate see both kinds
+    fix = torch.rand((B, H, W), generator=g) < 0.5
+    target = torch.where(fix, alpha.argmax(dim=1), target)
+    logits = torch.randn((B, C + 1, H, W), generator=g) * 4.0
+    keep = torch.rand((B, H, W), generator=g) > 0.3
+    out = {"alpha": alpha.numpy(), "target": target.numpy(), "logits": logits.numpy(), "keep": keep.numpy()}
+
+    def run(name, fn, x):
+        x = x.clone().requires_grad_(True)
+        loss = fn(x)
+        (grad,) = torch.autograd.grad(loss, x)
+        out[name + "/loss"] = loss.detach().numpy()
+        out[name + "/grad"] = grad.numpy()
+
+    run("comp", lambda a: ComplementKLUniform(ignore_index=0)(a, target), alpha)
+    run("comp_trainer", lambda a: ComplementKLUniform(ignore_index=0, gamma=1.25, tau=0.65, sigma=0.15)(a, target), alpha)   # trainer.py:339
+    run("comp_evid_gate", lambda a: ComplementKLUniform(ignore_index=0, s_target=40.0, normalize=False)(a, target), alpha)
+    run("comp_attached", lambda a: ComplementKLUniform(ignore_index=0, detach_uncert=False)(a, target), alpha)
+    run("wle", lambda a: WrongLowEvidence(ignore_index=0, s_low=0.0, margin=0.05, soft_margin_k=0.08)(a, target), alpha)  # trainer.py:376-381
+    run("wle_hard", lambda a: WrongLowEvidence(ignore_index=0, s_low=2.0, margin=0.1, soft_margin_k=0.0)(a, target), alpha)
+    run("wle_nomargin", lambda a: WrongLowEvidence(ignore_index=None, margin=0.0)(a, target), alpha)
+    run("band", lambda a: EvidenceRegBand(60.0, band=0.10, ignore_index=0)(a, target=target), alpha)
+    run("band_mask", lambda a: EvidenceRegBand(200.0, band=0.25)(a, mask=keep), alpha)
+    run("band_nomask", lambda a: EvidenceRegBand(30.0)(a), alpha)
+    run("ereg_log", lambda a: EvidenceReg(60.0, ignore_index=0)(a, target=target), alpha)
+    run("ereg_log_sc", lambda a: EvidenceReg(60.0, scale_correct=True)(a, mask=keep), alpha)
+    run("ereg_one_sided", lambda a: EvidenceReg(60.0, mode="one_sided", margin=0.2, ignore_index=(0, 3))(a, target=target), alpha)
+    run("ereg_l2", lambda a: EvidenceReg(60.0, mode="l2")(a), alpha)
+    run("klw", lambda a: KL_offClasses_to_uniform(ignore_index=0, with_conf_weighting=True, gamma=1.0)(a, target), alpha)
+    run("klw_g2", lambda a: KL_offClasses_to_uniform(ignore_index=0, with_conf_weighting=True, gamma=2.0)(a, target), alpha)
+    run("logit", lambda z: LogitRegularizer()(z), logits)
+    run("logit_thr_target", lambda z: LogitRegularizer(threshold=3.0, ignore_index=0)(z, target=target), logits)
+    run("logit_mask", lambda z: LogitRegularizer(threshold=None)(z, mask=keep), logits)
+    run("logit_target_noignore", lambda z: LogitRegularizer(threshold=1.0)(z, target=target), logits)
+    np.savez_compressed(os.path.join(GOLD, "loss_terms.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)
+    if len(sys.argv) > 1:                      # regenerate selected files only: python oracle/gen_golden.py loss_terms
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        return
     manifest = {
         "generator": "oracle/gen_golden.py",
         "reference_root": _refshim.REF_ROOT,
@@ -411,6 +462,7 @@ def main():
     gen_evidential()
     gen_metrics()
     gen_losses()
+    gen_loss_terms()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     for fn in sorted(os.listdir(GOLD)):

@@ -54,3 +54,53 @@ class _DirichletSingleTerm(torch.autograd.Function):
     def backward(ctx, grad_out):
         g, n = ctx.saved_tensors
         return g * (grad_out.double() / n).to(g.dtype), None, None, None, None, None
+
+
+def _ids_and_keep(target, ignore_index, mask=None):
+    """(ignored ids, keep mask) from the reference's two ways of masking: `ignore_index` on target, or `mask=`."""
+    if mask is not None:
+        return (), mask
+    if target is None:
+        return (), None
+    ids, keep = split_ignore(ignore_index)
+    if len(ids) > MAX_IDS:
+        keep = ~torch.isin(target, torch.as_tensor(ids, device=target.device, dtype=target.dtype))
+        ids = ()
+    return ids, keep
+
+
+class _EvidenceTerm(torch.autograd.Function):
+    """ops.TERM_COMP_KL / WRONG_LOW / EVID_BAND / EVID_REG / KL_CONF: value = sums[0] / max(sums[1], denom_min)."""
+
+    @staticmethod
+    def forward(ctx, alpha, target, term: int, params, ids, keep, denom_min: float):
+        r = ops.evidence_term(alpha.detach(), target, term, params, ignore=ids, keep_mask=keep,
+                              want_grad=ctx.needs_input_grad[0])
+        n = r["sums"][1].clamp_min(denom_min)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(r["grad"], n)
+        return (r["sums"][0] / n).to(alpha.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g, n = ctx.saved_tensors
+        return g * (grad_out.double() / n).to(g.dtype), None, None, None, None, None, None
+
+
+class _LogitReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, threshold, ids, keep):
+        r = ops.logit_regularizer(logits.detach(), threshold=threshold, target=target, ignore=ids, keep_mask=keep,
+                                  want_grad=ctx.needs_input_grad[0])
+        if target is None and keep is None:           # no mask: plain mean over every element (regularizers.py:63-64)
+            n = torch.full((), float(logits.numel()), dtype=torch.float64, device=logits.device)
+        else:                                         # masked: element sum over the number of valid PIXELS (:65-69)
+            n = r["sums"][1].clamp_min(1e-8)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(r["grad"], n)
+        return (r["sums"][0] / n).to(logits.dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g, n = ctx.saved_tensors
+        return g * (grad_out.double() / n).to(g.dtype), None, None, None, None

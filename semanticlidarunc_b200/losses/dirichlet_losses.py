@@ -3,7 +3,7 @@ by libslu's fused forward+backward kernel (csrc/slu_loss.cu).  `_valid_mask` mir
 
 `NLLDirichletCategorical` (:73-119), `DigammaDirichletCE` (:122-167) and `BrierDirichlet` (:174-220) -- weight
 0 in every shipped config (src/configs/SemanticKitti_default.yaml:50-62) -- run on the single-term kernel
-(slu_dirichlet_term).  `ComplementKLUniform` (:228-314) is not on the device path yet.
+(slu_dirichlet_term), `ComplementKLUniform` (:228-314) on slu_evidence_term.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ._function import _DirichletSingleTerm, _DirichletTerm
+from ._function import _DirichletSingleTerm, _DirichletTerm, _EvidenceTerm, _ids_and_keep
 from ._mask import _valid_mask  # noqa: F401  (re-exported, the reference Trainer imports it from here)
 
 
@@ -75,3 +75,28 @@ class BrierDirichlet(nn.Module):
 
     def forward(self, alpha: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         return _DirichletSingleTerm.apply(alpha, _prep(target), ops.TERM_BRIER, self.ignore_index, self.eps, self.s_ref)
+
+
+class ComplementKLUniform(nn.Module):
+    """KL(off-class conditional || uniform) gated by (1-p_y)^gamma * sigmoid((tau-p_y)/sigma) (:228-314)."""
+
+    def __init__(self, ignore_index: Optional[int] = 0, gamma: float = 2.0, tau: float = 0.55, sigma: float = 0.12,
+                 s_target: Optional[float] = None, normalize: bool = True, eps: float = 1e-8, detach_uncert: bool = True):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.gamma = float(gamma)
+        self.tau = float(tau)
+        self.sigma = float(sigma)
+        self.s_target = s_target
+        self.normalize = bool(normalize)
+        self.eps = eps
+        self.detach_uncert = bool(detach_uncert)
+
+    def forward(self, alpha: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        target = _prep(target)
+        if alpha.shape[1] <= 2:                       # the reference returns an exact zero here (:275-276)
+            return alpha.sum() * 0.0
+        ids, keep = _ids_and_keep(target, self.ignore_index)
+        prm = (self.gamma, self.tau, self.sigma, -1.0 if self.s_target is None else float(self.s_target),
+               float(self.normalize), self.eps, float(self.detach_uncert))
+        return _EvidenceTerm.apply(alpha, target, ops.TERM_COMP_KL, prm, ids, keep, 1.0)

@@ -200,6 +200,64 @@ def dirichlet_term(alpha: torch.Tensor, target: torch.Tensor, term: int, *, igno
     return {"sums": sums, "grad": grad}
 
 
+TERM_COMP_KL, TERM_WRONG_LOW, TERM_EVID_BAND, TERM_EVID_REG, TERM_KL_CONF = 5, 6, 7, 8, 9
+
+
+def _mask_args(target, keep_mask, ignore, shape, device):
+    B, H, W = shape
+    if target is not None:
+        if target.dim() == 4 and target.size(1) == 1:
+            target = target[:, 0]
+        if tuple(target.shape) != (B, H, W):
+            raise ValueError(f"target shape {tuple(target.shape)} != {(B, H, W)}")
+        target = _lib.as_buffer(target.to(device), torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask.to(device), torch.bool, "keep_mask")
+        if keep_mask.numel() != B * H * W:
+            raise ValueError("keep_mask must have B*H*W elements")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    return target, keep_mask, h_ign, len(ign)
+
+
+def evidence_term(alpha: torch.Tensor, target: Optional[torch.Tensor], term: int, params, *, ignore=(),
+                  keep_mask: Optional[torch.Tensor] = None, want_grad: bool = True) -> dict:
+    """One of the TERM_COMP_KL / WRONG_LOW / EVID_BAND / EVID_REG / KL_CONF terms (slu_evidence_term):
+    sums float64[2] (sum of per-pixel values | the term's denominator) and grad [B,C,H,W]."""
+    _lib.require_cuda()
+    alpha = _lib.as_buffer(alpha, torch.float32, "alpha")
+    if alpha.dim() != 4:
+        raise ValueError("alpha must be [B,C,H,W]")
+    B, Cc, H, W = alpha.shape
+    target, keep_mask, h_ign, n_ign = _mask_args(target, keep_mask, ignore, (B, H, W), alpha.device)
+    prm = (_lib.C.c_float * len(params))(*[float(v) for v in params])
+    sums = torch.zeros(2, dtype=torch.float64, device=alpha.device)
+    grad = torch.empty_like(alpha) if want_grad else None
+    rc = _lib.lib().slu_evidence_term(_lib.ptr(alpha), _lib.ptr(target), _lib.ptr(keep_mask), B, Cc, H * W, h_ign, n_ign,
+                                      int(term), prm, len(params), _lib.ptr(sums), _lib.ptr(grad), _lib.stream_ptr())
+    _lib.check(rc, "slu_evidence_term")
+    return {"sums": sums, "grad": grad}
+
+
+def logit_regularizer(logits: torch.Tensor, *, threshold: Optional[float] = None, target: Optional[torch.Tensor] = None,
+                      ignore=(), keep_mask: Optional[torch.Tensor] = None, want_grad: bool = True) -> dict:
+    """z^2 or relu(z - threshold)^2 summed over valid elements (slu_logit_regularizer): sums float64[2]
+    (element sum | valid pixels) and grad [B,Cz,H,W]."""
+    _lib.require_cuda()
+    logits = _lib.as_buffer(logits, torch.float32, "logits")
+    if logits.dim() != 4:
+        raise ValueError("logits must be [B,C,H,W]")
+    B, Cz, H, W = logits.shape
+    target, keep_mask, h_ign, n_ign = _mask_args(target, keep_mask, ignore, (B, H, W), logits.device)
+    sums = torch.zeros(2, dtype=torch.float64, device=logits.device)
+    grad = torch.empty_like(logits) if want_grad else None
+    rc = _lib.lib().slu_logit_regularizer(_lib.ptr(logits), _lib.ptr(target), _lib.ptr(keep_mask), B, Cz, H * W, h_ign, n_ign,
+                                          int(threshold is not None), float(threshold or 0.0), _lib.ptr(sums),
+                                          _lib.ptr(grad), _lib.stream_ptr())
+    _lib.check(rc, "slu_logit_regularizer")
+    return {"sums": sums, "grad": grad}
+
+
 def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse: float = 1.0, w_kl: float = 0.05,
                           ignore=(), keep_mask: Optional[torch.Tensor] = None, temperature: float = 1.0,
                           eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True) -> dict:

@@ -125,3 +125,45 @@ def test_frame_loss_evidential_hist_outputs_stay_in_bounds(cuda):
         for k, v in d.items():
             assert v.intact(), k
     assert gm.intact() and gk.intact() and sums.intact() and cm.intact() and bins.intact()
+
+
+def test_loss_term_outputs_stay_in_bounds(cuda):
+    """slu_evidence_term (all five terms), slu_dirichlet_term, slu_logit_regularizer on a ragged shape."""
+    B, C, H, W = 3, 13, 5, 77
+    alpha = torch.rand((B, C, H, W), device=cuda) * 5 + 1
+    tgt = torch.randint(0, C, (B, H, W), device=cuda)
+    ign = (_lib.C.c_int64 * 1)(0)
+    prms = {ops.TERM_COMP_KL: (2.0, 0.55, 0.12, -1.0, 1.0, 1e-8, 1.0), ops.TERM_WRONG_LOW: (0.0, 0.05, 0.08, 1e-8),
+            ops.TERM_EVID_BAND: (30.0, 0.1), ops.TERM_EVID_REG: (30.0, 0.0, 0.1, 0.0), ops.TERM_KL_CONF: (1.0, 1e-8)}
+    guards = []
+    for term, prm in prms.items():
+        g, s = Guarded((B, C, H, W), torch.float32, cuda), Guarded((2,), torch.float64, cuda)
+        s.win.zero_()
+        arr = (_lib.C.c_float * len(prm))(*prm)
+        rc = _lib.lib().slu_evidence_term(_lib.ptr(alpha), _lib.ptr(tgt), None, B, C, H * W, ign, 1, term, arr, len(prm),
+                                          _lib.ptr(s.win), _lib.ptr(g.win), _lib.stream_ptr())
+        _lib.check(rc, "slu_evidence_term")
+        guards += [g, s]
+    for term in (ops.TERM_NLL, ops.TERM_DIGAMMA_CE, ops.TERM_BRIER):
+        g, s = Guarded((B, C, H, W), torch.float32, cuda), Guarded((2,), torch.float64, cuda)
+        s.win.zero_()
+        rc = _lib.lib().slu_dirichlet_term(_lib.ptr(alpha), _lib.ptr(tgt), None, B, C, H * W, ign, 1, term, 1e-8, -1.0,
+                                           _lib.ptr(s.win), _lib.ptr(g.win), _lib.stream_ptr())
+        _lib.check(rc, "slu_dirichlet_term")
+        guards += [g, s]
+    z = torch.randn((B, C + 1, H, W), device=cuda)
+    g, s = Guarded((B, C + 1, H, W), torch.float32, cuda), Guarded((2,), torch.float64, cuda)
+    s.win.zero_()
+    rc = _lib.lib().slu_logit_regularizer(_lib.ptr(z), _lib.ptr(tgt), None, B, C + 1, H * W, ign, 1, 1, 0.5,
+                                          _lib.ptr(s.win), _lib.ptr(g.win), _lib.stream_ptr())
+    _lib.check(rc, "slu_logit_regularizer")
+    guards += [g, s]
+    torch.cuda.synchronize()
+    assert all(x.intact() for x in guards)
+    assert not any(bool((x.win == 777.0).any()) for x in guards)        # every output element was written
+    # wrong parameter count / missing target are refused before any launch
+    arr = (_lib.C.c_float * 2)(1.0, 1e-8)
+    assert _lib.lib().slu_evidence_term(_lib.ptr(alpha), _lib.ptr(tgt), None, B, C, H * W, ign, 1, ops.TERM_COMP_KL, arr, 2,
+                                        _lib.ptr(guards[1].win), None, _lib.stream_ptr()) == -1
+    assert _lib.lib().slu_evidence_term(_lib.ptr(alpha), None, None, B, C, H * W, None, 0, ops.TERM_KL_CONF, arr, 2,
+                                        _lib.ptr(guards[1].win), None, _lib.stream_ptr()) == -1

@@ -149,3 +149,80 @@ def test_alternative_terms_vs_fp64_autograd_with_masks(cuda):
             assert abs(float(l.detach()) - float(l_ref.detach())) <= 1e-5 * abs(float(l_ref.detach())) + 1e-9, mod.__name__
             ok, aerr, rerr = rel_close(a.grad.cpu().numpy(), g_ref.numpy(), 1e-5, 2e-6 * float(g_ref.abs().max()))
             assert ok, f"{mod.__name__} grad: abs {aerr:.3e} rel {rerr:.3e}"
+
+
+from tests.loss_term_cases import NAMES as TERM_NAMES  # noqa: E402
+from tests.loss_term_cases import cases as term_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("name", TERM_NAMES)
+def test_remaining_terms_vs_reference_golden(cuda, golden, name):
+    """ComplementKLUniform / WrongLowEvidence / EvidenceReg(Band) / conf-weighted KL / LogitRegularizer: value 1e-5
+    relative, gradient 1e-5 relative + 2e-6 of the largest entry, against the reference modules' outputs."""
+    g = golden("loss_terms.npz")
+    target, keep = torch.from_numpy(g["target"]).to(cuda), torch.from_numpy(g["keep"]).to(cuda)
+    key, _, make = term_cases(target, keep)[name]
+    mod, kw, positional = make()
+    x = torch.from_numpy(g[key]).to(cuda).requires_grad_(True)
+    loss = mod(x, kw["target"]) if positional else mod(x, **kw)
+    assert loss.dim() == 0 and loss.requires_grad
+    (grad,) = torch.autograd.grad(loss, x, retain_graph=True)
+    ref = float(g[name + "/loss"])
+    assert abs(float(loss.detach()) - ref) <= 1e-5 * abs(ref) + 1e-9, (name, float(loss.detach()), ref)
+    gref = g[name + "/grad"]
+    ok, aerr, rerr = rel_close(grad.cpu().numpy(), gref, 1e-5, 2e-6 * float(np.abs(gref).max()))
+    assert ok, f"{name} grad: abs {aerr:.3e} rel {rerr:.3e} (max |g| {float(np.abs(gref).max()):.3e})"
+    (grad3,) = torch.autograd.grad(loss * 3.0, x)
+    assert torch.allclose(grad3, grad * 3.0, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 8, 128), (1, 7, 5, 33), (1, 32, 2, 64), (1, 3, 3, 17)])
+def test_remaining_terms_vs_fp64_oracle_ragged(cuda, shape):
+    """Same terms on ragged shapes and stress inputs (no-evidence and very confident pixels), against the oracle
+    evaluated in float64 with autograd."""
+    B, C, H, W = shape
+    gen = torch.Generator().manual_seed(B * 1000 + C)
+    alpha = torch.nn.functional.softplus(torch.randn(shape, generator=gen) * 3.0) + 1.0
+    alpha[:, :, 0, :4] = 1.0 + 1e-8
+    alpha[:, 1, 1, :4] = 5.0e3
+    target = torch.randint(0, C, (B, H, W), generator=gen)
+    target = torch.where(torch.rand((B, H, W), generator=gen) < 0.5, alpha.argmax(dim=1), target)
+    keep = torch.rand((B, H, W), generator=gen) > 0.3
+    logits = torch.randn((B, C + 1, H, W), generator=gen) * 4.0
+    cpu = term_cases(target, keep)
+    dev = term_cases(target.to(cuda), keep.to(cuda))
+    for name in TERM_NAMES:
+        key, fn, _ = cpu[name]
+        src = alpha if key == "alpha" else logits
+        x_ref = src.clone().double().requires_grad_(True)
+        l_ref = fn(x_ref)
+        (g_ref,) = torch.autograd.grad(l_ref, x_ref, allow_unused=True)
+        g_ref = torch.zeros_like(x_ref) if g_ref is None else g_ref
+        mod, kw, positional = dev[name][2]()
+        x = src.clone().to(cuda).requires_grad_(True)
+        l = mod(x, kw["target"]) if positional else mod(x, **kw)
+        l.backward()
+        tol = 3e-5 if name.startswith("klw") else 1e-5        # lgamma cancellation at alpha = 5e3, as in the KL test above
+        assert abs(float(l.detach()) - float(l_ref.detach())) <= tol * abs(float(l_ref.detach())) + 1e-9, (name, shape, float(l.detach()), float(l_ref.detach()))
+        # where the fp32 reference algebra itself cancels (1 - p_y at alpha_y = 5e3), allow a few times the distance
+        # between the same oracle evaluated in float32 and in float64
+        x32 = src.clone().requires_grad_(True)
+        (g32,) = torch.autograd.grad(fn(x32), x32, allow_unused=True)
+        own = (g32.double() - g_ref).abs().numpy() if g32 is not None else 0.0
+        err = np.abs(x.grad.cpu().double().numpy() - g_ref.numpy())
+        lim = 1e-5 * np.abs(g_ref.numpy()) + 2e-6 * float(g_ref.abs().max()) + 1e-12 + 4.0 * own
+        assert np.all(err <= lim), f"{name} {shape} grad: worst excess {float((err - lim).max()):.3e}, max |g| {float(g_ref.abs().max()):.3e}"
+
+
+def test_remaining_terms_all_ignored(cuda):
+    from semanticlidarunc_b200.losses.dirichlet_losses import ComplementKLUniform
+    from semanticlidarunc_b200.losses.regularizers import KL_offClasses_to_uniform, WrongLowEvidence
+    alpha = (torch.rand((1, 20, 4, 32)) + 1.0).to(cuda).requires_grad_(True)
+    target = torch.zeros((1, 4, 32), dtype=torch.long, device=cuda)
+    for mod in (ComplementKLUniform(ignore_index=0), WrongLowEvidence(ignore_index=0),
+                KL_offClasses_to_uniform(ignore_index=0, with_conf_weighting=True)):
+        l = mod(alpha, target)
+        assert float(l.detach()) == 0.0
+        (g,) = torch.autograd.grad(l, alpha)
+        assert float(g.abs().sum()) == 0.0
+    assert float(ComplementKLUniform()(alpha[:, :2], target).detach()) == 0.0      # C <= 2: exact zero (:275-276)
