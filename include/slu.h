@@ -217,6 +217,10 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
                       int64_t n, int C, int has_ignore, int64_t ignore,
                       int n_bins, const float* h_edges,
                       int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream);
+/* A/B switch (tests, profiles): 1 = always run the generic warp-aggregated histogram kernel instead of the
+ * streaming one slu_confusion_ece picks for 16-byte aligned inputs.  Results are bit-identical either way. */
+int slu_debug_hist_generic(int on);
+
 
 /* ---------------------------------------------------------------------------------------------
  * Error/score histogram: the sufficient statistic of the reference's AUROC, risk-coverage

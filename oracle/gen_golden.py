@@ -442,6 +442,35 @@ def gen_loss_terms():
     np.savez_compressed(os.path.join(GOLD, "loss_terms.npz"), **out)
 
 
+def gen_aurc():
+    """Risk-coverage curves from the reference's metrics/aurc.py on continuous, tied and degenerate inputs."""
+    from metrics.aurc import UncertaintyAggregator, aurc_from_risks_confids, rc_curve_stats
+    rng = np.random.default_rng(606)
+    out = {}
+    for name, n, quant in (("cont", 4000, None), ("ties", 3000, 0.01), ("two", 2, None), ("one", 1, None), ("allwrong", 50, None)):
+        conf = rng.random(n).astype(np.float32)
+        if quant:
+            conf = (np.round(conf / quant) * quant).astype(np.float32)
+        risks = (rng.random(n) < (1.0 - conf) * 0.8).astype(np.float32) if name != "allwrong" else np.ones(n, np.float32)
+        cov, sel, w = rc_curve_stats(risks, conf)
+        aurc, eaurc, _, _ = aurc_from_risks_confids(risks, conf)
+        out.update({f"{name}/conf": conf, f"{name}/risks": risks, f"{name}/cov": cov, f"{name}/sel": sel, f"{name}/w": w,
+                    f"{name}/aurc": np.array(aurc), f"{name}/eaurc": np.array(eaurc)})
+    # the aggregator end to end: softmax probs [B,C,H,W] + labels [B,1,H,W], both confidence definitions
+    g = torch.Generator().manual_seed(607)
+    probs = torch.softmax(torch.randn((3, 20, 16, 128), generator=g) * 2.0, dim=1)
+    lab = torch.randint(0, 20, (3, 1, 16, 128), generator=g)
+    lab = torch.where(torch.rand(lab.shape, generator=g) < 0.6, probs.argmax(dim=1, keepdim=True), lab)
+    out["agg/probs"], out["agg/labels"] = probs.numpy(), lab.numpy()
+    for tag, mp in (("entropy", False), ("maxprob", True)):
+        agg = UncertaintyAggregator(ignore_index=0, use_max_prob_confidence=mp)
+        agg.add_batch(probs[:2], lab[:2])
+        agg.add_batch(probs[2:], lab[2:])
+        r = agg.finalize(make_plots=False)
+        out[f"agg/{tag}"] = np.array([r["AURC"], r["EAURC"], r["num_pixels"]], dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLD, "aurc.npz"), **out)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)
@@ -463,6 +492,7 @@ def main():
     gen_metrics()
     gen_losses()
     gen_loss_terms()
+    gen_aurc()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     for fn in sorted(os.listdir(GOLD)):

@@ -154,3 +154,35 @@ def binned_accuracy(uncert: np.ndarray, correct: np.ndarray, num_bins: int):
     csum = np.histogram(uncert, bins=edges, weights=correct.astype(np.float32))[0]
     acc = np.divide(csum, n, out=np.full_like(csum, np.nan, dtype=float), where=n > 0)
     return n, acc
+
+
+# ---- risk-coverage / AURC (src/metrics/aurc.py:7-45), exact restatement without the Python loop -------------------
+def rc_curve_stats(risks: np.ndarray, confids: np.ndarray):
+    """aurc.py:7-35.  The reference walks the samples in ascending confidence, drops one at a time and records a
+    point at i == 0 and at the first sample of every new tie group; the trailing samples form one last segment."""
+    n = risks.size
+    idx = np.argsort(confids)                       # same call (same tie order) as aurc.py:10
+    r = risks[idx].astype(np.float64)
+    c = confids[idx]
+    total = float(r.sum())
+    i = np.arange(0, max(n - 1, 0))
+    rec = i[(i == 0) | (c[i] != c[np.maximum(i - 1, 0)])] if n > 1 else np.zeros(0, dtype=np.int64)
+    cs = np.cumsum(r)
+    coverages = np.concatenate(([1.0], (n - 1 - rec) / n))
+    sel = np.concatenate(([total / n], (total - cs[rec]) / (n - 1 - rec)))
+    weights = np.diff(np.concatenate(([-1], rec))) / n
+    tail = (n - 2 - rec[-1]) if rec.size else 0
+    if tail > 0:
+        coverages = np.append(coverages, 0.0)
+        sel = np.append(sel, sel[-1])
+        weights = np.append(weights, tail / n)
+    return coverages, sel, weights
+
+
+def aurc_from_risks_confids(risks: np.ndarray, confids: np.ndarray):
+    """aurc.py:38-45 -> (aurc, eaurc, coverages, rc_risks)."""
+    coverages, rc_risks, weights = rc_curve_stats(risks, confids)
+    aurc = float(np.sum((rc_risks[:-1] + rc_risks[1:]) * 0.5 * weights))
+    n = risks.size
+    opt = np.cumsum(np.sort(risks)) / np.arange(1, n + 1)
+    return aurc, aurc - float(opt.sum() / n), coverages, rc_risks

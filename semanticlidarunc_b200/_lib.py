@@ -39,6 +39,7 @@ SIGNATURES = {
     "slu_logit_regularizer": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _p, _p, _p]),
     "slu_diag_special": (_i, [_p, _i64, _p, _p]),
     "slu_confusion_ece": (_i, [_p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
+    "slu_debug_hist_generic": (_i, [_i]),
     "slu_score_hist": (_i, [_p, _p, _p, _i64, _i, _p, _i, _p, _p]),
     "slu_class_score_hist": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
     "slu_project_workspace_bytes": (_i64, [_i64, _i, _i64]),

@@ -208,3 +208,71 @@ def test_summary_cache_round_trip(cuda, tmp_path):
     with _pt.raises(KeyError):
         from semanticlidarunc_b200.models.summary_cache import restore_summary
         restore_summary({"meta": {}}, iou_evaluator=IoUEvaluator(C))
+
+
+@pytest.mark.parametrize("tag,maxprob", [("entropy", False), ("maxprob", True)])
+def test_uncertainty_aggregator_aurc_vs_reference_golden(cuda, golden, tag, maxprob):
+    """UncertaintyAggregator (src/metrics/aurc.py:210-350) on the device histogram: pixel count exact, AURC and
+    E-AURC within 1e-5 of the reference's sort-based values."""
+    from semanticlidarunc_b200.metrics.aurc import UncertaintyAggregator, compute_batch_uncertainty_metrics, aurc_from_risks_confids
+    g = golden("aurc.npz")
+    probs, lab = torch.from_numpy(g["agg/probs"]).to(cuda), torch.from_numpy(g["agg/labels"]).to(cuda)
+    agg = UncertaintyAggregator(ignore_index=0, use_max_prob_confidence=maxprob)
+    agg.add_batch(probs[:2], lab[:2])
+    agg.add_batch(probs[2:].cpu(), lab[2:].cpu())                 # host tensors are accepted, as in the reference
+    r = agg.finalize(make_plots=False)
+    ref = g["agg/" + tag]
+    assert r["num_pixels"] == int(ref[2])
+    assert abs(r["AURC"] - ref[0]) <= 1e-5 and abs(r["EAURC"] - ref[1]) <= 1e-5, (r, ref)
+    m = compute_batch_uncertainty_metrics(probs, lab, ignore_index=0, use_max_prob_confidence=maxprob)
+    assert abs(m["AURC"] - ref[0]) <= 1e-5 and m["num_pixels"] == int(ref[2])
+    assert m["recalls"].shape == (8,) and np.all(np.diff(m["recalls"]) >= 0) and m["recalls"][-1] <= 1.0
+    a, e, _, _ = aurc_from_risks_confids(g["cont/risks"], g["cont/conf"])
+    assert abs(a - float(g["cont/aurc"])) <= 1e-6 and abs(e - float(g["cont/eaurc"])) <= 1e-6
+    agg.reset()
+    with pytest.raises(RuntimeError):
+        agg.finalize(make_plots=False)
+
+
+@pytest.mark.parametrize("C,n,n_bins,offset", [(20, 1_000_003, 15, 0), (20, 262_144, 15, 0), (20, 4099, 15, 0), (64, 300_001, 32, 0),
+                                                (20, 100_000, 64, 0), (100, 50_000, 15, 0), (20, 70_001, 15, 1), (7, 16_384, 10, 2)])
+@pytest.mark.parametrize("coherent", [False, True])
+def test_streaming_and_generic_histogram_kernels_agree(cuda, C, n, n_bins, offset, coherent):
+    """slu_confusion_ece picks the streaming kernel (vector loads, private cells) for aligned inputs and the generic
+    warp-aggregated one otherwise (offset != 0: views that are not 16-byte aligned; n_bins = 64: cells do not fit);
+    integer counts must be bit-identical between the two and equal to the oracle's."""
+    from semanticlidarunc_b200 import _lib
+    g = torch.Generator().manual_seed(C * 7 + n)
+    if coherent:
+        lab = torch.randint(0, C, ((n + offset + 63) // 64,), generator=g).repeat_interleave(64)[: n + offset]
+        pred = torch.where(torch.rand((n + offset,), generator=g) < 0.9, lab, torch.randint(0, C, (n + offset,), generator=g))
+        conf = 1.0 - torch.rand((n + offset,), generator=g) * 0.05
+    else:
+        pred = torch.randint(-1, C + 1, (n + offset,), generator=g)
+        lab = torch.randint(-1, C + 1, (n + offset,), generator=g)
+        conf = torch.rand((n + offset,), generator=g)
+        conf[offset:offset + 6] = torch.tensor([0.0, 1.0, 1.0 / n_bins, 0.5, float("nan"), 1.5])
+    pd, ld, cd = pred.to(cuda)[offset:], lab.to(cuda)[offset:], conf.to(cuda)[offset:]
+    out = []
+    for generic in (0, 1):
+        _lib.lib().slu_debug_hist_generic(generic)
+        try:
+            cm = torch.zeros((C, C), dtype=torch.int64, device=cuda)
+            bins = ops.new_ece_bins(n_bins, cuda)
+            ops.confusion_ece(pd, ld, cd, num_classes=C, ignore_index=0, confmat=cm, ece_bins=bins)
+            ops.confusion_ece(pd, ld, cd, num_classes=C, ignore_index=0, confmat=cm, ece_bins=bins)      # accumulates
+            out.append((cm.cpu(), bins.cpu()))
+        finally:
+            _lib.lib().slu_debug_hist_generic(0)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    p, l, c = pred[offset:], lab[offset:], conf[offset:]
+    assert torch.equal(out[0][0], 2 * om.confusion_counts(p, l, C))
+    valid = (l != 0) & ~torch.isnan(c)
+    nn, nc, cs = om.ece_bin_counts(c[valid].clamp(0, 1).numpy(), (p[valid] == l[valid]).numpy(), n_bins)
+    assert np.array_equal(out[0][1][0].numpy(), 2 * nn) and np.array_equal(out[0][1][1].numpy(), 2 * nc)
+    # bins only / confusion only
+    b2 = ops.new_ece_bins(n_bins, cuda)
+    ops.confusion_ece(pd, ld, cd, num_classes=C, ignore_index=0, ece_bins=b2)
+    cm2 = torch.zeros((C, C), dtype=torch.int64, device=cuda)
+    ops.confusion_ece(pd, ld, None, num_classes=C, confmat=cm2)
+    assert torch.equal(2 * b2.cpu(), out[0][1]) and torch.equal(2 * cm2.cpu(), out[0][0])

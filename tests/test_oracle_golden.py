@@ -127,6 +127,34 @@ def test_loss_terms_oracle_vs_golden(golden):
         assert float(np.abs(g[name + "/grad"]).max()) > 0.0, name        # every case exercises its gradient
 
 
+def _np_score_hist(score, is_err, M):
+    b = np.minimum((np.clip(score, 0, 1).astype(np.float64) * M).astype(np.int64), M - 1)
+    hist = np.zeros((2, M), np.int64)
+    np.add.at(hist, (is_err.astype(np.int64), b), 1)
+    return hist
+
+
+@pytest.mark.parametrize("name", ["cont", "ties", "two", "one", "allwrong"])
+def test_aurc_oracle_and_histogram_form_vs_golden(golden, name):
+    """rc_curve_stats / aurc_from_risks_confids (src/metrics/aurc.py:7-45): the restatement is exact; the
+    fixed-resolution histogram form the device path uses stays within 1e-6 on continuous confidences and within
+    1e-4 where the reference's own result depends on how argsort orders exact ties."""
+    from semanticlidarunc_b200.metrics import aurc as A
+    g = golden("aurc.npz")
+    conf, risks = g[name + "/conf"], g[name + "/risks"]
+    cov, sel, w = om.rc_curve_stats(risks, conf)
+    assert np.array_equal(cov, g[name + "/cov"]) and np.array_equal(sel, g[name + "/sel"]) and np.array_equal(w, g[name + "/w"])
+    a, e, _, _ = om.aurc_from_risks_confids(risks, conf)
+    assert a == float(g[name + "/aurc"]) and e == float(g[name + "/eaurc"])
+    hist = _np_score_hist(np.float32(1.0) - conf, risks, A.AURC_BINS)
+    ah, eh, _, _ = A.aurc_from_hist(hist)
+    tol = 1e-4 if name == "ties" else 1e-6
+    assert abs(ah - a) <= tol and abs(eh - e) <= tol, (ah - a, eh - e)
+    n, ne = int(risks.size), int(risks.sum())
+    opt_ref = float((np.cumsum(np.sort(risks.astype(np.float64))) / np.arange(1, n + 1)).sum() / n)
+    assert abs(A.optimal_aurc(n, ne) - opt_ref) <= 1e-12
+
+
 def test_full_size_projection_digests_cpu():
     """One full HDL-64 scan through the oracle must hit the reference's digests (others run on GPU)."""
     import hashlib
