@@ -13,10 +13,9 @@
 //   probability_helper: alpha0 = sum(alpha) + eps, H = -sum p log(p + eps)          (eps = 1e-8)
 //   AUROC MI          : a0 = sum(alpha) + e, p = alpha/a0, clamp(p, e) inside the log (e = 1e-12)
 //   ECE 'alpha'       : p = alpha / (sum(alpha) + e), conf = max p                  (e = 1e-12)
-// Bound: the per-class digamma (4-step recurrence as one rational, logf, 5-term series: ~50 instructions)
-// makes this kernel instruction-bound rather than HBM-bound at C=20.  Softmax uses ex2.approx and one
-// reciprocal, the entropies lg2.approx, like the MC kernel; digamma keeps the accurate logf because AU and
-// EU are differences of O(ln alpha0) terms.
+// Bound: instructions, not HBM, at C=20: per class one ex2 (softmax), one reciprocal and one lg2 for the digamma
+// DIFFERENCE psi(alpha_c+1) - psi(alpha0+1) (slu_special.cuh::psi_g: psi(x) = ln x + g(1/x) with a degree-7 polynomial,
+// the logarithm taken once on the ratio of the two arguments), two lg2 for the entropies: 5 MUFU per class.
 #include <math.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
@@ -55,7 +54,8 @@ struct EvParams {
     long long n_px;            // B * HW
 };
 
-template <int CP>
+// EXACT: C == CP, no per-class predicate anywhere;  MI: the AUROC-convention mutual information is requested.
+template <int CP, bool EXACT, bool MI>
 __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_constant__ EvParams p) {
     __shared__ unsigned s_cm[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
     __shared__ unsigned s_n[SLU_MAX_BINS], s_c[SLU_MAX_BINS];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
             const float* base = p.outputs + ((long long)b * (p.C + 1)) * p.HW + px;
             float z[CP];
 #pragma unroll
-            for (int c = 0; c < CP; ++c) z[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : -1.0e30f;
+            for (int c = 0; c < CP; ++c) z[c] = (EXACT || c < p.C) ? ldg_stream(base + (long long)c * p.HW) : -1.0e30f;
             const float sl = ldg_stream(base + (long long)p.C * p.HW) * p.inv_temp;
             // softplus (ATen: x > 20 ? x : log1p(exp(x)))
             const float scale = sl > 20.f ? sl : log1pf(expf(sl));
@@ -96,47 +96,58 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 const float pc = z[c] * invS;
-                if (c < p.C && pc > best) { best = pc; pred = c; }          // tester.py:493-495
+                if ((EXACT || c < p.C) && pc > best) { best = pc; pred = c; }          // tester.py:493-495
                 a[c] = __fadd_rn(__fadd_rn(1.0f, __fmul_rn(scale, pc)), p.eps);   // probability_helper.py:104
             }
         } else {
             const float* base = p.alpha_in + ((long long)b * p.C) * p.HW + px;
 #pragma unroll
-            for (int c = 0; c < CP; ++c) a[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
+            for (int c = 0; c < CP; ++c) a[c] = (EXACT || c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
         }
         // sums and arg max over alpha
         float asum = 0.f, amax = 0.f;
         int aarg = 0;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-            if (c < p.C) {
+            if (EXACT || c < p.C) {
                 asum += a[c];
                 if (c == 0 || a[c] > amax || (a[c] != a[c] && amax == amax)) { amax = a[c]; aarg = c; }
-                if (p.alpha_out && live) p.alpha_out[((long long)b * p.C + c) * p.HW + px] = a[c];
             }
+        }
+        if (p.alpha_out && live) {
+            float* ao = p.alpha_out + ((long long)b * p.C) * p.HW + px;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) ao[(long long)c * p.HW] = a[c];
         }
         if (!p.outputs) pred = aarg;
         const float a0 = asum + p.eps;                     // probability_helper.py:119,127
         const float a0m = asum + p.eps_m;                  // auroc.py:57
-        const bool want_unc = p.h || p.au || p.eu || p.mi;
+        const bool want_unc = p.h || p.au || p.eu || MI;
         float H = 0.f, AU = 0.f, Hm = 0.f, EHm = 0.f;
         if (want_unc) {                                    // warp-uniform
-            const float psi0 = digamma_pos(a0 + 1.0f);
-            const float psi0m = digamma_pos(a0m + 1.0f);
-            const float inv0 = __frcp_rn(a0), inv0m = __frcp_rn(a0m);
+            // psi(alpha_c + 1) - psi(alpha0 + 1) = ln((alpha_c+1)/(alpha0+1)) + g_c - g_0: one rcp and one lg2 per class
+            const float x0 = a0 + 1.0f;
+            const PsiG q0 = psi_g(x0);
+            const bool same0 = a0m == a0;                  // alpha >= 1: both eps vanish in fp32 and the two sums coincide
+            PsiG q0m = q0;
+            if (MI && !same0) q0m = psi_g(a0m + 1.0f);
+            const float inv0 = __frcp_rn(a0), inv0m = (MI && !same0) ? __frcp_rn(a0m) : inv0;
             float H2 = 0.f, Hm2 = 0.f;                     // entropies in log2 units (lg2.approx, rel. error <= 2^-22)
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                if (c < p.C) {
+                if (EXACT || c < p.C) {
                     const float ph = a[c] * inv0;
-                    const float psi = digamma_pos(a[c] + 1.0f);
+                    const float xc = a[c] + 1.0f;
+                    const PsiG q = psi_g(xc);
+                    const float d = psi_diff(xc, q, q0);
                     H2 = fmaf(-ph, lg2_fast(ph + p.eps), H2);                // :121
-                    AU = fmaf(-ph, psi - psi0, AU);                          // :128-130
-                    if (p.mi) {
+                    AU = fmaf(-ph, d, AU);                                   // :128-130
+                    if (MI) {
                         const float pm = a[c] * inv0m;
                         const float pmc = fmaxf(pm, p.eps_m);
                         Hm2 = fmaf(-pmc, lg2_fast(pmc), Hm2);                // auroc.py:59
-                        EHm = fmaf(-pm, psi - psi0m, EHm);                   // auroc.py:60-61
+                        EHm = fmaf(-pm, same0 ? d : psi_diff(xc, q, q0m), EHm);   // auroc.py:60-61
                     }
                 }
             }
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
             if (p.h) p.h[g] = __fdiv_rn(H, p.logC);
             if (p.au) p.au[g] = AU;
             if (p.eu) p.eu[g] = H - AU;
-            if (p.mi) p.mi[g] = __fdiv_rn(Hm - EHm, p.logC);
+            if (MI) p.mi[g] = __fdiv_rn(Hm - EHm, p.logC);
         }
         if (p.labels) {
             const long long lab = live ? p.labels[g] : -1;
@@ -183,8 +194,13 @@ static int launch_ev(const EvParams& p, cudaStream_t st) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long chunks = (p.n_px + EV_THREADS - 1) / EV_THREADS;
-    const long long cap = 4LL * sms;
-    evidential_kernel<CP><<<(unsigned)(chunks < cap ? chunks : cap), EV_THREADS, 0, st>>>(p);
+    const long long cap = 5LL * sms;                       // 48 registers: five resident CTAs of 256 threads
+    const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
+    const bool exact = p.C == CP, mi = p.mi != nullptr;
+    if (exact && mi) evidential_kernel<CP, true, true><<<grid, EV_THREADS, 0, st>>>(p);
+    else if (exact) evidential_kernel<CP, true, false><<<grid, EV_THREADS, 0, st>>>(p);
+    else if (mi) evidential_kernel<CP, false, true><<<grid, EV_THREADS, 0, st>>>(p);
+    else evidential_kernel<CP, false, false><<<grid, EV_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("evidential_kernel");
     return 0;
 }

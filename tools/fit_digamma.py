@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Coefficients of h(w) in csrc/slu_special.cuh::psi_g:  psi(x) = ln x + w (w h(w) - 1/2), w = 1/x in [0, 1].
+Least-squares fit on 400 Chebyshev nodes in 40-digit arithmetic (mpmath), then the fp32 Horner evaluation is checked
+against scipy's float64 digamma over x in [1, 1e7].  CPU only; prints the coefficients lowest order first."""
+import mpmath as mp
+import numpy as np
+from numpy.polynomial import Polynomial
+from numpy.polynomial import chebyshev as Ch
+from scipy.special import digamma
+
+mp.mp.dps = 40
+DEG = 7
+
+
+def h(w):
+    w = mp.mpf(w)
+    return mp.mpf(-1) / 12 if w == 0 else (mp.digamma(1 / w) + mp.log(w) + w / 2) / w ** 2
+
+
+nodes = np.cos(np.pi * (np.arange(400) + 0.5) / 400)
+hv = np.array([float(h(float(x))) for x in (nodes + 1) / 2])
+coef = Polynomial(Ch.cheb2poly(Ch.chebfit(nodes, hv, DEG)))(Polynomial([-1, 2.0])).coef
+print(", ".join("%.9ef" % c for c in coef))
+f = np.float32
+x = np.concatenate([np.linspace(1, 8, 40001), np.logspace(0, 7, 40001)]).astype(f)
+w = (f(1) / x).astype(f)
+acc = np.full_like(w, f(coef[-1]))
+for c in coef[-2::-1]:
+    acc = (acc * w + f(c)).astype(f)
+g = ((acc * w - f(0.5)) * w).astype(np.float64)
+err = np.abs(np.log(x.astype(np.float64)) + g - digamma(x.astype(np.float64)))
+print("max |psi_fp32 - psi| = %.3e at x = %.4f" % (err.max(), x[err.argmax()]))

@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""GPU-side time of each stage's kernels, free of Python / launch overhead: every stage is captured into a CUDA graph
+once and the graph is replayed between CUDA events (median of 20, L2 flushed before each replay).  The wrapper-level
+numbers of tools/stage_report.py include ~15-60 us of Python per call, which hides the kernels of the small configs.
+Algorithmic bytes per SURVEY.md 8d.  JSON to stdout."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from semanticlidarunc_b200 import ops, synth  # noqa: E402
+from semanticlidarunc_b200.dataset.definitions import build_id_lut  # noqa: E402
+
+dev = torch.device("cuda", 0)
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+only = set(sys.argv[1:])
+
+
+def graph_time(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts))
+
+
+rows = []
+
+
+def add(name, fn, nbytes, units, note=""):
+    if only and not any(o in name for o in only):
+        return
+    ms = graph_time(fn)
+    gbs = nbytes / ms / 1e6
+    rows.append({"stage": name, "ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 2), "GBps": round(gbs, 1),
+                 "frac_of_measured_peak": round(gbs / PEAK, 3), "scans_per_s": round(units / ms * 1e3, 1), "note": note})
+    print(rows[-1], file=sys.stderr)
+
+
+lut = torch.from_numpy(build_id_lut()).to(dev)
+for sensor, B in (("hdl64", 1), ("hdl64", 16), ("os1-128", 1), ("os1-128", 16)):
+    scans = [synth.synth_scan(i, sensor) for i in range(B)]
+    H, W = synth.SENSORS[sensor][4:6]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    xyzi = torch.from_numpy(np.concatenate([s[0] for s in scans])).to(dev)
+    raw = torch.from_numpy(np.concatenate([s[1] for s in scans]).view(np.int32)).to(dev)
+    res = ops.project_batch(xyzi, raw, offs, H, W, lut=lut)
+    ws = res["workspace"]
+    n = int(offs[-1])
+    add(f"projection {sensor} B={B}", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws), 20 * n + 24 * B * H * W, B, "5 launches")
+    lab_img, pix = res["label"], res["pix"]
+    add(f"back-projection {sensor} B={B}", lambda: ops.backproject(lab_img, pix, offs), 8 * n + 8 * B * H * W, B)
+
+T, C, H, W = 20, 20, 64, 2048
+g = torch.Generator(device=dev).manual_seed(0)
+for B in (1, 16):
+    logits = torch.randn((T, B, C, H, W), generator=g, device=dev) * 3.0
+    labels = torch.randint(0, C, (B, H, W), generator=g, device=dev)
+    cm, bins = ops.new_confmat(C, dev), ops.new_ece_bins(15, dev)
+    add(f"MC reduce+metrics T=20 B={B}", lambda: ops.reduce_metrics(logits, labels, kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0, confmat=cm, ece_bins=bins),
+        (4 * T * C + 32) * B * H * W, B, "config 2")
+    one = logits[0].contiguous()
+    add(f"single-pass softmax entropy+ECE T=1 B={B}", lambda: ops.reduce_metrics(one, labels, kind="logits", ignore_index=0, confmat=cm, ece_bins=bins),
+        (4 * C + 32) * B * H * W, B, "config 1")
+    add(f"single-pass T=1 B={B}, maps only (no histograms)", lambda: ops.reduce_metrics(one, None, kind="logits"), (4 * C + 24) * B * H * W, B)
+    ev = torch.randn((B, C + 1, H, W), generator=g, device=dev) * 3.0
+    add(f"evidential reduce+metrics B={B}", lambda: ops.evidential_reduce(ev, labels, from_outputs=True, ignore_index=0, confmat=cm, ece_bins=bins),
+        (4 * (C + 1) + 8 + 8 + 5 * 4) * B * H * W, B, "tester Dirichlet block")
+    add(f"fused evidential loss fwd+bwd B={B}", lambda: ops.evidential_loss_fused(ev, labels, ignore=(0,)), 176 * B * H * W, B, "config 5: count kernel + fused kernel")
+    alpha = torch.nn.functional.softplus(ev[:, :C]) + 1.0
+    add(f"Dirichlet MSE+KL terms fwd+bwd B={B}", lambda: ops.dirichlet_loss(alpha, labels, ignore=(0,)), (80 + 8 + 160) * B * H * W, B, "two gradients written")
+    del logits
+print(json.dumps({"peak_GBps": PEAK, "rows": rows}, indent=1))
