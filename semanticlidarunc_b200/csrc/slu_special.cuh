@@ -55,13 +55,16 @@ __device__ __forceinline__ float trigamma_pos(float x) {
     return r + y;
 }
 
-// lgamma(a), psi(a), psi'(a) together, a > 0 (the KL regulariser needs all three per off-class).
-//   1 <= a < 1.25 (a class without evidence: the common case): Taylor series about 1,
-//       lgamma(1+d) = -g d + sum_{k>=2} (-1)^k zeta(k)/k d^k, and its two derivatives; truncation < 2e-8.
-//   otherwise: one shared recurrence up to x >= 7 (product for lgamma, sum 1/x for psi, sum 1/x^2 for psi'),
-//       one log of x shared by lgamma and psi, Stirling series in 1/x^2.
-// lgamma and psi (value-only terms) are good to ~3e-6 * max(1, |.|); psi' (the gradient) to ~3e-7 relative.
-// The KL term they feed carries the constant lgamma(C) ~ 39, and is held to 1e-5 relative in the tests.
+// lgamma(a), psi(a), psi'(a) together, a > 0 (the KL regulariser needs all three per off-class), branch-free for
+// a >= 1 (every Dirichlet concentration the heads produce): with w = 1/a and ln a from one lg2.approx,
+//   lgamma(a) = (a - 1/2) ln a - a + ln(2 pi)/2 + w r(w)         r(0) = 1/12
+//   psi(a)    = ln a + w (w h(w) - 1/2)                           h(0) = -1/12   (psi_g above)
+//   psi'(a)   = w + w^2/2 + w^3 v(w)                              v(0) = 1/6
+// r (degree 6), h and v (degree 7) are least-squares fits on Chebyshev nodes of w in [0,1] (tools/fit_digamma.py):
+// lgamma to 1.2e-8 * max(1,|.|) before fp32 assembly, psi to 9e-8 absolute, psi' to 1.6e-7 relative.  Two MUFU
+// (rcp, lg2) and ~30 FMA per call; a < 1 (clamped concentrations only) takes one recurrence step first.
+// psi' (the only one gradients use) is good to 3e-7 relative; lgamma and psi enter the KL value only, next to the
+// constant lgamma(C) ~ 39, and are held to 1e-5 * max(1,|.|) in the tests.
 struct LDT { float lg, psi, tri; };
 
 __device__ __forceinline__ float rcp_fast(float x) {
@@ -105,67 +108,33 @@ __device__ __forceinline__ float psi_diff(float xa, const PsiG& a, const PsiG& b
 }
 
 __device__ __forceinline__ LDT ldt_pos(float a) {
-    LDT r;
-    if (a >= 1.0f && a < 1.25f) {
-        const float d = a - 1.0f;
-        float l = 0.083353840546109f;
-        l = fmaf(l, d, -0.09095401714582904f); l = fmaf(l, d, 0.1000994575127818f);
-        l = fmaf(l, d, -0.11133426586956469f); l = fmaf(l, d, 0.12550966952474304f);
-        l = fmaf(l, d, -0.1440498967688461f);  l = fmaf(l, d, 0.1695571769974082f);
-        l = fmaf(l, d, -0.20738555102867398f); l = fmaf(l, d, 0.27058080842778454f);
-        l = fmaf(l, d, -0.40068563438653143f); l = fmaf(l, d, 0.8224670334241132f);
-        r.lg = d * fmaf(l, d, -0.5772156649015329f);
-        float q = 1.0000612481350588f;
-        q = fmaf(q, d, -1.0001227133475785f); q = fmaf(q, d, 1.000246086553308f);
-        q = fmaf(q, d, -1.0004941886041194f); q = fmaf(q, d, 1.000994575127818f);
-        q = fmaf(q, d, -1.0020083928260821f); q = fmaf(q, d, 1.0040773561979444f);
-        q = fmaf(q, d, -1.008349277381923f);  q = fmaf(q, d, 1.0173430619844492f);
-        q = fmaf(q, d, -1.03692775514337f);   q = fmaf(q, d, 1.0823232337111381f);
-        q = fmaf(q, d, -1.2020569031595942f); q = fmaf(q, d, 1.6449340668482264f);
-        r.psi = fmaf(q, d, -0.5772156649015329f);
-        float t = 15.00022923389113f;
-        t = fmaf(t, d, -14.000428235308298f); t = fmaf(t, d, 13.000796225755764f);
-        t = fmaf(t, d, -12.001472560170942f); t = fmaf(t, d, 11.002706952086388f);
-        t = fmaf(t, d, -10.004941886041195f); t = fmaf(t, d, 9.008951176150363f);
-        t = fmaf(t, d, -8.016067142608657f);  t = fmaf(t, d, 7.02854149338561f);
-        t = fmaf(t, d, -6.050095664291537f);  t = fmaf(t, d, 5.086715309922246f);
-        t = fmaf(t, d, -4.14771102057348f);   t = fmaf(t, d, 3.2469697011334144f);
-        t = fmaf(t, d, -2.4041138063191885f); t = fmaf(t, d, 1.6449340668482264f);
-        r.tri = t;
-        return r;
+    float x = a, lg_fix = 0.f, psi_fix = 0.f, tri_fix = 0.f;
+    if (a < 1.0f) {                                          // rare: one recurrence step up
+        const float ia = rcp_fast(a);
+        lg_fix = -lg2_fast_(a) * 0.6931471805599453f;        // lgamma(a) = lgamma(a+1) - ln a
+        psi_fix = -ia;                                       // psi(a)    = psi(a+1) - 1/a
+        tri_fix = ia * ia;                                   // psi'(a)   = psi'(a+1) + 1/a^2
+        x = a + 1.0f;
     }
-    // shared recurrence, at most six steps, predicated (no data-dependent trip count inside a warp)
-    float x = a, prod = 1.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        if (x < 7.f) {
-            const float i = rcp_fast(x);
-            prod *= x;
-            r1 += i;
-            r2 = fmaf(i, i, r2);
-            x += 1.f;
-        }
-    }
-    // the two logs only enter the loss VALUE (gradients use psi' alone); lg2.approx (rel. error 2^-22) keeps
-    // the KL value within 1e-6 relative, since the value carries the constant lgamma(C) ~ 39
+    const float w = rcp_fast(x);
     const float lnx = lg2_fast_(x) * 0.6931471805599453f;
-    const float inv = rcp_fast(x);
-    const float z = inv * inv;
-    float sl = fmaf(z, -5.95238095238095238e-4f, 7.93650793650793651e-4f);      // 1/1260 - z/1680
-    sl = fmaf(z, sl, -2.77777777777777778e-3f);                                   // -1/360
-    sl = fmaf(z, sl, 8.33333333333333333e-2f);                                    // 1/12
-    r.lg = (fmaf(x - 0.5f, lnx, -x) + 0.918938533204672742f + inv * sl) - lg2_fast_(prod) * 0.6931471805599453f;
-    float sp = fmaf(z, 7.57575757575757576e-3f, -4.16666666666666667e-3f);
-    sp = fmaf(z, sp, 3.96825396825396825e-3f);
-    sp = fmaf(z, sp, -8.33333333333333333e-3f);
-    sp = fmaf(z, sp, 8.33333333333333333e-2f);
-    r.psi = (lnx - 0.5f * inv - z * sp) - r1;
-    float st = fmaf(z, 7.57575757575757576e-2f, -3.33333333333333333e-2f);
-    st = fmaf(z, st, 2.38095238095238095e-2f);
-    st = fmaf(z, st, -3.33333333333333333e-2f);
-    st = fmaf(z, st, 1.66666666666666667e-1f);
-    r.tri = fmaf(st, z * inv, fmaf(0.5f, z, inv)) + r2;
-    return r;
+    float r = 1.383177419e-04f;
+    r = fmaf(r, w, -6.336787229e-04f); r = fmaf(r, w, 1.049638091e-03f); r = fmaf(r, w, -5.343459393e-05f);
+    r = fmaf(r, w, -2.772524576e-03f); r = fmaf(r, w, -1.822395578e-07f); r = fmaf(r, w, 8.333333419e-02f);
+    float h = 2.889277183e-04f;
+    h = fmaf(h, w, -1.886666441e-03f); h = fmaf(h, w, 4.937323876e-03f); h = fmaf(h, w, -5.935221128e-03f);
+    h = fmaf(h, w, 4.237475471e-04f);  h = fmaf(h, w, 8.287647461e-03f); h = fmaf(h, w, 1.917667073e-06f);
+    h = fmaf(h, w, -8.333334680e-02f);
+    float v = -3.238177565e-03f;
+    v = fmaf(v, w, 1.716627286e-02f);  v = fmaf(v, w, -3.719230805e-02f); v = fmaf(v, w, 3.725572734e-02f);
+    v = fmaf(v, w, -2.641956099e-03f); v = fmaf(v, w, -3.307210709e-02f); v = fmaf(v, w, -1.011315425e-05f);
+    v = fmaf(v, w, 1.666667325e-01f);
+    LDT o;
+    o.lg = (fmaf(x - 0.5f, lnx, -x) + 0.918938533204672742f) + fmaf(w, r, lg_fix);
+    o.psi = lnx + fmaf(w, fmaf(h, w, -0.5f), psi_fix);
+    const float w2 = w * w;
+    o.tri = fmaf(w2 * w, v, fmaf(0.5f, w2, w)) + tri_fix;
+    return o;
 }
 
 }  // namespace slu

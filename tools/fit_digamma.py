@@ -30,3 +30,40 @@ for c in coef[-2::-1]:
 g = ((acc * w - f(0.5)) * w).astype(np.float64)
 err = np.abs(np.log(x.astype(np.float64)) + g - digamma(x.astype(np.float64)))
 print("max |psi_fp32 - psi| = %.3e at x = %.4f" % (err.max(), x[err.argmax()]))
+
+# ---- lgamma and trigamma corrections used by ldt_pos:  lgamma(x) = (x-1/2) ln x - x + ln(2 pi)/2 + w r(w),
+#      psi'(x) = w + w^2/2 + w^3 v(w)
+from scipy.special import gammaln, polygamma  # noqa: E402
+
+HL2PI = mp.log(2 * mp.pi) / 2
+
+
+def r_fn(w):
+    w = mp.mpf(w)
+    if w == 0:
+        return mp.mpf(1) / 12
+    xx = 1 / w
+    return (mp.loggamma(xx) - ((xx - mp.mpf(1) / 2) * mp.log(xx) - xx + HL2PI)) / w
+
+
+def v_fn(w):
+    w = mp.mpf(w)
+    if w == 0:
+        return mp.mpf(1) / 6
+    return (mp.polygamma(1, 1 / w) - w - w * w / 2) / w ** 3
+
+
+for name, fn, deg in (("r", r_fn, 6), ("v", v_fn, 7)):
+    vals = np.array([float(fn(float(t))) for t in (nodes + 1) / 2])
+    cf = Polynomial(Ch.cheb2poly(Ch.chebfit(nodes, vals, deg)))(Polynomial([-1, 2.0])).coef
+    print(name, ", ".join("%.9ef" % c for c in cf))
+    acc = np.full_like(w, f(cf[-1]))
+    for c in cf[-2::-1]:
+        acc = (acc * w + f(c)).astype(f)
+    xd = x.astype(np.float64)
+    if name == "r":
+        lg = ((xd - 0.5) * np.log(xd) - xd + float(HL2PI)) + (w * acc).astype(np.float64)
+        print("  max |lgamma err| / max(1,|lgamma|) = %.3e" % (np.abs(lg - gammaln(xd)) / np.maximum(1, np.abs(gammaln(xd)))).max())
+    else:
+        tri = (w + f(0.5) * w * w + w * w * w * acc).astype(np.float64)
+        print("  max rel |trigamma err| = %.3e" % (np.abs(tri - polygamma(1, xd)) / polygamma(1, xd)).max())
