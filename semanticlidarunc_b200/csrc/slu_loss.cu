@@ -25,6 +25,10 @@
 namespace slu {
 
 constexpr int LOSS_THREADS = 256;
+#ifndef SLU_LOSS_MINB
+#define SLU_LOSS_MINB 3
+#endif
+constexpr int LOSS_MINB = SLU_LOSS_MINB;       // resident CTAs per SM the class-loop kernels are compiled for
 constexpr int MAX_IGNORE = 8;
 
 struct LossParams {
@@ -42,8 +46,10 @@ struct LossParams {
     float* grad_kl;                // [B,C,HW] or NULL
 };
 
-template <int CP>
-__global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __grid_constant__ LossParams p) {
+// EXACT: C == CP (no per-class predicate).  The true class enters the KL sums as a~ = 1, for which lgamma = 0 and
+// (a~ - 1) = 0, so the class loop needs no branch on c == y (y differs from thread to thread).
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) dirichlet_loss_kernel(const __grid_constant__ LossParams p) {
     const int tid = threadIdx.x;
     double acc_mse = 0.0, acc_kl = 0.0;
     unsigned n_valid = 0;
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
         ++n_valid;
         float a[CP];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) a[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
+        for (int c = 0; c < CP; ++c) a[c] = (EXACT || c < p.C) ? ldg_stream(base + (long long)c * p.HW) : 0.f;
         const int y = (int)tgt;            // the reference's scatter_ requires 0 <= target < C on valid pixels
 
         if (p.want_mse) {
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
             float sq = 0.f, sp2 = 0.f;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                if (c < p.C) {
+                if (EXACT || c < p.C) {
                     const float pc = a[c] * invD;
                     const float d = (c == y ? 1.0f : 0.0f) - pc;
                     sq = fmaf(d, d, sq);
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
             float var = 0.f;
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (c < p.C) var = fmaf(a[c] * (a0 - a[c]), invG, var);
+                if (EXACT || c < p.C) var = fmaf(a[c] * (a0 - a[c]), invG, var);
             acc_mse += (double)(sq + var);
             if (gm) {
                 const float N = a0 * a0 - s2;
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
                 const float common = 2.0f * Q * invD + 2.0f * a0 * invG - N * Gp * invG * invG;
 #pragma unroll
                 for (int c = 0; c < CP; ++c) {
-                    if (c < p.C) {
+                    if (EXACT || c < p.C) {
                         const float pc = a[c] * invD;
                         const float yc = (c == y ? 1.0f : 0.0f);
                         gm[(long long)c * p.HW] = fmaf(-2.0f * (yc - pc), invD, fmaf(-2.0f * a[c], invG, common));
@@ -119,21 +125,18 @@ __global__ void __launch_bounds__(LOSS_THREADS) dirichlet_loss_kernel(const __gr
             float s = 0.f;
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
+                if (EXACT || c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
             const LDT fs = ldt_pos(s);
             float kl = fs.lg;
             const float tail = (s - (float)p.C) * fs.tri;
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
-                if (c < p.C) {
-                    float gj = 0.f;
-                    if (c != y) {
-                        const float ac = fmaxf(a[c], p.eps_kl);
-                        const LDT f = ldt_pos(ac);
-                        kl -= f.lg;
-                        kl = fmaf(ac - 1.0f, f.psi - fs.psi, kl);
-                        if (a[c] > p.eps_kl) gj = fmaf(ac - 1.0f, f.tri, -tail);
-                    }
+                if (EXACT || c < p.C) {
+                    const float ac = fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
+                    const LDT f = ldt_pos(ac);
+                    kl -= f.lg;
+                    kl = fmaf(ac - 1.0f, f.psi - fs.psi, kl);
+                    const float gj = (c != y && a[c] > p.eps_kl) ? fmaf(ac - 1.0f, f.tri, -tail) : 0.f;
                     if (gk) gk[(long long)c * p.HW] = gj;
                 }
             }
@@ -166,7 +169,8 @@ static int launch_loss(const LossParams& p, cudaStream_t st) {
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
     const long long cap = 6LL * sms;
-    dirichlet_loss_kernel<CP><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
+    if (p.C == CP) dirichlet_loss_kernel<CP, true><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
+    else dirichlet_loss_kernel<CP, false><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("dirichlet_loss_kernel");
     return 0;
 }
@@ -219,8 +223,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_
     }
 }
 
-template <int CP>
-__global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(const __grid_constant__ FusedParams p) {
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) evidential_loss_fused_kernel(const __grid_constant__ FusedParams p) {
     const int tid = threadIdx.x;
     const float inv_n = (float)(1.0 / fmax(p.sums[2], 1.0));
     double acc_mse = 0.0, acc_kl = 0.0;
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(con
         const int y = (int)tgt;
         float pr[CP], a[CP];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) pr[c] = (c < p.C) ? ldg_stream(base + (long long)c * p.HW) : -1.0e30f;
+        for (int c = 0; c < CP; ++c) pr[c] = (EXACT || c < p.C) ? ldg_stream(base + (long long)c * p.HW) : -1.0e30f;
         const float sl = ldg_stream(base + (long long)p.C * p.HW) * p.inv_temp;
         const float scale = sl > 20.f ? sl : log1pf(expf(sl));
         const float dscale = sl > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl));       // d softplus
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(con
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
             pr[c] *= invS;
-            a[c] = (c < p.C) ? __fadd_rn(__fadd_rn(1.0f, __fmul_rn(scale, pr[c])), p.eps_alpha) : 0.f;
+            a[c] = (EXACT || c < p.C) ? __fadd_rn(__fadd_rn(1.0f, __fmul_rn(scale, pr[c])), p.eps_alpha) : 0.f;
             a0 += a[c];
             s2 = fmaf(a[c], a[c], s2);
             if (c == y) ay = a[c];
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(con
         float sq = 0.f, sp2 = 0.f, var = 0.f;
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-            if (c < p.C) {
+            if (EXACT || c < p.C) {
                 const float pc = a[c] * invD;
                 const float d = (c == y ? 1.0f : 0.0f) - pc;
                 sq = fmaf(d, d, sq);
@@ -283,22 +287,22 @@ __global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(con
         float s = 0.f;
 #pragma unroll
         for (int c = 0; c < CP; ++c)
-            if (c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
+            if (EXACT || c < p.C) s += fmaxf(c == y ? 1.0f : a[c], p.eps_kl);
         const LDT fs = ldt_pos(s);
         float kl = fs.lg;
         const float tail = (s - (float)p.C) * fs.tri;
         float gp_sum = 0.f;                      // sum_c g_c p_c
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
-            if (c < p.C) {
+            if (EXACT || c < p.C) {
                 const float pc = a[c] * invD;
                 float gc = p.w_mse * fmaf(-2.0f * ((c == y ? 1.0f : 0.0f) - pc), invD, fmaf(-2.0f * a[c], invG, common));
-                if (c != y) {
-                    const float ac = fmaxf(a[c], p.eps_kl);
+                {
+                    const float ac = fmaxf(c == y ? 1.0f : a[c], p.eps_kl);      // a~_y = 1: lgamma = 0, (a~ - 1) = 0
                     const LDT f = ldt_pos(ac);
                     kl -= f.lg;
                     kl = fmaf(ac - 1.0f, f.psi - fs.psi, kl);
-                    if (a[c] > p.eps_kl) gc = fmaf(p.w_kl, fmaf(ac - 1.0f, f.tri, -tail), gc);
+                    if (c != y && a[c] > p.eps_kl) gc = fmaf(p.w_kl, fmaf(ac - 1.0f, f.tri, -tail), gc);
                 }
                 a[c] = gc * inv_n;               // a[] now holds d(loss)/d(alpha_c)
                 gp_sum = fmaf(a[c], pr[c], gp_sum);
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) evidential_loss_fused_kernel(con
         if (go) {
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (c < p.C) go[(long long)c * p.HW] = scale * pr[c] * (a[c] - gp_sum);
+                if (EXACT || c < p.C) go[(long long)c * p.HW] = scale * pr[c] * (a[c] - gp_sum);
             go[(long long)p.C * p.HW] = gp_sum * dscale * p.inv_temp;
         }
     }
@@ -337,7 +341,8 @@ static int launch_fused(const FusedParams& p, cudaStream_t st) {
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
     count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("count_valid_kernel");
-    evidential_loss_fused_kernel<CP><<<grid, LOSS_THREADS, 0, st>>>(p);
+    if (p.C == CP) evidential_loss_fused_kernel<CP, true><<<grid, LOSS_THREADS, 0, st>>>(p);
+    else evidential_loss_fused_kernel<CP, false><<<grid, LOSS_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("evidential_loss_fused_kernel");
     return 0;
 }
