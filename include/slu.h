@@ -100,6 +100,11 @@ int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_labels,
                               int64_t* d_confmat, int64_t* d_ece_bins,
                               slu_stream_t stream);
 
+/* A/B switch (tests, profiles): 1 = single-sample inputs (T == 1) also take the multi-sample staged kernel instead
+ * of the dedicated one-thread-per-pixel kernel slu_reduce_metrics picks for them. */
+int slu_debug_reduce_no_single(int on);
+
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 3+4 for the evidential (Dirichlet) head, single pass.
  * Replaces: src/models/tester.py:484-512 = to_alpha_concentrations_from_shape_and_scale

@@ -1,4 +1,5 @@
 // slu_api.cu -- version, error reporting and device queries of libslu.
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include "slu_common.cuh"
@@ -31,6 +32,18 @@ int sm_count_current_device() {
         cached_sms = sms;
     }
     return cached_sms;
+}
+
+bool one_step_bin_search_ok(const float* e, int n_bins) {
+    if (!(e[0] >= 0.f) || !(e[n_bins] <= 1.f)) return false;
+    for (int i = 0; i < n_bins; ++i) {
+        const float lo = e[i], hi = nextafterf(e[i + 1], -1.0f);
+        int g0 = (int)(lo * (float)n_bins), g1 = (int)(hi * (float)n_bins);
+        g0 = g0 > n_bins - 1 ? n_bins - 1 : g0;
+        g1 = g1 > n_bins - 1 ? n_bins - 1 : g1;
+        if (g0 < i - 1 || g1 > i + 1) return false;
+    }
+    return true;
 }
 
 }  // namespace slu

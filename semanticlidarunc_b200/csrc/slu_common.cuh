@@ -23,6 +23,11 @@ int sm_count_current_device();
         if (e__ != cudaSuccess) return slu::cuda_fail(e__, what);   \
     } while (0)
 
+// floor(v * n_bins) is within one bin of the truth for these edges (true for (near-)uniform edges such as the
+// reference's linspace(0,1,n_bins+1)): the kernels may then use find_bin_fast.  fl(v * n_bins) is monotone in v, so
+// checking each bin's two ends (its lower edge and the float just below its upper edge) covers every v inside it.
+bool one_step_bin_search_ok(const float* edges, int n_bins);
+
 #ifdef __CUDACC__
 // ---- device: PTX wrappers ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -116,6 +121,15 @@ __device__ __forceinline__ int find_bin(const float* edges, int n_bins, float v)
     while (k > 0 && v < edges[k]) --k;
     while (k < n_bins - 1 && v >= edges[k + 1]) ++k;
     return k;
+}
+// Same result as find_bin for edges that passed one_step_bin_search_ok(): no loop, two edge loads.  v in [0,1].
+__device__ __forceinline__ int find_bin_fast(const float* edges, int n_bins, float v) {
+    int k = (int)(v * (float)n_bins);
+    k = k > n_bins - 1 ? n_bins - 1 : k;
+    const float lo = edges[k], hi = edges[k + 1];
+    k += (v >= hi && k < n_bins - 1) ? 1 : 0;
+    k -= (v < lo && k > 0) ? 1 : 0;
+    return (v >= edges[0] && v <= edges[n_bins]) ? k : -1;
 }
 #endif  // __CUDACC__
 

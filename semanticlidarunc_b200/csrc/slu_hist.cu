@@ -245,20 +245,6 @@ __global__ void __launch_bounds__(V2_THREADS) confusion_ece_stream_kernel(const 
 
 static int g_hist_force_generic = 0;
 
-// The streaming kernel finds a bin as floor(v * n_bins) corrected by at most one step; true for (near-)uniform edges
-// such as the reference's linspace(0,1,n_bins+1).  fl(v * n_bins) is monotone in v, so checking each bin's two ends
-// (its lower edge and the float just below its upper edge) covers every v inside it.
-static bool one_step_bin_search_ok(const float* e, int n_bins) {
-    if (!(e[0] >= 0.f) || !(e[n_bins] <= 1.f)) return false;
-    for (int i = 0; i < n_bins; ++i) {
-        const float lo = e[i], hi = nextafterf(e[i + 1], -1.0f);
-        int g0 = (int)(lo * (float)n_bins), g1 = (int)(hi * (float)n_bins);
-        g0 = g0 > n_bins - 1 ? n_bins - 1 : g0;
-        g1 = g1 > n_bins - 1 ? n_bins - 1 : g1;
-        if (g0 < i - 1 || g1 > i + 1) return false;
-    }
-    return true;
-}
 
 // ---- error/score histogram: the sufficient statistic of AUROC, risk-coverage and accuracy-vs-uncertainty ----
 // Replaces the per-pixel host arrays of AUROCAggregator (src/metrics/auroc.py:101-141), UncertaintyAccuracyAggregator

@@ -79,6 +79,8 @@ struct ReduceParams {
     float invT;
     int literal_clamp;   // apply the eps clamp per value inside H_t
     int need_ht;         // mutual information requested (per-sample entropies needed)
+    int allow_single;    // T == 1 may take reduce_single_kernel (not the explicit *_direct entry point)
+    int bins_one_step;   // edges passed one_step_bin_search_ok(): find_bin_fast is valid
 };
 
 // Per-CTA histogram scratch in static shared memory.
@@ -189,13 +191,17 @@ __device__ __forceinline__ void pixel_epilogue(Acc<CP>& a, bool live, int b, lon
     for (int c = 0; c < CP; ++c) {
         if (EXACT || c < p.C) {
             const float pb = a.pbar[c] * p.invT;
-            if (p.pbar && live) p.pbar[obase + (long long)c * p.HW] = pb;
             // torch.argmax: first maximal index, NaN counts as maximal
             if (c == 0 || pb > pmax || (pb != pb && pmax == pmax)) { pmax = pb; arg = c; }
             const float pc = fmaxf(pb, p.eps);
             Hb2 = fmaf(-pc, lg2_approx(pc), Hb2);          // log2 units; |rel err| of lg2.approx <= 2^-22
             sump += fmaxf(pb, 0.f);
         }
+    }
+    if (p.pbar && live) {                                  // uniform in p.pbar: no store slots issued when not requested
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+            if (EXACT || c < p.C) p.pbar[obase + (long long)c * p.HW] = a.pbar[c] * p.invT;
     }
     const float Hb = Hb2 * LN2;
     float conf = pmax;
@@ -382,9 +388,180 @@ __global__ void __launch_bounds__(TILE, 2) reduce_direct_kernel(const __grid_con
     hist_flush(hs, p, tid, blockDim.x);
 }
 
+// =====================================================================================================
+// Single-sample kernel (T == 1: the single-pass branches src/models/trainer.py:1170-1225, ECE/AUROC updates on
+// probabilities or concentrations, config 1 of BASELINE.json).  With one sample per pixel there is nothing to
+// stream through a ring: 108 B/pixel, and the per-pixel epilogue is as long as the sample step.  One thread per
+// pixel, 128-thread CTAs at full occupancy (<= 64 registers), every thread's C loads issued at once (80 B in
+// flight per thread, 160 KB per SM), grid-stride over tiles so the shared-memory histograms are flushed once per CTA.
+// =====================================================================================================
+constexpr int SINGLE_THREADS = 128;
+constexpr int SINGLE_FLUSH_TILES = 128;      // 2^17 * 128 px * 128 tiles < 2^32: the split confidence sums cannot overflow
+
+// Per-CTA histogram scratch of the single-sample kernel: plain shared-memory atomics (ATOMS.POPC.INC for the counts).
+// 64-bit shared atomics are CAS loops on sm_100, so sum(conf * 2^32) is kept as two 32-bit halves (low 16 bits, rest).
+struct SingleHist {
+    unsigned confmat[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
+    unsigned bin_n[SLU_MAX_BINS], bin_c[SLU_MAX_BINS], bin_lo[SLU_MAX_BINS], bin_hi[SLU_MAX_BINS];
+    float edges[SLU_MAX_BINS + 1];
+};
+
+__device__ __forceinline__ void single_hist_zero(SingleHist& hs, const ReduceParams& p, int tid) {
+    for (int i = tid; i < p.C * p.C; i += SINGLE_THREADS) hs.confmat[i] = 0;
+    for (int i = tid; i < SLU_MAX_BINS; i += SINGLE_THREADS) { hs.bin_n[i] = 0; hs.bin_c[i] = 0; hs.bin_lo[i] = 0; hs.bin_hi[i] = 0; }
+}
+__device__ __forceinline__ void single_hist_flush(SingleHist& hs, const ReduceParams& p, int tid) {
+    if (p.confmat)
+        for (int i = tid; i < p.C * p.C; i += SINGLE_THREADS)
+            if (hs.confmat[i]) atomicAdd(&p.confmat[i], (unsigned long long)hs.confmat[i]);
+    if (p.bins)
+        for (int i = tid; i < p.n_bins; i += SINGLE_THREADS) {
+            if (hs.bin_n[i]) {
+                atomicAdd(&p.bins[i], (unsigned long long)hs.bin_n[i]);
+                if (hs.bin_c[i]) atomicAdd(&p.bins[p.n_bins + i], (unsigned long long)hs.bin_c[i]);
+                atomicAdd(&p.bins[2 * p.n_bins + i], ((unsigned long long)hs.bin_hi[i] << 16) + hs.bin_lo[i]);
+            }
+        }
+}
+
+template <int CP, int KIND, bool EXACT>
+__global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const __grid_constant__ ReduceParams p) {
+    __shared__ SingleHist hs;
+    const int tid = threadIdx.x;
+    single_hist_zero(hs, p, tid);
+    for (int i = tid; i <= p.n_bins; i += SINGLE_THREADS) hs.edges[i] = p.edges[i];
+    __syncthreads();
+    const float pad = (KIND == SLU_IN_LOGITS) ? -1.0e30f : 0.f;
+    const long long tiles_per_scan = (p.HW + SINGLE_THREADS - 1) / SINGLE_THREADS;
+    const long long n_tiles = tiles_per_scan * p.B;
+    int since_flush = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (p.labels && ++since_flush > SINGLE_FLUSH_TILES) {        // CTA-uniform
+            __syncthreads();
+            single_hist_flush(hs, p, tid);
+            __syncthreads();
+            single_hist_zero(hs, p, tid);
+            __syncthreads();
+            since_flush = 1;
+        }
+        const int b = (int)(tile / tiles_per_scan);
+        const long long px = (tile - (long long)b * tiles_per_scan) * SINGLE_THREADS + tid;
+        const bool live = px < p.HW;
+        const float* src = p.in + ((long long)b * p.C) * p.HW + (live ? px : p.HW - 1);
+        float x[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            x[c] = (EXACT || c < p.C) ? ldg_stream(src) : pad;
+            src += p.HW;
+        }
+        // ---- distribution p (in x[]), entropy in log2 units
+        float Hb2 = 0.f;
+        bool literal = true;
+        if (KIND == SLU_IN_LOGITS) {
+            float m = x[0];
+#pragma unroll
+            for (int c = 1; c < CP; ++c) m = fmaxf(m, x[c]);
+            const float m2 = m * LOG2E;
+            float S = 0.f, A = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const float arg = fmaf(x[c], LOG2E, -m2);
+                const float e = ex2_approx(arg);
+                x[c] = e;
+                S += e;
+                A = fmaf(e, arg, A);
+            }
+            const float inv = __frcp_rn(S);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) x[c] *= inv;
+            if (!p.literal_clamp) {
+                // H[p] = ln S - ln2 * A/S: no per-class log.  The eps clamp it skips moves H by <= C*eps*|ln eps| (5.5e-10).
+                Hb2 = fmaf(-A, inv, lg2_approx(S));
+                literal = !(fabsf(Hb2) <= 3.0e38f);              // -inf logits / overflow
+            }
+        } else if (KIND == SLU_IN_ALPHA) {                       // p = alpha / (alpha0 + eps)   (src/metrics/ece.py:57-58)
+            float a0 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) a0 += x[c];
+            const float d = a0 + p.eps;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) x[c] = __fdiv_rn(x[c], d);
+        }
+        if (literal && (p.hnorm != nullptr)) {
+            Hb2 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) { const float pc = fmaxf(x[c], p.eps); Hb2 = fmaf(-pc, lg2_approx(pc), Hb2); }
+        }
+        // ---- arg max (torch.argmax: first maximal index, NaN counts as maximal), renormalising sum
+        float pmax = x[0], sump = fmaxf(x[0], 0.f);
+        int arg = 0;
+#pragma unroll
+        for (int c = 1; c < CP; ++c) {
+            if (EXACT || c < p.C) {
+                const bool gt = (x[c] > pmax) | ((x[c] != x[c]) & (pmax == pmax));
+                pmax = gt ? x[c] : pmax;
+                arg = gt ? c : arg;
+                sump += fmaxf(x[c], 0.f);
+            }
+        }
+        float conf = pmax;
+        if (p.conf_mode == SLU_CONF_RENORM) conf = __fdiv_rn(fmaxf(pmax, 0.f), fmaxf(sump, p.eps));
+        const long long o = (long long)b * p.HW + px;
+        if (live) {
+            if (p.pbar) {                                         // CTA-uniform: skipped entirely when not requested
+                float* dst = p.pbar + (long long)b * p.C * p.HW + px;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) *dst = x[c];
+                    dst += p.HW;
+                }
+            }
+            if (p.pred) p.pred[o] = arg;
+            if (p.conf) p.conf[o] = conf;
+            if (p.hnorm) p.hnorm[o] = __fdiv_rn(Hb2 * LN2, p.logC);
+            if (p.minorm) p.minorm[o] = 0.f;                      // H[p_bar] and H[p_1] are the same number: MI is exactly 0
+        }
+        if (p.labels && live) {
+            const long long lab = p.labels[o];
+            if (p.confmat && (unsigned long long)lab < (unsigned long long)p.C) atomicAdd(&hs.confmat[(int)lab * p.C + arg], 1u);
+            if (p.bins) {
+                const float cf = __saturatef(conf);                                   // ece.py:83 clamp_(0,1)
+                int bin = p.bins_one_step ? find_bin_fast(hs.edges, p.n_bins, cf) : find_bin(hs.edges, p.n_bins, cf);
+                if (conf != conf || (p.has_ignore && lab == p.ignore)) bin = -1;      // NaN stays out of every bin
+                if (bin >= 0) {
+                    const unsigned long long fx = __float2ull_rn(cf * 4294967296.0f);
+                    atomicAdd(&hs.bin_n[bin], 1u);
+                    if ((long long)arg == lab) atomicAdd(&hs.bin_c[bin], 1u);
+                    atomicAdd(&hs.bin_lo[bin], (unsigned)(fx & 0xffffu));
+                    atomicAdd(&hs.bin_hi[bin], (unsigned)(fx >> 16));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    single_hist_flush(hs, p, tid);
+}
+
+template <int CP, int KIND>
+static int launch_single(const ReduceParams& p, cudaStream_t stream) {
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long n_tiles = ((p.HW + SINGLE_THREADS - 1) / SINGLE_THREADS) * p.B;
+    const long long max_ctas = 8LL * sms;
+    const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
+    if (p.C == CP) reduce_single_kernel<CP, KIND, true><<<grid, SINGLE_THREADS, 0, stream>>>(p);
+    else reduce_single_kernel<CP, KIND, false><<<grid, SINGLE_THREADS, 0, stream>>>(p);
+    SLU_LAUNCH_CHECK("reduce_single_kernel");
+    return 0;
+}
+
 // ---- host side --------------------------------------------------------------------------------------
+static int g_reduce_no_single = 0;
+
 template <int CP, int KIND>
 static int launch(const ReduceParams& p, bool staged, cudaStream_t stream) {
+    if (p.T == 1 && p.allow_single && !g_reduce_no_single) return launch_single<CP, KIND>(p, stream);
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long max_ctas = (long long)(staged ? Occ<CP>::staged : 2) * sms;
@@ -463,6 +640,8 @@ static int reduce_entry(const float* d_in, const int64_t* d_labels, int T, int B
     p.literal_clamp = (eps > 0.f && (double)C * eps * fabs(log((double)eps)) > 1e-8) ? 1 : 0;
     p.need_ht = (d_minorm != nullptr && T > 1) ? 1 : 0;
     p.invT = 1.0f / (float)T;
+    p.allow_single = allow_staged ? 1 : 0;
+    p.bins_one_step = (p.n_bins > 0 && one_step_bin_search_ok(p.edges, p.n_bins)) ? 1 : 0;
 
     const bool staged = allow_staged && (HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -491,4 +670,10 @@ extern "C" int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_lab
                                          int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
     return slu::reduce_entry(d_in, d_labels, T, B, C, HW, in_kind, conf_mode, eps, normalize, has_ignore, ignore, n_bins, h_edges,
                              d_pbar, d_pred, d_conf, d_hnorm, d_minorm, d_confmat, d_ece_bins, stream, false);
+}
+
+/* A/B switch for tests and profiles: 1 = T == 1 inputs also go through the multi-sample (staged) kernel. */
+extern "C" int slu_debug_reduce_no_single(int on) {
+    slu::g_reduce_no_single = on ? 1 : 0;
+    return 0;
 }

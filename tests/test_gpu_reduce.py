@@ -156,3 +156,54 @@ def test_argument_errors(cuda):
         ops.reduce_metrics(x, None, kind="alpha")            # alpha needs T == 1
     with pytest.raises(ValueError):
         ops.reduce_metrics(x, None, kind="logits", confmat=ops.new_confmat(20, cuda))    # histogram without labels
+
+
+@pytest.mark.parametrize("shape", [(2, 20, 8, 256), (3, 20, 4, 192), (1, 7, 3, 37), (2, 13, 5, 100), (1, 32, 2, 128), (1, 2, 2, 64), (16, 20, 2, 130)])
+def test_single_sample_kernel_vs_oracle_and_staged(cuda, shape):
+    """T == 1 takes reduce_single_kernel (one thread per pixel, entropy from the softmax sums); it must agree with the
+    oracle to 1e-5 and, on margin-enforced inputs, bit for bit in pred / counts with the multi-sample kernel."""
+    from semanticlidarunc_b200 import _lib
+    B, C, H, W = shape
+    x, lab = synth.synth_mc_logits(100 + B + C, 1, B, C, H, W)
+    x, lab = enforce_margins(x, lab)
+    out, cm, bins, ref = run_both(x, lab, C, cuda)
+    check(out, cm, bins, ref)
+    assert float(out["MI_norm"].abs().max()) == 0.0                  # T == 1: MI is exactly 0 in the reference
+    _lib.lib().slu_debug_reduce_no_single(1)
+    try:
+        out2, cm2, bins2, _ = run_both(x, lab, C, cuda)
+    finally:
+        _lib.lib().slu_debug_reduce_no_single(0)
+    assert torch.equal(out["pred"], out2["pred"]) and torch.equal(cm, cm2) and torch.equal(bins[:2], bins2[:2])
+    assert torch.allclose(out["H_norm"], out2["H_norm"], rtol=1e-5, atol=1e-6)
+    assert torch.equal(out["p_bar"], out2["p_bar"]) and torch.equal(out["conf"], out2["conf"])
+
+
+def test_single_sample_probs_alpha_large_eps_and_neg_inf(cuda):
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn((1, 2, 20, 4, 100), generator=g) * 4.0
+    # probabilities and concentrations (ECE / AUROC modes) through the same kernel
+    probs = torch.softmax(x, dim=2)
+    ref = ou.mc_reduce(x)
+    out = ops.reduce_metrics(probs[0].to(cuda), None, kind="probs", want=("H_norm", "pred", "conf"))
+    ok, aerr, rerr = rel_close(out["H_norm"].cpu().numpy(), ref["H_norm"].numpy(), RTOL, ATOL)
+    assert ok, (aerr, rerr)
+    alpha = torch.rand((2, 20, 4, 100), generator=g) * 30 + 1.0
+    out = ops.reduce_metrics(alpha.to(cuda), None, kind="alpha", want=("conf", "pred"))
+    pa = om.to_probs(alpha, "alpha")
+    assert torch.equal(out["pred"].cpu(), pa.argmax(1))
+    ok, aerr, rerr = rel_close(out["conf"].cpu().numpy(), pa.max(1).values.numpy(), RTOL, 0.0)
+    assert ok, (aerr, rerr)
+    # eps large enough to matter: the literal clamp path
+    out = ops.reduce_metrics(x.to(cuda), None, kind="logits", eps=1e-3, want=("H_norm",))
+    ok, aerr, rerr = rel_close(out["H_norm"].cpu().numpy(), ou.mc_reduce(x, eps=1e-3)["H_norm"].numpy(), RTOL, ATOL)
+    assert ok, (aerr, rerr)
+    # a masked class (-inf logit) and a pixel whose logits are all huge
+    x2 = x.clone()
+    x2[:, :, 5] = float("-inf")
+    x2[:, 0, :, 0, :3] += 80.0
+    out = ops.reduce_metrics(x2.to(cuda), None, kind="logits", want=("H_norm", "pred"))
+    got = out["H_norm"].cpu().numpy()
+    assert np.isfinite(got).all()
+    ok, aerr, rerr = rel_close(got, ou.mc_reduce(x2)["H_norm"].numpy(), RTOL, ATOL)
+    assert ok, (aerr, rerr)
