@@ -131,6 +131,52 @@ __device__ __forceinline__ int find_bin_fast(const float* edges, int n_bins, flo
     k -= (v < lo && k > 0) ? 1 : 0;
     return (v >= edges[0] && v <= edges[n_bins]) ? k : -1;
 }
+
+// ---- per-CTA histogram scratch updated with plain shared-memory atomics ------------------------------------------
+// (single-sample and evidential kernels: one epilogue per pixel, so the warp collectives of warp_bins_add would cost as
+// much as the pixel's arithmetic.)  Counts use ATOMS.POPC.INC.  64-bit shared atomics are CAS loops on sm_100, so
+// sum(conf * 2^32) is kept as two 32-bit halves (low 16 bits | the rest, < 2^17 per pixel): a CTA must flush before a
+// bin has received ATOMIC_HIST_MAX_PX pixels.
+constexpr int ATOMIC_HIST_MAX_PX = 16384;            // 2^17 * 2^14 < 2^32
+struct AtomicHist {
+    unsigned confmat[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
+    unsigned bin_n[SLU_MAX_BINS], bin_c[SLU_MAX_BINS], bin_lo[SLU_MAX_BINS], bin_hi[SLU_MAX_BINS];
+    float edges[SLU_MAX_BINS + 1];
+};
+__device__ __forceinline__ void atomic_hist_zero(AtomicHist& hs, int C, int tid, int nthreads) {
+    for (int i = tid; i < C * C; i += nthreads) hs.confmat[i] = 0;
+    for (int i = tid; i < SLU_MAX_BINS; i += nthreads) { hs.bin_n[i] = 0; hs.bin_c[i] = 0; hs.bin_lo[i] = 0; hs.bin_hi[i] = 0; }
+}
+__device__ __forceinline__ void atomic_hist_flush(AtomicHist& hs, int C, int n_bins, unsigned long long* confmat,
+                                                  unsigned long long* bins, int tid, int nthreads) {
+    if (confmat)
+        for (int i = tid; i < C * C; i += nthreads)
+            if (hs.confmat[i]) atomicAdd(&confmat[i], (unsigned long long)hs.confmat[i]);
+    if (bins)
+        for (int i = tid; i < n_bins; i += nthreads)
+            if (hs.bin_n[i]) {
+                atomicAdd(&bins[i], (unsigned long long)hs.bin_n[i]);
+                if (hs.bin_c[i]) atomicAdd(&bins[n_bins + i], (unsigned long long)hs.bin_c[i]);
+                atomicAdd(&bins[2 * n_bins + i], ((unsigned long long)hs.bin_hi[i] << 16) + hs.bin_lo[i]);
+            }
+}
+// One live pixel: confusion cell (label, pred_cm) and reliability bin of `conf` with correctness pred_ece == label.
+__device__ __forceinline__ void atomic_hist_add(AtomicHist& hs, int C, int n_bins, bool want_cm, bool want_bins, bool one_step,
+                                                long long lab, int pred_cm, int pred_ece, float conf, bool has_ignore, long long ignore) {
+    if (want_cm && (unsigned long long)lab < (unsigned long long)C) atomicAdd(&hs.confmat[(int)lab * C + pred_cm], 1u);   // evaluator.py:49
+    if (want_bins) {
+        const float cf = __saturatef(conf);                                   // ece.py:83 clamp_(0,1)
+        int bin = one_step ? find_bin_fast(hs.edges, n_bins, cf) : find_bin(hs.edges, n_bins, cf);
+        if (conf != conf || (has_ignore && lab == ignore)) bin = -1;          // NaN stays out of every bin
+        if (bin >= 0) {
+            const unsigned long long fx = __float2ull_rn(cf * 4294967296.0f);
+            atomicAdd(&hs.bin_n[bin], 1u);
+            if ((long long)pred_ece == lab) atomicAdd(&hs.bin_c[bin], 1u);
+            atomicAdd(&hs.bin_lo[bin], (unsigned)(fx & 0xffffu));
+            atomicAdd(&hs.bin_hi[bin], (unsigned)(fx >> 16));
+        }
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace slu

@@ -52,23 +52,29 @@ struct EvParams {
     unsigned long long* confmat;
     unsigned long long* bins;
     long long n_px;            // B * HW
+    int bins_one_step;         // edges passed one_step_bin_search_ok()
 };
 
 // EXACT: C == CP, no per-class predicate anywhere;  MI: the AUROC-convention mutual information is requested.
 template <int CP, bool EXACT, bool MI>
 __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_constant__ EvParams p) {
-    __shared__ unsigned s_cm[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
-    __shared__ unsigned s_n[SLU_MAX_BINS], s_c[SLU_MAX_BINS];
-    __shared__ unsigned long long s_s[SLU_MAX_BINS];
-    __shared__ float s_edges[SLU_MAX_BINS + 1];
+    __shared__ AtomicHist hs;
     const int tid = threadIdx.x;
-    for (int i = tid; i < p.C * p.C; i += EV_THREADS) s_cm[i] = 0;
-    for (int i = tid; i < SLU_MAX_BINS; i += EV_THREADS) { s_n[i] = 0; s_c[i] = 0; s_s[i] = 0ull; }
-    for (int i = tid; i <= p.n_bins; i += EV_THREADS) s_edges[i] = p.edges[i];
+    atomic_hist_zero(hs, p.C, tid, EV_THREADS);
+    for (int i = tid; i <= p.n_bins; i += EV_THREADS) hs.edges[i] = p.edges[i];
     __syncthreads();
+    int since_flush = 0;
 
     const long long chunks = (p.n_px + EV_THREADS - 1) / EV_THREADS;
     for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        if (p.labels && ++since_flush > ATOMIC_HIST_MAX_PX / EV_THREADS) {      // CTA-uniform: keep the split sums below 2^32
+            __syncthreads();
+            atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV_THREADS);
+            __syncthreads();
+            atomic_hist_zero(hs, p.C, tid, EV_THREADS);
+            __syncthreads();
+            since_flush = 1;
+        }
         const long long g = ch * EV_THREADS + tid;
         const bool live = g < p.n_px;
         const long long gs = live ? g : p.n_px - 1;
@@ -111,7 +117,9 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
         for (int c = 0; c < CP; ++c) {
             if (EXACT || c < p.C) {
                 asum += a[c];
-                if (c == 0 || a[c] > amax || (a[c] != a[c] && amax == amax)) { amax = a[c]; aarg = c; }
+                const bool gt = (c == 0) | (a[c] > amax) | ((a[c] != a[c]) & (amax == amax));   // torch.argmax: first maximum, NaN maximal
+                amax = gt ? a[c] : amax;
+                aarg = gt ? c : aarg;
             }
         }
         if (p.alpha_out && live) {
@@ -163,30 +171,12 @@ __global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_con
             if (p.eu) p.eu[g] = H - AU;
             if (MI) p.mi[g] = __fdiv_rn(Hm - EHm, p.logC);
         }
-        if (p.labels) {
-            const long long lab = live ? p.labels[g] : -1;
-            if (p.confmat) {
-                const bool ok = live && lab >= 0 && lab < p.C;
-                warp_hist_add(s_cm, ok ? (int)lab * p.C + pred : 0, ok);
-            }
-            if (p.bins) {
-                const float cf = fminf(fmaxf(conf, 0.f), 1.f);
-                const int bin = (conf == conf) ? find_bin(s_edges, p.n_bins, cf) : -1;
-                const bool ok = live && bin >= 0 && !(p.has_ignore && lab == p.ignore);
-                warp_bins_add(s_n, s_c, s_s, bin, (long long)aarg == lab, cf, ok);      // ece.py:75,84: argmax of alpha/alpha0
-            }
-        }
+        if (p.labels && live)       // confusion: tester's argmax of the shape softmax; ECE: argmax of alpha/alpha0 (ece.py:75,84)
+            atomic_hist_add(hs, p.C, p.n_bins, p.confmat != nullptr, p.bins != nullptr, p.bins_one_step != 0, p.labels[g], pred, aarg,
+                            conf, p.has_ignore != 0, p.ignore);
     }
     __syncthreads();
-    if (p.confmat)
-        for (int i = tid; i < p.C * p.C; i += EV_THREADS)
-            if (s_cm[i]) atomicAdd(&p.confmat[i], (unsigned long long)s_cm[i]);
-    if (p.bins)
-        for (int i = tid; i < p.n_bins; i += EV_THREADS) {
-            if (s_n[i]) atomicAdd(&p.bins[i], (unsigned long long)s_n[i]);
-            if (s_c[i]) atomicAdd(&p.bins[p.n_bins + i], (unsigned long long)s_c[i]);
-            if (s_s[i]) atomicAdd(&p.bins[2 * p.n_bins + i], s_s[i]);
-        }
+    atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV_THREADS);
 }
 
 template <int CP>
@@ -234,6 +224,7 @@ extern "C" int slu_evidential_reduce(const float* d_outputs, const float* d_alph
     p.has_ignore = has_ignore; p.ignore = ignore;
     p.n_bins = d_ece_bins ? n_bins : 0;
     for (int i = 0; i <= p.n_bins && d_ece_bins; ++i) p.edges[i] = h_edges[i];
+    p.bins_one_step = (p.n_bins > 0 && one_step_bin_search_ok(p.edges, p.n_bins)) ? 1 : 0;
     p.alpha_out = d_alpha_out; p.pred = reinterpret_cast<long long*>(d_pred);
     p.conf = d_conf; p.h = d_h; p.au = d_au; p.eu = d_eu; p.mi = d_mi;
     p.confmat = reinterpret_cast<unsigned long long*>(d_confmat);

@@ -396,39 +396,13 @@ __global__ void __launch_bounds__(TILE, 2) reduce_direct_kernel(const __grid_con
 // flight per thread, 160 KB per SM), grid-stride over tiles so the shared-memory histograms are flushed once per CTA.
 // =====================================================================================================
 constexpr int SINGLE_THREADS = 128;
-constexpr int SINGLE_FLUSH_TILES = 128;      // 2^17 * 128 px * 128 tiles < 2^32: the split confidence sums cannot overflow
-
-// Per-CTA histogram scratch of the single-sample kernel: plain shared-memory atomics (ATOMS.POPC.INC for the counts).
-// 64-bit shared atomics are CAS loops on sm_100, so sum(conf * 2^32) is kept as two 32-bit halves (low 16 bits, rest).
-struct SingleHist {
-    unsigned confmat[SLU_MAX_CLASSES * SLU_MAX_CLASSES];
-    unsigned bin_n[SLU_MAX_BINS], bin_c[SLU_MAX_BINS], bin_lo[SLU_MAX_BINS], bin_hi[SLU_MAX_BINS];
-    float edges[SLU_MAX_BINS + 1];
-};
-
-__device__ __forceinline__ void single_hist_zero(SingleHist& hs, const ReduceParams& p, int tid) {
-    for (int i = tid; i < p.C * p.C; i += SINGLE_THREADS) hs.confmat[i] = 0;
-    for (int i = tid; i < SLU_MAX_BINS; i += SINGLE_THREADS) { hs.bin_n[i] = 0; hs.bin_c[i] = 0; hs.bin_lo[i] = 0; hs.bin_hi[i] = 0; }
-}
-__device__ __forceinline__ void single_hist_flush(SingleHist& hs, const ReduceParams& p, int tid) {
-    if (p.confmat)
-        for (int i = tid; i < p.C * p.C; i += SINGLE_THREADS)
-            if (hs.confmat[i]) atomicAdd(&p.confmat[i], (unsigned long long)hs.confmat[i]);
-    if (p.bins)
-        for (int i = tid; i < p.n_bins; i += SINGLE_THREADS) {
-            if (hs.bin_n[i]) {
-                atomicAdd(&p.bins[i], (unsigned long long)hs.bin_n[i]);
-                if (hs.bin_c[i]) atomicAdd(&p.bins[p.n_bins + i], (unsigned long long)hs.bin_c[i]);
-                atomicAdd(&p.bins[2 * p.n_bins + i], ((unsigned long long)hs.bin_hi[i] << 16) + hs.bin_lo[i]);
-            }
-        }
-}
+constexpr int SINGLE_FLUSH_TILES = ATOMIC_HIST_MAX_PX / SINGLE_THREADS;   // the split confidence sums cannot overflow
 
 template <int CP, int KIND, bool EXACT>
 __global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const __grid_constant__ ReduceParams p) {
-    __shared__ SingleHist hs;
+    __shared__ AtomicHist hs;
     const int tid = threadIdx.x;
-    single_hist_zero(hs, p, tid);
+    atomic_hist_zero(hs, p.C, tid, SINGLE_THREADS);
     for (int i = tid; i <= p.n_bins; i += SINGLE_THREADS) hs.edges[i] = p.edges[i];
     __syncthreads();
     const float pad = (KIND == SLU_IN_LOGITS) ? -1.0e30f : 0.f;
@@ -438,9 +412,9 @@ __global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (p.labels && ++since_flush > SINGLE_FLUSH_TILES) {        // CTA-uniform
             __syncthreads();
-            single_hist_flush(hs, p, tid);
+            atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, SINGLE_THREADS);
             __syncthreads();
-            single_hist_zero(hs, p, tid);
+            atomic_hist_zero(hs, p.C, tid, SINGLE_THREADS);
             __syncthreads();
             since_flush = 1;
         }
@@ -524,23 +498,12 @@ __global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const 
         }
         if (p.labels && live) {
             const long long lab = p.labels[o];
-            if (p.confmat && (unsigned long long)lab < (unsigned long long)p.C) atomicAdd(&hs.confmat[(int)lab * p.C + arg], 1u);
-            if (p.bins) {
-                const float cf = __saturatef(conf);                                   // ece.py:83 clamp_(0,1)
-                int bin = p.bins_one_step ? find_bin_fast(hs.edges, p.n_bins, cf) : find_bin(hs.edges, p.n_bins, cf);
-                if (conf != conf || (p.has_ignore && lab == p.ignore)) bin = -1;      // NaN stays out of every bin
-                if (bin >= 0) {
-                    const unsigned long long fx = __float2ull_rn(cf * 4294967296.0f);
-                    atomicAdd(&hs.bin_n[bin], 1u);
-                    if ((long long)arg == lab) atomicAdd(&hs.bin_c[bin], 1u);
-                    atomicAdd(&hs.bin_lo[bin], (unsigned)(fx & 0xffffu));
-                    atomicAdd(&hs.bin_hi[bin], (unsigned)(fx >> 16));
-                }
-            }
+            atomic_hist_add(hs, p.C, p.n_bins, p.confmat != nullptr, p.bins != nullptr, p.bins_one_step != 0, lab, arg, arg, conf,
+                            p.has_ignore != 0, p.ignore);
         }
     }
     __syncthreads();
-    single_hist_flush(hs, p, tid);
+    atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, SINGLE_THREADS);
 }
 
 template <int CP, int KIND>
