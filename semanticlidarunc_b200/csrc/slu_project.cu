@@ -120,6 +120,7 @@ struct ProjParams {
     float* part_min;               // [B*gx] per-block fp32 theta min
     float* part_max;               // [B*gx]
     int* part_diag;                // [B*gx*2] per-block (missing ids, near-edge points)
+    double* part_exact;            // [B*gx*2] per-block exact fp64 theta (min, max) over the block's candidates
     int gx;                        // blocks per scan of the point kernels
     // outputs
     int* pix;                      // [n_total]
@@ -367,68 +368,70 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     const int w = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) { s_min[w] = tmin; s_max[w] = tmax; s_miss[w] = missing; s_near[w] = near_cnt; }
     __syncthreads();
+    const long long slot = (long long)b * p.gx + blockIdx.x;           // every block writes its slot: no init needed
+    float bmin = s_min[0], bmax = s_max[0];
+    for (int i = 1; i < PT_THREADS / 32; ++i) { bmin = fminf(bmin, s_min[i]); bmax = fmaxf(bmax, s_max[i]); }
     if (threadIdx.x == 0) {
-        for (int i = 1; i < PT_THREADS / 32; ++i) {
-            tmin = fminf(tmin, s_min[i]); tmax = fmaxf(tmax, s_max[i]);
-            missing += s_miss[i]; near_cnt += s_near[i];
-        }
-        const long long slot = (long long)b * p.gx + blockIdx.x;       // every block writes its slot: no init needed
-        p.part_min[slot] = tmin; p.part_max[slot] = tmax;
+        for (int i = 1; i < PT_THREADS / 32; ++i) { missing += s_miss[i]; near_cnt += s_near[i]; }
+        p.part_min[slot] = bmin; p.part_max[slot] = bmax;
         p.part_diag[2 * slot] = missing; p.part_diag[2 * slot + 1] = near_cnt;
+    }
+    if (p.use_range) return;
+    // Exact fp64 theta min/max of the scan without a second pass over the points: the point P that attains the exact
+    // minimum satisfies theta32(P) <= theta(P) + m/2 <= theta(Q) + m/2 <= theta32(Q) + m for every Q, in particular for
+    // the Q of its own block, so it is among the block's points within the margin m of the BLOCK's fp32 minimum (same
+    // for the maximum).  Each block evaluates those few candidates in fp64 and publishes its exact (min, max); the row
+    // kernel reduces the gx partials.  (The separate extremes launch of the first version is gone.)
+    const float m = (float)ANGLE_MARGIN;
+    double emin = INFINITY, emax = -INFINITY;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        const float t = p.theta32[n];                      // written by this same thread above
+        if (t <= bmin + m || t >= bmax - m || t != t) {
+            const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
+            if (th == th) { emin = fmin(emin, th); emax = fmax(emax, th); }
+        }
+    }
+    __shared__ double s_emin[PT_THREADS / 32], s_emax[PT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_emin[w] = emin; s_emax[w] = emax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < PT_THREADS / 32; ++i) { emin = fmin(emin, s_emin[i]); emax = fmax(emax, s_emax[i]); }
+        p.part_exact[2 * slot] = emin; p.part_exact[2 * slot + 1] = emax;
     }
 }
 
-// fp32 min/max of the scan from the per-block partials (every block reduces them again: <= gx values)
-__device__ __forceinline__ void scan_minmax32(const ProjParams& p, int b, float& lo, float& hi) {
-    __shared__ float s_lo[PT_THREADS / 32], s_hi[PT_THREADS / 32];
-    float a = INFINITY, c = -INFINITY;
+// exact fp64 theta range of scan b from the angle kernel's per-block partials (block-wide call)
+__device__ __forceinline__ void scan_theta_range_fast(const ProjParams& p, int b, double& lo, double& hi) {
+    if (p.use_range) { lo = p.theta_lo; hi = p.theta_hi; return; }
+    __shared__ double s_lo[PT_THREADS / 32], s_hi[PT_THREADS / 32];
+    double a = INFINITY, c = -INFINITY;
     for (int i = threadIdx.x; i < p.gx; i += blockDim.x) {
-        a = fminf(a, p.part_min[(long long)b * p.gx + i]);
-        c = fmaxf(c, p.part_max[(long long)b * p.gx + i]);
+        a = fmin(a, p.part_exact[2 * ((long long)b * p.gx + i)]);
+        c = fmax(c, p.part_exact[2 * ((long long)b * p.gx + i) + 1]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        a = fminf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        c = fmaxf(c, __shfl_xor_sync(0xffffffffu, c, o));
+        a = fmin(a, __shfl_xor_sync(0xffffffffu, a, o));
+        c = fmax(c, __shfl_xor_sync(0xffffffffu, c, o));
     }
     if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = a; s_hi[threadIdx.x >> 5] = c; }
     __syncthreads();
     a = s_lo[0]; c = s_hi[0];
-    for (int i = 1; i < PT_THREADS / 32; ++i) { a = fminf(a, s_lo[i]); c = fmaxf(c, s_hi[i]); }
+    for (int i = 1; i < PT_THREADS / 32; ++i) { a = fmin(a, s_lo[i]); c = fmax(c, s_hi[i]); }
+    if (!(a <= c)) { a = 0.0; c = 0.0; }                   // empty scan (or no finite angle)
     lo = a; hi = c;
-}
-
-// exact fp64 theta min/max: only points within the margin of the fp32 extremes are evaluated in fp64
-__global__ void __launch_bounds__(PT_THREADS) proj_fast_extremes_kernel(const __grid_constant__ ProjParams p) {
-    const int b = blockIdx.y;
-    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
-    float lo32, hi32;
-    scan_minmax32(p, b, lo32, hi32);
-    const float m = (float)ANGLE_MARGIN;
-    double tmin = INFINITY, tmax = -INFINITY;
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const float t = p.theta32[n];
-        if (t <= lo32 + m || t >= hi32 - m || t != t) {
-            const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
-            if (th == th) { tmin = fmin(tmin, th); tmax = fmax(tmax, th); }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-        tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    }
-    if ((threadIdx.x & 31) == 0 && tmin <= tmax) {
-        atomicMin(&p.tminmax[2 * b], order_bits(tmin));
-        atomicMax(&p.tminmax[2 * b + 1], order_bits(tmax));
-    }
 }
 
 __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
     double lo, hi;
-    scan_theta_range(p, b, lo, hi);
+    scan_theta_range_fast(p, b, lo, hi);
     const Edges eh = make_edges(lo, hi, p.H);
     const FastEdges fh = make_fast_edges(eh);
     __shared__ int s_q[DEFER_CAP];
@@ -555,7 +558,7 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 
 constexpr int MAX_GX = 2048;         // upper bound of blocks per scan (partials are sized for it)
 struct Workspace {
-    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, theta32, part_min, part_max, part_diag, total;
+    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, theta32, part_min, part_max, part_diag, part_exact, total;
 };
 static Workspace carve(int64_t n_total, int B, int64_t HW) {
     Workspace w;
@@ -573,6 +576,7 @@ static Workspace carve(int64_t n_total, int B, int64_t HW) {
     w.part_min = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
     w.part_max = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
     w.part_diag = o; o = align_up(o + (int64_t)B * gx_max * 8, 256);
+    w.part_exact = o; o = align_up(o + (int64_t)B * gx_max * 16, 256);
     w.total = o;
     return w;
 }
@@ -611,16 +615,13 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     p.part_min = reinterpret_cast<float*>(base + w.part_min);
     p.part_max = reinterpret_cast<float*>(base + w.part_max);
     p.part_diag = reinterpret_cast<int*>(base + w.part_diag);
+    p.part_exact = reinterpret_cast<double*>(base + w.part_exact);
     const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
     p.gx = (int)gp.x;
     if (!generic && !exact_only()) {
-        // fp32-prefiltered path: angles(+init) -> [exact extremes] -> rows -> ties
+        // fp32-prefiltered path: angles (+ init, + exact theta extremes per block) -> rows -> ties
         proj_fast_angles_kernel<<<gp, PT_THREADS, 0, st>>>(p);
         SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
-        if (!p.use_range && n_total > 0) {
-            proj_fast_extremes_kernel<<<gp, PT_THREADS, 0, st>>>(p);
-            SLU_LAUNCH_CHECK("proj_fast_extremes_kernel");
-        }
         proj_fast_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);
         SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
         if (n_total > 0) {

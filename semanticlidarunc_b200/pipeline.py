@@ -3,7 +3,7 @@
 `ScanEvaluator` is the call a user of the reference's test loop makes instead of the MC block of
 Tester.test_epoch (src/models/tester.py:395-471) plus the loader's projection
 (src/dataset/dataloader_semantic_KITTI.py:35-97): it owns the device accumulators (confusion
-matrix, reliability bins), runs a batch of scans with 7 kernel launches and never synchronises
+matrix, reliability bins), runs a batch of scans with 6 kernel launches and never synchronises
 until `summary()`.
 
   step_device(...)  inputs already in HBM (what a GPU backbone hands over)
@@ -63,7 +63,7 @@ class ScanEvaluator:
             timing[1].record()
         red["point_labels"] = ops.backproject(red["pred"], proj["pix"], offsets)
         red["img"], red["label"], red["pix"] = proj["img"], proj["label"], proj["pix"]
-        self.launches += 7                # init, angles, rows, ties, resolve | reduce | back-project
+        self.launches += 6                # angles(+init,+extremes), rows, ties, resolve | reduce | back-project
         return red
 
     # ---------------------------------------------------------------- host buffers, pipelined
