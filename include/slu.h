@@ -34,6 +34,7 @@ extern "C" {
 #define SLU_E_RANGE    (-2)        /* size outside what the kernels support           */
 #define SLU_E_ALIGN    (-3)        /* pointer not aligned as documented               */
 #define SLU_E_DEVICE   (-4)        /* not an sm_100 device / no device                */
+#define SLU_E_IO       (-5)        /* a scan file could not be read / is malformed    */
 
 #define SLU_MAX_CLASSES 32         /* register-resident class axis                    */
 #define SLU_MAX_BINS    64         /* reliability bins                                */
@@ -331,6 +332,30 @@ int slu_organized_planes(const float* d_xyzi, const uint32_t* d_raw_label, const
  */
 int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix, const int64_t* h_offsets,
                     int64_t n_total, int B, int64_t HW, int64_t* d_out, slu_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-disk scans to HBM: native I/O threads read KITTI-style files into pinned host slots and
+ * the consumer copies them to the device on its own stream.
+ * Replaces: np.fromfile(frame_path, float32).reshape(-1,4) / np.fromfile(label_path, uint32) at the top of every
+ *           loader's __getitem__ (src/dataset/dataloader_semantic_KITTI.py:35-39) and the pageable H2D copy of
+ *           the batch (src/models/trainer.py:520-527).
+ *   slu_stager_create   n_slots pinned slots of max_points_per_scan points (20 B/point) and n_io_threads readers on
+ *                       the CURRENT device; the stager owns them until slu_stager_destroy.  flags: 0, or
+ *                       SLU_STAGER_HOST_DEST = pageable slots and HOST destination pointers in slu_stager_fetch
+ *                       (no CUDA call at all: exercises the reader threads and the error paths on a box without a GPU).
+ *   slu_stager_submit   queue (bin_path, label_path or NULL) -> ticket (0, 1, 2, ... in submission order).
+ *   slu_stager_fetch    wait until that scan is in a slot, enqueue H2D copies of its points [n,4] float32 to d_xyzi
+ *                       and raw labels [n] uint32 to d_label (skipped if NULL / no label file) on `stream`; the slot
+ *                       is recycled when those copies complete.  Fetch tickets in submission order.
+ *                       Errors: SLU_E_IO (missing file, size not a multiple of 16 B, label count != point count),
+ *                       SLU_E_RANGE (scan larger than capacity_points or than the slot).
+ */
+#define SLU_STAGER_HOST_DEST 1
+int slu_stager_create(int n_slots, int64_t max_points_per_scan, int n_io_threads, int flags, void** out_handle);
+int slu_stager_submit(void* handle, const char* bin_path, const char* label_path, int64_t* out_ticket);
+int slu_stager_fetch(void* handle, int64_t ticket, float* d_xyzi, uint32_t* d_label, int64_t capacity_points,
+                     int64_t* out_n_points, int* out_has_label, slu_stream_t stream);
+int slu_stager_destroy(void* handle);
 
 /* ---------------------------------------------------------------------------------------------
  * Diagnostic: stream n float32 from d_in once (16-byte loads, grid = 8 CTAs/SM) and write one

@@ -51,6 +51,10 @@ SIGNATURES = {
     "slu_organized_planes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "slu_frame_tensors": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _i, _p]),
     "slu_backproject": (_i, [_p, _p, _p, _i64, _i, _i64, _p, _p]),
+    "slu_stager_create": (_i, [_i, _i64, _i, _i, C.POINTER(C.c_void_p)]),
+    "slu_stager_submit": (_i, [_p, C.c_char_p, C.c_char_p, C.POINTER(_i64)]),
+    "slu_stager_fetch": (_i, [_p, _i64, _p, _p, _i64, C.POINTER(_i64), C.POINTER(_i), _p]),
+    "slu_stager_destroy": (_i, [_p]),
     "slu_diag_read_stream": (_i, [_p, _i64, _p, _p]),
 }
 
@@ -91,6 +95,8 @@ def check(rc: int, what: str):
     if rc == 0:
         return
     msg = lib().slu_last_error().decode(errors="replace")
+    if rc == -5:
+        raise OSError(f"{what}: {msg}")
     if rc < 0:
         raise ValueError(f"{what}: {msg} (slu error {rc})")
     raise SluError(f"{what}: CUDA error {rc}: {msg}")

@@ -67,6 +67,37 @@ class SemanticKitti(Dataset):
         out["pix"], out["offsets"], out["missing_label_ids"] = proj["pix"], offs, missing
         return self._finish(out)
 
+    def staged_batches(self, indices, batch_size: int = 16, n_slots: int = 32, n_io_threads: int = 4, max_points: int = 300_000):
+        """Yield `device_batch`-style dicts for `indices` in chunks of `batch_size`, the files read by libslu's native
+        I/O threads (dataset/stager.py) one batch ahead of the projection kernels.  Augmentations are drawn per scan
+        from numpy's global RNG in the reference's order, as in __getitem__."""
+        from .stager import ScanStager
+        dev = self._dev()
+        indices = list(indices)
+        with ScanStager(n_slots=max(n_slots, 2 * batch_size), max_points=max_points, n_io_threads=n_io_threads, device=dev) as st:
+            chunks = [indices[i:i + batch_size] for i in range(0, len(indices), batch_size)]
+            tickets = [[st.submit(*self.data_path[j]) for j in chunks[0]]] if chunks else []
+            for k, chunk in enumerate(chunks):
+                if k + 1 < len(chunks):                                  # the next batch's files are read while this one runs
+                    tickets.append([st.submit(*self.data_path[j]) for j in chunks[k + 1]])
+                xyzi = torch.empty((len(chunk) * max_points, 4), dtype=torch.float32, device=dev)
+                raw = torch.empty((len(chunk) * max_points,), dtype=torch.int32, device=dev)
+                offs, pos = [0], 0
+                for t in tickets[k]:
+                    n, has = st.fetch_into(t, xyzi[pos:pos + max_points], raw[pos:pos + max_points])
+                    if not has:
+                        raw[pos:pos + n].zero_()
+                    pos += n
+                    offs.append(pos)
+                aug = [self._draw_augmentation() for _ in chunk]
+                yaw = [0.0 if a[0] is None else a[0] for a in aug] if self.rotate else None
+                offs = np.asarray(offs, dtype=np.int64)
+                proj = ops.project_batch(xyzi[:pos], raw[:pos], offs, self.projection[0], self.projection[1], lut=self._lut,
+                                         yaw_deg=yaw, theta_range=self.THETA_RANGE, want_label=False)
+                out = self._frame(proj["img"], [a[1] for a in aug])
+                out["pix"], out["offsets"], out["missing_label_ids"] = proj["pix"], offs, proj["diag"][:, 0]
+                yield self._finish(out)
+
     def _frame(self, img, flip):
         return ops.frame_tensors(img, out_hw=self.RESIZE_TO if self.resize else None, flip=flip)
 
