@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[1]): a batch of 16 SemanticKITTI-shaped scans (HDL-64, 120 000
 points -> 64x2048) with MC-dropout logits [T=20, B=16, C=20, 64, 2048] fp32.  One step = one batch:
-  projection (5 launches) -> fused MC reduction + confusion/ECE histograms (1) -> label back-projection (1).
+  projection (4 launches) -> fused MC reduction + confusion/ECE histograms (1) -> label back-projection (1).
 Synthetic seeded inputs (datasets are not available offline).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path

@@ -63,7 +63,7 @@ for sensor, B in (("hdl64", 1), ("hdl64", 16), ("os1-128", 1), ("os1-128", 16)):
     res = ops.project_batch(xyzi, raw, offs, H, W, lut=lut)
     ws = res["workspace"]
     n = int(offs[-1])
-    add(f"projection {sensor} B={B}", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws), 20 * n + 24 * B * H * W, B, "5 launches")
+    add(f"projection {sensor} B={B}", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws), 20 * n + 24 * B * H * W, B, "4 launches")
     lab_img, pix = res["label"], res["pix"]
     add(f"back-projection {sensor} B={B}", lambda: ops.backproject(lab_img, pix, offs), 8 * n + 8 * B * H * W, B)
 

@@ -56,7 +56,7 @@ for sensor, B in (("hdl64", 1), ("hdl64", 16), ("os1-128", 1), ("os1-128", 16)):
         return r
     res = proj()
     n = int(offs[-1])
-    rows.append(row(f"projection {sensor} B={B}", timeit(proj, flush_l2=True), 20 * n + 24 * B * H * W, B, "scans", "5 launches, L2 flushed between runs"))
+    rows.append(row(f"projection {sensor} B={B}", timeit(proj, flush_l2=True), 20 * n + 24 * B * H * W, B, "scans", "4 launches, L2 flushed between runs"))
     lab_img = res["label"]
     rows.append(row(f"back-projection {sensor} B={B}", timeit(lambda: ops.backproject(lab_img, res["pix"], offs), flush_l2=True),
                     8 * n + 8 * B * H * W, B, "scans", "pix int32 in, int64 out, int64 label image"))
@@ -75,7 +75,7 @@ for B in (1, 16):
     rows.append(row(f"single-pass softmax entropy+ECE T=1 B={B}", timeit(f1, flush_l2=True), (4 * C + 32) * B * H * W, B, "scans", "config 1 shape"))
     ev = torch.randn((B, C + 1, H, W), generator=g, device=dev) * 3.0
     fe = lambda: ops.evidential_reduce(ev, labels, from_outputs=True, ignore_index=0, confmat=cm, ece_bins=bins)
-    rows.append(row(f"evidential reduce+metrics B={B}", timeit(fe, flush_l2=True), (4 * (C + 1) + 8 + 8 + 5 * 4) * B * H * W, B, "scans", "digamma-bound"))
+    rows.append(row(f"evidential reduce+metrics B={B}", timeit(fe, flush_l2=True), (4 * (C + 1) + 8 + 8 + 5 * 4) * B * H * W, B, "scans", "MUFU / issue-bound"))
     alpha = (torch.nn.functional.softplus(ev[:, :C]) + 1.0).requires_grad_(True)
     mse, kl = DirichletMSELoss(ignore_index=0), KL_offClasses_to_uniform(ignore_index=0)
     def loss_step():
