@@ -320,9 +320,16 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     __syncthreads();
     float tmin = INFINITY, tmax = -INFINITY;
     int missing = 0, near_cnt = 0;
+    const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
+    int pend_lut = 0;
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
-        if (p.raw_label && p.lut && __ldg(p.lut + (__ldg(p.raw_label + n) & 0xffffu)) < 0) ++missing;
+        const float4 v4 = __ldg(p.xyzi + n);
+        // label-id check (the reference raises KeyError on ids outside id_map, dataloader_semantic_KITTI.py:47): the raw
+        // label is loaded together with the point, its LUT gather is issued here and only tested one iteration later,
+        // so neither load stalls the angle arithmetic
+        const unsigned raw = check_ids ? (__ldg(p.raw_label + n) & 0xffffu) : 0u;
+        missing += pend_lut < 0 ? 1 : 0;
+        const Pt q = load_pt(p, b, v4);
         const double x = q.x, y = q.y, z = q.z;
         const float4 v = make_float4((float)x, (float)y, (float)z, 0.f);     // fp32 view for the prefilter
         const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
@@ -331,6 +338,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         const float phi32 = atan2f(v.y, v.x);
         const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
         p.theta32[n] = th32;
+        pend_lut = check_ids ? __ldg(p.lut + raw) : 0;          // tested at the top of the next iteration
         if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
         int cnt_w = fast_count_le(fw, phi32);
         if (cnt_w < 0) {
@@ -346,6 +354,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         if (c < 0) c += p.W;
         p.col[n] = c;
     }
+    missing += pend_lut < 0 ? 1 : 0;
     __syncthreads();
     for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
         const long long n = n0 + s_q[i];
@@ -452,7 +461,11 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         if ((threadIdx.x & 31) == 0 && missing) atomicAdd(&p.diag[2 * b], missing);
     }
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        int cnt_h = fast_count_le(fh, p.theta32[n]);
+        // all three per-point loads are issued before the first use: one memory wait per point instead of three
+        const float t32 = p.theta32[n];
+        const int col = p.col[n];
+        const unsigned long long rk = p.rkey[n];
+        int cnt_h = fast_count_le(fh, t32);
         if (cnt_h < 0) {
             const int slot = atomicAdd(&s_qn, 1);
             if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
@@ -464,9 +477,9 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         }
         int r = (p.H - 1 - cnt_h) % p.H;
         if (r < 0) r += p.H;
-        const int px = r * p.W + p.col[n];
+        const int px = r * p.W + col;
         p.pix[n] = px;
-        atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
+        atomicMin(&p.key[(long long)b * p.HW + px], rk);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
@@ -490,8 +503,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_cons
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const long long cell = (long long)b * p.HW + p.pix[n];
-        if (p.rkey[n] == p.key[cell]) atomicMin(&p.winner[cell], (int)(n - n0));
+        const int px = p.pix[n];
+        const unsigned long long rk = p.rkey[n];
+        const long long cell = (long long)b * p.HW + px;
+        if (rk == p.key[cell]) atomicMin(&p.winner[cell], (int)(n - n0));
     }
 }
 
