@@ -207,3 +207,48 @@ def test_single_sample_probs_alpha_large_eps_and_neg_inf(cuda):
     assert np.isfinite(got).all()
     ok, aerr, rerr = rel_close(got, ou.mc_reduce(x2)["H_norm"].numpy(), RTOL, ATOL)
     assert ok, (aerr, rerr)
+
+
+def test_full_size_batch_properties(cuda):
+    """BASELINE.json configs[1] at full size ([T=20,B=16,C=20,64,2048] fp32 = 3.36 GB; the oracle cannot run this in
+    seconds): size-independent properties, the two load paths against each other, and an oracle check on a slice."""
+    T, B, C, H, W = 20, 16, 20, 64, 2048
+    g = torch.Generator(device=cuda).manual_seed(2024)
+    x = torch.randn((T, B, C, H, W), generator=g, device=cuda) * 3.0
+    lab = torch.randint(-1, C + 1, (B, H, W), generator=g, device=cuda)            # includes out-of-range labels
+    cm, bins = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    out = ops.reduce_metrics(x, lab, kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0, confmat=cm, ece_bins=bins,
+                             want=("p_bar", "pred", "conf", "H_norm", "MI_norm"))
+    # histogram invariants (a checksum of the counts)
+    assert int(cm.sum()) == int(((lab >= 0) & (lab < C)).sum())
+    assert int(bins[0].sum()) == int((lab != 0).sum()) and bool((bins[1] <= bins[0]).all())
+    assert torch.equal(cm.sum(dim=1), torch.bincount(lab[(lab >= 0) & (lab < C)].reshape(-1), minlength=C))
+    # the maps are consistent with the kernel's own mean distribution
+    pb = out["p_bar"]
+    assert torch.equal(out["pred"], pb.argmax(dim=1))
+    assert float((pb.sum(dim=1) - 1.0).abs().max()) < 2e-6
+    assert torch.allclose(out["conf"], pb.max(dim=1).values / pb.clamp_min(0).sum(dim=1), rtol=1e-6, atol=0)
+    assert float(out["H_norm"].min()) >= 0.0 and float(out["H_norm"].max()) <= 1.0 + 1e-6
+    assert float(out["MI_norm"].min()) >= 0.0 and bool((out["MI_norm"] <= out["H_norm"] + 1e-6).all())
+    # shard additivity: the two halves of the batch add up to the whole (what the multi-GPU all-reduce relies on)
+    cm2, bins2 = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    for sl in (slice(0, 8), slice(8, 16)):
+        ops.reduce_metrics(x[:, sl].contiguous(), lab[sl], kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0, confmat=cm2,
+                           ece_bins=bins2, want=())
+    assert torch.equal(cm, cm2) and torch.equal(bins, bins2)
+    # TMA-staged and direct-load kernels run the same arithmetic: bit-identical maps and counts
+    cm3, bins3 = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    out3 = ops.reduce_metrics(x, lab, kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0, confmat=cm3, ece_bins=bins3,
+                              want=("pred", "conf", "H_norm", "MI_norm"), direct=True)
+    assert torch.equal(cm, cm3) and torch.equal(bins, bins3)
+    for k in ("pred", "conf", "H_norm", "MI_norm"):
+        assert torch.equal(out[k], out3[k]), k
+    # oracle on the last scan's last two image rows (offsets at full-size strides)
+    xs = x[:, 15:16, :, 62:64, :].cpu()
+    ref = ou.mc_reduce(xs)
+    for k in ("H_norm", "MI_norm"):
+        ok, aerr, rerr = rel_close(out[k][15:16, 62:64].cpu().numpy(), ref[k].numpy(), RTOL, ATOL)
+        assert ok, f"{k}: abs {aerr:.3e} rel {rerr:.3e}"
+    top = ref["p_bar"].topk(2, dim=1).values
+    safe = (top[:, 0] - top[:, 1]) > 1e-5
+    assert torch.equal(out["pred"][15:16, 62:64].cpu()[safe], ref["pred"][safe])
