@@ -528,7 +528,12 @@ static int launch(const ReduceParams& p, bool staged, cudaStream_t stream) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long max_ctas = (long long)(staged ? Occ<CP>::staged : 2) * sms;
-    const int grid = (int)(p.n_tiles < max_ctas ? p.n_tiles : max_ctas);
+    // balanced persistent grid: every CTA gets the same number of tiles (+-1).  With 512 tiles (one HDL-64 scan) on 444
+    // resident CTAs, 68 CTAs would run a second tile alone at a fraction of the HBM bandwidth; 256 CTAs x 2 tiles finish
+    // together.  Large batches keep every resident slot busy (more bytes in flight; the last partial wave is < 1/19 there).
+    const long long waves = (p.n_tiles + max_ctas - 1) / max_ctas;
+    const long long full = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
+    const int grid = (int)(waves <= 4 ? (p.n_tiles + waves - 1) / waves : full);     // many waves: the imbalance is < 1/waves
     if (staged) {
         const size_t dyn = (size_t)STAGES * p.C * TILE * sizeof(float);
         SLU_CUDA(cudaFuncSetAttribute(reduce_staged_kernel<CP, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
