@@ -252,3 +252,29 @@ def test_full_size_batch_properties(cuda):
     top = ref["p_bar"].topk(2, dim=1).values
     safe = (top[:, 0] - top[:, 1]) > 1e-5
     assert torch.equal(out["pred"][15:16, 62:64].cpu()[safe], ref["pred"][safe])
+
+
+def test_periodic_histogram_flush_in_long_sweeps(cuda):
+    """The single-sample and evidential kernels keep sum(conf * 2^32) as two 32-bit halves per CTA and flush them to the
+    int64 accumulators before they can overflow.  160 scans in one launch make every CTA flush in mid-loop; the two
+    80-scan halves stay below the threshold.  All counters, including the fixed-point confidence sums, must be equal."""
+    B, C, H, W = 160, 20, 64, 2048
+    g = torch.Generator(device=cuda).manual_seed(7)
+    x = torch.randn((B, C + 1, H, W), generator=g, device=cuda) * 3.0
+    lab = torch.randint(0, C, (B, H, W), generator=g, device=cuda)
+
+    def single(xs, ls, cm, bins):
+        ops.reduce_metrics(xs[:, :C].contiguous(), ls, kind="logits", conf_mode=ops.CONF_RENORM, ignore_index=0, confmat=cm, ece_bins=bins, want=())
+
+    def evid(xs, ls, cm, bins):
+        ops.evidential_reduce(xs, ls, from_outputs=True, ignore_index=0, confmat=cm, ece_bins=bins, want=())
+
+    for fn in (single, evid):
+        cm, bins = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+        fn(x, lab, cm, bins)
+        cm2, bins2 = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+        fn(x[:80], lab[:80], cm2, bins2)
+        fn(x[80:], lab[80:], cm2, bins2)
+        assert int(cm.sum()) == B * H * W
+        assert torch.equal(cm, cm2) and torch.equal(bins, bins2), fn.__name__
+        assert int(bins[2].max()) > 2 ** 40                     # far beyond what a 32-bit half could hold
