@@ -154,11 +154,18 @@ int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target, const uint
  * alpha transform.  C >= 3 (the reference's MSE term is defined as 0 for C <= 2).
  *   d_outputs [B,C+1,HW];  d_sums [3] float64 must be ZERO on entry: sum mse | sum kl | n_valid on exit;
  *   loss = (w_mse*sums[0] + w_kl*sums[1]) / max(sums[2],1);  d_grad_outputs [B,C+1,HW] or NULL.
+ *   precounted != 0: d_sums[2] already holds the number of valid pixels the mean runs over (d_sums[0..1] zero) and no
+ *   count kernel is launched -- the batch-sharded training step: every rank counts its pixels (slu_count_valid), the
+ *   counts are all-reduced, and each rank's gradient and loss share come out as fractions of the GLOBAL mean.
  */
 int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
                               int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
                               float temperature, float eps_alpha, float eps_mse, float eps_kl,
-                              float w_mse, float w_kl, double* d_sums, float* d_grad_outputs, slu_stream_t stream);
+                              float w_mse, float w_kl, int precounted, double* d_sums, float* d_grad_outputs, slu_stream_t stream);
+
+/* Number of valid pixels (validity as in slu_dirichlet_loss), ADDED to d_count[0] (float64). */
+int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t n_px,
+                    const int64_t* h_ignore, int n_ignore, double* d_count, slu_stream_t stream);
 
 /* Alternative data-fit terms, one per call, forward + analytic backward.
  * Replaces: NLLDirichletCategorical (src/losses/dirichlet_losses.py:73-119), DigammaDirichletCE (:122-167),

@@ -34,7 +34,8 @@ SIGNATURES = {
     "slu_evidential_reduce": (_i, [_p, _p, _p, _i, _i, _i64, _f, _f, _f, _i, _i, _i64, _i, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "slu_dirichlet_loss": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p]),
-    "slu_evidential_loss_fused": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _f, _f, _f, _f, _p, _p, _p]),
+    "slu_evidential_loss_fused": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p]),
+    "slu_count_valid": (_i, [_p, _p, _i64, _p, _i, _p, _p]),
     "slu_dirichlet_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _p]),
     "slu_evidence_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _p, _i, _p, _p, _p]),
     "slu_logit_regularizer": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _p, _p, _p]),

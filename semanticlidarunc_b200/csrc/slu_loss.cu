@@ -333,14 +333,16 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) evidential_loss_fused
 }
 
 template <int CP>
-static int launch_fused(const FusedParams& p, cudaStream_t st) {
+static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
     const long long cap = 6LL * sms;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
-    count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p);
-    SLU_LAUNCH_CHECK("count_valid_kernel");
+    if (!precounted) {
+        count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("count_valid_kernel");
+    }
     if (p.C == CP) evidential_loss_fused_kernel<CP, true><<<grid, LOSS_THREADS, 0, st>>>(p);
     else evidential_loss_fused_kernel<CP, false><<<grid, LOSS_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("evidential_loss_fused_kernel");
@@ -524,7 +526,7 @@ extern "C" int slu_diag_special(const float* d_in, int64_t n, float* d_out, slu_
 extern "C" int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
                                          int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
                                          float temperature, float eps_alpha, float eps_mse, float eps_kl,
-                                         float w_mse, float w_kl, double* d_sums, float* d_grad_outputs,
+                                         float w_mse, float w_kl, int precounted, double* d_sums, float* d_grad_outputs,
                                          slu_stream_t stream) {
     using namespace slu;
     if (!d_outputs || !d_target || !d_sums) return fail(SLU_E_ARG, "d_outputs / d_target / d_sums is NULL");
@@ -542,14 +544,14 @@ extern "C" int slu_evidential_loss_fused(const float* d_outputs, const int64_t* 
     p.sums = d_sums; p.grad = d_grad_outputs;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch ((C + 3) / 4 * 4) {
-        case 4: return launch_fused<4>(p, st);
-        case 8: return launch_fused<8>(p, st);
-        case 12: return launch_fused<12>(p, st);
-        case 16: return launch_fused<16>(p, st);
-        case 20: return launch_fused<20>(p, st);
-        case 24: return launch_fused<24>(p, st);
-        case 28: return launch_fused<28>(p, st);
-        default: return launch_fused<32>(p, st);
+        case 4: return launch_fused<4>(p, precounted != 0, st);
+        case 8: return launch_fused<8>(p, precounted != 0, st);
+        case 12: return launch_fused<12>(p, precounted != 0, st);
+        case 16: return launch_fused<16>(p, precounted != 0, st);
+        case 20: return launch_fused<20>(p, precounted != 0, st);
+        case 24: return launch_fused<24>(p, precounted != 0, st);
+        case 28: return launch_fused<28>(p, precounted != 0, st);
+        default: return launch_fused<32>(p, precounted != 0, st);
     }
 }
 
@@ -583,4 +585,25 @@ extern "C" int slu_dirichlet_loss(const float* d_alpha, const int64_t* d_target,
         case 28: return launch_loss<28>(p, st);
         default: return launch_loss<32>(p, st);
     }
+}
+
+extern "C" int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t n_px,
+                               const int64_t* h_ignore, int n_ignore, double* d_count, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_target || !d_count) return fail(SLU_E_ARG, "d_target / d_count is NULL");
+    if (n_px < 1) return fail(SLU_E_ARG, "n_px=%lld must be >= 1", (long long)n_px);
+    if (n_ignore < 0 || n_ignore > MAX_IGNORE || (n_ignore > 0 && !h_ignore)) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,%d]", n_ignore, MAX_IGNORE);
+    FusedParams p{};
+    p.target = reinterpret_cast<const long long*>(d_target); p.keep = d_keep_mask;
+    p.n_px = n_px;
+    for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
+    p.n_ignore = n_ignore;
+    p.sums = d_count - 2;                                   // count_valid_kernel adds to sums[2]
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long chunks = (n_px + LOSS_THREADS - 1) / LOSS_THREADS;
+    const long long cap = 6LL * sms;
+    count_valid_kernel<<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    SLU_LAUNCH_CHECK("count_valid_kernel");
+    return 0;
 }

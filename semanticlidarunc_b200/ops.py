@@ -260,9 +260,13 @@ def logit_regularizer(logits: torch.Tensor, *, threshold: Optional[float] = None
 
 def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse: float = 1.0, w_kl: float = 0.05,
                           ignore=(), keep_mask: Optional[torch.Tensor] = None, temperature: float = 1.0,
-                          eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True) -> dict:
+                          eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True,
+                          count_reduce=None) -> dict:
     """Head output [B,C+1,H,W] -> sums float64[3] (sum mse | sum kl | n_valid) and d(loss)/d(outputs)
-    (slu_evidential_loss_fused); loss = (w_mse*sums[0] + w_kl*sums[1]) / max(sums[2], 1)."""
+    (slu_evidential_loss_fused); loss = (w_mse*sums[0] + w_kl*sums[1]) / max(sums[2], 1).
+
+    count_reduce: optional callable applied in place to the 1-element float64 valid-pixel count between the count kernel
+    and the loss kernel (the batch-sharded step passes an all-reduce: gradient and sums then refer to the GLOBAL mean)."""
     _lib.require_cuda()
     outputs = _lib.as_buffer(outputs, torch.float32, "outputs")
     if outputs.dim() != 4:
@@ -279,9 +283,15 @@ def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse:
     h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
     sums = torch.zeros(3, dtype=torch.float64, device=outputs.device)
     grad = torch.empty_like(outputs) if want_grad else None
+    precounted = 0
+    if count_reduce is not None:
+        _lib.check(_lib.lib().slu_count_valid(_lib.ptr(target), _lib.ptr(keep_mask), B * H * W, h_ign, len(ign),
+                                              _lib.ptr(sums[2:]), _lib.stream_ptr()), "slu_count_valid")
+        count_reduce(sums[2:])
+        precounted = 1
     rc = _lib.lib().slu_evidential_loss_fused(_lib.ptr(outputs), _lib.ptr(target), _lib.ptr(keep_mask), B, C1 - 1, H * W,
                                               h_ign, len(ign), float(temperature), float(eps_alpha), float(eps_mse),
-                                              float(eps_kl), float(w_mse), float(w_kl), _lib.ptr(sums), _lib.ptr(grad),
+                                              float(eps_kl), float(w_mse), float(w_kl), precounted, _lib.ptr(sums), _lib.ptr(grad),
                                               _lib.stream_ptr())
     _lib.check(rc, "slu_evidential_loss_fused")
     return {"sums": sums, "grad": grad}

@@ -1,0 +1,35 @@
+"""Batch-sharded evidential training loss over NCCL (BASELINE.json configs[4]): needs two visible GPUs; the round-end
+single-GPU run skips it.  tools/train_step_bench.py exits non-zero unless every rank's gradient equals the matching
+slice of the single-process full-batch gradient bit for bit and the loss shares add up to the full-batch loss."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_precounted_mode_matches_local_count(cuda):
+    """group=None and an identity count_reduce give the same sums and gradient (the precounted kernel path)."""
+    from semanticlidarunc_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    out = (torch.randn((2, 21, 8, 256), generator=g) * 3.0).to(cuda)
+    tgt = torch.randint(0, 20, (2, 8, 256), generator=g).to(cuda)
+    a = ops.evidential_loss_fused(out, tgt, ignore=(0,))
+    b = ops.evidential_loss_fused(out, tgt, ignore=(0,), count_reduce=lambda c: None)
+    assert torch.equal(a["sums"], b["sums"]) and torch.equal(a["grad"], b["grad"])
+    c = ops.evidential_loss_fused(out, tgt, ignore=(0,), count_reduce=lambda cnt: cnt.mul_(4.0))     # as if 4 equal shards
+    assert torch.allclose(c["grad"] * 4.0, a["grad"], rtol=1e-6, atol=0) and float(c["sums"][2]) == 4.0 * float(a["sums"][2])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_sharded_training_step():
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "tools", "train_step_bench.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["shard_grad_equals_full_batch_bitwise"] and line["loss_sum_of_shares_rel_err"] < 1e-6
