@@ -208,7 +208,7 @@ __device__ __forceinline__ bool px_valid(const FusedParams& p, long long g, long
     return v;
 }
 
-__global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_constant__ FusedParams p) {
+__global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_constant__ FusedParams p, double* __restrict__ out) {
     unsigned n = 0;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.n_px; g += (long long)gridDim.x * blockDim.x)
         n += px_valid(p, g, p.target[g]) ? 1u : 0u;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_
     if (threadIdx.x == 0) {
         unsigned t = 0;
         for (int i = 0; i < LOSS_THREADS / 32; ++i) t += s_n[i];
-        if (t) atomicAdd(&p.sums[2], (double)t);
+        if (t) atomicAdd(out, (double)t);
     }
 }
 
@@ -340,7 +340,7 @@ static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) 
     const long long cap = 6LL * sms;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
     if (!precounted) {
-        count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p);
+        count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p, p.sums + 2);
         SLU_LAUNCH_CHECK("count_valid_kernel");
     }
     if (p.C == CP) evidential_loss_fused_kernel<CP, true><<<grid, LOSS_THREADS, 0, st>>>(p);
@@ -598,12 +598,11 @@ extern "C" int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_ma
     p.n_px = n_px;
     for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
     p.n_ignore = n_ignore;
-    p.sums = d_count - 2;                                   // count_valid_kernel adds to sums[2]
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long chunks = (n_px + LOSS_THREADS - 1) / LOSS_THREADS;
     const long long cap = 6LL * sms;
-    count_valid_kernel<<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    count_valid_kernel<<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, d_count);
     SLU_LAUNCH_CHECK("count_valid_kernel");
     return 0;
 }

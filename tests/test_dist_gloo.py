@@ -46,6 +46,16 @@ def _worker(rank, world, port, q):
     assert list(mine) == list(range(rank, N_SCANS, world))
     cm, bins = _counts(mine)
     sdist.allreduce_counts(cm, bins)
+    # the sharded training loss combines exactly one number: the valid-pixel count (losses/evidential.py::_count_reducer)
+    from semanticlidarunc_b200.losses.evidential import _count_reducer
+    red = _count_reducer(True)
+    count = torch.tensor([float(100 + rank)], dtype=torch.float64)
+    red(count)
+    assert float(count) == 201.0 and _count_reducer(None) is None
+    # score histograms (AUROC / AURC state) combine the same way
+    hist = torch.full((2, 16), rank + 1, dtype=torch.int64)
+    sdist.allreduce_counts(hist)
+    assert int(hist.sum()) == 3 * 32
     q.put((rank, cm.numpy(), bins.numpy()))
     dist.barrier()
     dist.destroy_process_group()
@@ -88,3 +98,5 @@ def test_allreduce_is_noop_without_process_group():
     cm = torch.ones((C, C), dtype=torch.int64)
     sdist.allreduce_counts(cm, None)
     assert int(cm.sum()) == C * C
+    from semanticlidarunc_b200.losses.evidential import _count_reducer
+    assert _count_reducer(True) is None and _count_reducer(None) is None        # no process group: local mean
