@@ -23,6 +23,10 @@
 namespace slu {
 
 constexpr int EV_THREADS = 256;
+#ifndef SLU_EV_MINB
+#define SLU_EV_MINB 5
+#endif
+constexpr int EV_MINB = SLU_EV_MINB;      // resident CTAs per SM the kernel is compiled for
 
 __device__ __forceinline__ float lg2_fast(float x) {
     float y;
@@ -57,7 +61,7 @@ struct EvParams {
 
 // EXACT: C == CP, no per-class predicate anywhere;  MI: the AUROC-convention mutual information is requested.
 template <int CP, bool EXACT, bool MI>
-__global__ void __launch_bounds__(EV_THREADS) evidential_kernel(const __grid_constant__ EvParams p) {
+__global__ void __launch_bounds__(EV_THREADS, EV_MINB) evidential_kernel(const __grid_constant__ EvParams p) {
     __shared__ AtomicHist hs;
     const int tid = threadIdx.x;
     atomic_hist_zero(hs, p.C, tid, EV_THREADS);

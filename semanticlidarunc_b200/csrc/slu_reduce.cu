@@ -467,16 +467,29 @@ __global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const 
             for (int c = 0; c < CP; ++c)
                 if (EXACT || c < p.C) { const float pc = fmaxf(x[c], p.eps); Hb2 = fmaf(-pc, lg2_approx(pc), Hb2); }
         }
-        // ---- arg max (torch.argmax: first maximal index, NaN counts as maximal), renormalising sum
-        float pmax = x[0], sump = fmaxf(x[0], 0.f);
+        // ---- arg max (torch.argmax: first maximal index, NaN counts as maximal), renormalising sum.  The plain sum of
+        //      the distribution is NaN exactly when some entry is: only then does the NaN-aware comparison run.
+        float pmax = x[0], sump = fmaxf(x[0], 0.f), psum = x[0];
         int arg = 0;
 #pragma unroll
         for (int c = 1; c < CP; ++c) {
             if (EXACT || c < p.C) {
-                const bool gt = (x[c] > pmax) | ((x[c] != x[c]) & (pmax == pmax));
+                const bool gt = x[c] > pmax;
                 pmax = gt ? x[c] : pmax;
                 arg = gt ? c : arg;
                 sump += fmaxf(x[c], 0.f);
+                psum += x[c];
+            }
+        }
+        if (psum != psum) {                                       // rare: NaN / inf inputs
+            pmax = x[0]; arg = 0;
+#pragma unroll
+            for (int c = 1; c < CP; ++c) {
+                if (EXACT || c < p.C) {
+                    const bool gt = (x[c] > pmax) | ((x[c] != x[c]) & (pmax == pmax));
+                    pmax = gt ? x[c] : pmax;
+                    arg = gt ? c : arg;
+                }
             }
         }
         float conf = pmax;

@@ -278,3 +278,20 @@ def test_periodic_histogram_flush_in_long_sweeps(cuda):
         assert int(cm.sum()) == B * H * W
         assert torch.equal(cm, cm2) and torch.equal(bins, bins2), fn.__name__
         assert int(bins[2].max()) > 2 ** 40                     # far beyond what a 32-bit half could hold
+
+
+def test_single_sample_argmax_with_nan_matches_torch(cuda):
+    """torch.argmax treats NaN as maximal (first NaN wins); the single-sample kernel only runs its NaN-aware comparison for
+    pixels whose distribution contains one."""
+    g = torch.Generator().manual_seed(5)
+    probs = torch.softmax(torch.randn((2, 20, 4, 64), generator=g) * 3.0, dim=1)
+    probs[0, 7, 1, :10] = float("nan")
+    probs[1, 3, 2, 5:9] = float("nan")
+    probs[1, 12, 2, 5:9] = float("nan")                     # two NaNs: the first index wins
+    probs[0, 0, 3, :4] = float("inf")
+    out = ops.reduce_metrics(probs.to(cuda), None, kind="probs", want=("pred",))
+    assert torch.equal(out["pred"].cpu(), probs.argmax(dim=1))
+    logits = torch.randn((1, 20, 2, 64), generator=g)
+    logits[0, 4, 0, :8] = float("nan")
+    out = ops.reduce_metrics(logits.to(cuda), None, kind="logits", want=("pred",))
+    assert torch.equal(out["pred"].cpu(), torch.softmax(logits, dim=1).argmax(dim=1))
