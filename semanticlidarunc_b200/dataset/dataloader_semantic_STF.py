@@ -31,6 +31,10 @@ class SemanticSTF(SemanticKitti):
             label, xyzi = label[keep], xyzi[keep]
         return np.ascontiguousarray(xyzi), np.ascontiguousarray(label)
 
+    def staged_batches(self, *a, **kw):
+        # 5-column records and the r < 1.8 m / intensity filters happen on the host (read_scan): not the stager's 16-byte format
+        raise NotImplementedError("SemanticSTF files are 5-column records filtered in read_scan(); use __getitem__ / device_batch")
+
     def _draw_augmentation(self):
         yaw = float(np.random.randint(-180, 180)) if self.rotate else None
         do_flip = bool(np.random.choice([True, False])) if self.flip else False
