@@ -2,7 +2,9 @@
 
 numpy in / numpy out, as the reference's DataLoader workers call it; the arithmetic runs in
 libslu's projection kernels (csrc/slu_project.cu).  `project_device` is the same call without the
-host round trip, and `ops.project_batch` the batched, loader-fused form.
+host round trip, and `ops.project_batch` the batched, loader-fused form.  `build_normal_xyz` (:30-59) is the loader
+kernel's normal stage on its own.  `rotate_z` (:4-18) has no stand-alone counterpart: the yaw augmentation is applied
+to the points inside the projection kernels (`ops.project_batch(yaw_deg=...)`, float64, the reference's matrix).
 """
 from __future__ import annotations
 
@@ -17,6 +19,24 @@ def to_deflection_coordinates(x, y, z):
     x, y, z = (torch.as_tensor(v, dtype=torch.float64) for v in (x, y, z))
     p = torch.sqrt(x ** 2 + y ** 2)
     return torch.atan2(y, x), -torch.atan2(p, z) + np.pi / 2
+
+
+def build_normal_xyz(xyz, norm_factor=0.25, ksize=3):
+    """Surface normals of an organised cloud, `xyz` [h,w,3] -> [h,w,3] float32 (src/dataset/utils.py:30-59: six 3x3
+    Scharr derivatives, cross product, normalisation), computed by libslu's loader kernel (csrc/slu_loader.cu).
+    numpy in / numpy out like the reference; a CUDA tensor in gives a CUDA tensor out."""
+    if ksize != 3:
+        raise NotImplementedError("only the 3x3 Scharr stencil of the reference call sites is implemented")
+    is_np = not torch.is_tensor(xyz)
+    dev = _lib.require_cuda(xyz.device if (not is_np and xyz.is_cuda) else None)
+    t = torch.as_tensor(np.ascontiguousarray(xyz, dtype=np.float32) if is_np else xyz).to(dev, torch.float32)
+    if t.dim() != 3 or t.size(2) != 3:
+        raise ValueError("xyz must be [h,w,3]")
+    h, w = t.shape[:2]
+    img = torch.zeros((1, 6, h, w), dtype=torch.float32, device=dev)
+    img[0, :3] = t.permute(2, 0, 1)
+    n = ops.frame_tensors(img, norm_factor=float(norm_factor))["normals"][0].permute(1, 2, 0).contiguous()
+    return n.cpu().numpy() if is_np else n
 
 
 def project_device(pc: torch.Tensor, height=64, width=2048, theta_range=None, sort_largest_first=False):

@@ -194,3 +194,16 @@ def test_stf_getitem_vs_reference(cuda, golden):
     assert 20 not in np.unique(sem) and 21 in np.unique(sem)
     m = normals_condition_mask(xyz)[::4, ::16]
     assert np.abs(normals[:, ::4, ::16].astype(np.float64) - g["stf/normals_sub"])[:, m].max() <= 5e-5
+
+
+def test_build_normal_xyz_standalone_vs_reference_golden(cuda, golden):
+    """dataset.utils.build_normal_xyz ([h,w,3] in, [h,w,3] out, src/dataset/utils.py:30-59) against the normals the
+    reference Dataset produced from the same xyz image."""
+    from semanticlidarunc_b200.dataset.utils import build_normal_xyz
+    g = golden("kitti_loader.npz")
+    xyz = g["xyz"]                                             # [3,H,W] as the Dataset returns it
+    n = build_normal_xyz(np.ascontiguousarray(xyz.transpose(1, 2, 0)))
+    assert isinstance(n, np.ndarray) and n.shape == xyz.shape[1:] + (3,) and n.dtype == np.float32
+    assert normals_close(n.transpose(2, 0, 1), g["normals"], xyz)
+    nd = build_normal_xyz(torch.from_numpy(np.ascontiguousarray(xyz.transpose(1, 2, 0))).to(cuda))
+    assert nd.is_cuda and np.array_equal(nd.cpu().numpy(), n)
