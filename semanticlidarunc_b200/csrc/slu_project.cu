@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_angles_kernel(const __grid_co
         bool near;
         const int cnt_w = count_le(ew, phi, near);
         if (near) ++near_cnt;
-        int c = (p.W - 1 - cnt_w) % p.W;
+        int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
         if (c < 0) c += p.W;
         p.col[n] = c;
         p.theta[n] = theta;
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
         // the scan's own extreme points sit exactly ON the first/last edge by construction
         if (near && !p.use_range) near = !(p.theta[n] == lo || p.theta[n] == hi);
         if (near) ++near_cnt;
-        int r = (p.H - 1 - cnt_h) % p.H;
+        int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
         if (r < 0) r += p.H;
         const int px = r * p.W + p.col[n];
         p.pix[n] = px;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
             cnt_w = count_le(ew, exact_phi(q), near);
             if (near) ++near_cnt;
         }
-        int c = (p.W - 1 - cnt_w) % p.W;
+        int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
         if (c < 0) c += p.W;
         p.col[n] = c;
     }
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         bool near;
         const int cnt_w = count_le(ew, exact_phi(load_pt(p, b, __ldg(p.xyzi + n))), near);
         if (near) ++near_cnt;
-        int c = (p.W - 1 - cnt_w) % p.W;
+        int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
         if (c < 0) c += p.W;
         p.col[n] = c;
     }
@@ -475,7 +475,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
             if (near && !p.use_range) near = !(th == lo || th == hi);
             if (near) ++near_cnt;
         }
-        int r = (p.H - 1 - cnt_h) % p.H;
+        int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
         if (r < 0) r += p.H;
         const int px = r * p.W + col;
         p.pix[n] = px;
@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         const int cnt_h = count_le(eh, th, near);
         if (near && !p.use_range) near = !(th == lo || th == hi);
         if (near) ++near_cnt;
-        int r = (p.H - 1 - cnt_h) % p.H;
+        int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
         if (r < 0) r += p.H;
         const int px = r * p.W + p.col[n];
         p.pix[n] = px;
