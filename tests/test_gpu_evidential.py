@@ -86,3 +86,17 @@ def test_digamma_range_through_AU(cuda):
     r = ops.evidential_reduce(alpha.to(cuda), from_outputs=False, want=("AU", "H", "EU"))
     ok, aerr, rerr = rel_close(r["AU"].cpu().numpy(), ou.get_aleatoric_uncertainty(alpha.double()).numpy(), RTOL, ATOL)
     assert ok, f"AU: abs {aerr:.3e} rel {rerr:.3e}"
+
+
+def test_small_concentrations_take_the_two_eps_path(cuda):
+    """alpha0 << 1 (concentrations passed in directly, not from the head): alpha0 + 1e-8 and alpha0 + 1e-12 differ in
+    fp32, so the AUROC-convention MI is evaluated against its own psi(alpha0 + 1e-12 + 1) in the kernel's rare path."""
+    g = torch.Generator().manual_seed(9)
+    alpha = torch.rand((1, 20, 4, 128), generator=g) * 2e-3 + 1e-4
+    alpha[:, :, 2:] += 1.0                                   # half of the pixels stay on the common path
+    r = ops.evidential_reduce(alpha.to(cuda), from_outputs=False, want=("MI", "AU", "H"))
+    ref_mi = ou.dirichlet_mi(alpha.double())
+    ok, aerr, rerr = rel_close(r["MI"].cpu().numpy(), ref_mi.numpy(), RTOL, 2 * ATOL)
+    assert ok, f"MI: abs {aerr:.3e} rel {rerr:.3e}"
+    ok, aerr, rerr = rel_close(r["AU"].cpu().numpy(), ou.get_aleatoric_uncertainty(alpha.double()).numpy(), RTOL, 2 * ATOL)
+    assert ok, f"AU: abs {aerr:.3e} rel {rerr:.3e}"
