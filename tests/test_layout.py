@@ -32,3 +32,25 @@ def test_gpu_tests_and_bench_do_not_read_reference_tree():
 def test_oracle_headers_say_test_infrastructure():
     for f in _py_files("oracle"):
         assert "TEST INFRASTRUCTURE ONLY" in open(f).read() or f.endswith("_refshim.py"), f
+
+
+def test_running_mean_decorator_on_cpu_tensors():
+    """utils.agg.mean_aggregator (src/utils/agg.py:6-91): value passthrough, masked / unmasked accumulation, scalars, reset."""
+    import torch
+    from semanticlidarunc_b200.utils.agg import mean_aggregator
+
+    @mean_aggregator()
+    def twice(x):
+        """doc"""
+        return 2 * x
+
+    assert twice.__name__ == "twice" and twice.__doc__ == "doc"
+    a = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    assert torch.equal(twice(a), 2 * a) and twice.mean() == 0.0
+    out = twice.accumulate(a)
+    assert torch.equal(out, 2 * a) and abs(twice.mean() - 5.0) < 1e-12
+    twice.accumulate(a, mask=torch.tensor([[True, False, False], [False, False, True]]))     # adds 0 and 10 over 2 elements
+    assert abs(twice.mean() - (30.0 + 10.0) / 8) < 1e-12
+    twice.add(4.0)
+    assert abs(twice.mean(reset=True) - 44.0 / 9) < 1e-12 and twice.mean() == 0.0
+    twice.sync_ddp()                                         # no process group: a no-op
