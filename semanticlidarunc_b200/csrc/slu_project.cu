@@ -499,6 +499,82 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     if ((threadIdx.x & 31) == 0 && near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
 }
 
+// Fixed elevation range (theta_range given: SemanticCUDAL +-pi/8, SemanticWADS +-pi/2, src/dataset/dataloader_semantic_CUDAL.py:95):
+// the row edges do not depend on the scan, so column, row and the depth test run in ONE pass over the points -- no fp32
+// theta / column round trip through memory, and the 64-bit atomic stream overlaps the angle arithmetic.  The per-pixel
+// state is reset by proj_init_kernel beforehand (the depth test cannot share a launch with its own initialisation).
+__global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    const Edges ew = make_edges(-PI, PI, p.W);
+    const Edges eh = make_edges(p.theta_lo, p.theta_hi, p.H);
+    const FastEdges fw = make_fast_edges(ew), fh = make_fast_edges(eh);
+    __shared__ int s_q[DEFER_CAP];
+    __shared__ int s_qn;
+    if (threadIdx.x == 0) s_qn = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.theta_out) { p.theta_out[2 * b] = p.theta_lo; p.theta_out[2 * b + 1] = p.theta_hi; }
+    __syncthreads();
+    int missing = 0, near_cnt = 0;
+    const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
+    int pend_lut = 0;
+    unsigned long long* key = p.key + (long long)b * p.HW;
+    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+        const float4 v4 = __ldg(p.xyzi + n);
+        const unsigned raw = check_ids ? (__ldg(p.raw_label + n) & 0xffffu) : 0u;
+        missing += pend_lut < 0 ? 1 : 0;
+        const Pt q = load_pt(p, b, v4);
+        const double x = q.x, y = q.y, z = q.z;
+        const float4 v = make_float4((float)x, (float)y, (float)z, 0.f);
+        const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
+        const unsigned long long rk = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
+        p.rkey[n] = rk;                                            // the tie pass compares against it
+        const float phi32 = atan2f(v.y, v.x);
+        const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
+        pend_lut = check_ids ? __ldg(p.lut + raw) : 0;
+        int cnt_w = fast_count_le(fw, phi32);
+        int cnt_h = fast_count_le(fh, th32);
+        if (cnt_w < 0 || cnt_h < 0) {
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
+            bool near;
+            if (cnt_w < 0) { cnt_w = count_le(ew, exact_phi(q), near); if (near) ++near_cnt; }
+            if (cnt_h < 0) { cnt_h = count_le(eh, exact_theta(q), near); if (near) ++near_cnt; }
+        }
+        int c = p.W - 1 - cnt_w;
+        if (c < 0) c += p.W;
+        int rr = p.H - 1 - cnt_h;
+        if (rr < 0) rr += p.H;
+        const int px = rr * p.W + c;
+        p.pix[n] = px;
+        atomicMin(&key[px], rk);
+    }
+    missing += pend_lut < 0 ? 1 : 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
+        // queued points: both bins from the exact fp64 angles (a bin the prefilter had certified cannot be near an edge)
+        const long long n = n0 + s_q[i];
+        const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
+        bool near_w, near_h;
+        const int cnt_w = count_le(ew, exact_phi(q), near_w);
+        const int cnt_h = count_le(eh, exact_theta(q), near_h);
+        near_cnt += (near_w ? 1 : 0) + (near_h ? 1 : 0);
+        int c = p.W - 1 - cnt_w;
+        if (c < 0) c += p.W;
+        int rr = p.H - 1 - cnt_h;
+        if (rr < 0) rr += p.H;
+        const int px = rr * p.W + c;
+        p.pix[n] = px;
+        atomicMin(&key[px], p.rkey[n]);
+    }
+    missing = __reduce_add_sync(0xffffffffu, missing);
+    near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
+    if ((threadIdx.x & 31) == 0) {
+        if (missing) atomicAdd(&p.diag[2 * b], missing);
+        if (near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
+    }
+}
+
 __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
@@ -610,6 +686,7 @@ static int point_grid_x(const long long* offsets, int B, int sms) {
 // Initial value from SLU_PROJECT_EXACT=1, changed at run time by slu_debug_project_exact().
 static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && e[0] == '1') ? 1 : 0; }();
 static bool exact_only() { return g_exact_only != 0; }
+static int g_no_fused = [] { const char* e = getenv("SLU_PROJECT_NO_FUSED"); return (e && e[0] == '1') ? 1 : 0; }();   // A/B: two-pass kernels with a fixed range too
 
 static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t* d_pix, int32_t* d_winner,
                           int32_t* d_diag, bool generic, cudaStream_t st) {
@@ -634,11 +711,21 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
     p.gx = (int)gp.x;
     if (!generic && !exact_only()) {
-        // fp32-prefiltered path: angles (+ init, + exact theta extremes per block) -> rows -> ties
-        proj_fast_angles_kernel<<<gp, PT_THREADS, 0, st>>>(p);
-        SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
-        proj_fast_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);
-        SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
+        if (p.use_range && !g_no_fused) {
+            // fixed elevation range: init -> one fused pass (angles + rows + depth test) -> ties
+            const long long cells = (long long)p.B * p.HW;
+            const long long gi = (cells + PT_THREADS - 1) / PT_THREADS;
+            proj_init_kernel<<<(unsigned)(gi < 8LL * sms ? (gi < 1 ? 1 : gi) : 8LL * sms), PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_init_kernel");
+            proj_fast_fused_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_fast_fused_kernel");
+        } else {
+            // fp32-prefiltered path: angles (+ init, + exact theta extremes per block) -> rows -> ties
+            proj_fast_angles_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
+            proj_fast_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
+        }
         if (n_total > 0) {
             proj_ties_kernel<<<gp, PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_ties_kernel");

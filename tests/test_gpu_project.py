@@ -198,3 +198,36 @@ def test_fast_and_exact_kernels_agree_bit_for_bit(cuda):
         o = oproj.kitti_frame(a, r, H, W, build_id_lut())
         assert np.array_equal(fast["pix"][offs[b]:offs[b + 1]].cpu().numpy().astype(np.int64), o["pix"])
         assert np.array_equal(fast["winner"][b].cpu().numpy().reshape(-1).astype(np.int64), o["winner"])
+
+
+@pytest.mark.parametrize("theta_range,H", [((-np.pi / 8, np.pi / 8), 128), ((-np.pi / 2, np.pi / 2), 64)])
+def test_fixed_range_fused_pass_agrees_with_exact_kernels(cuda, theta_range, H):
+    """With a fixed elevation range (SemanticCUDAL +-pi/8 at 128 rows, SemanticWADS +-pi/2) the batched entry point runs
+    ONE fused point pass (columns + rows + depth test).  It must give the bits of the all-fp64 kernels and of the oracle,
+    including on points placed a few ulps around row and column edges and outside the range."""
+    from semanticlidarunc_b200 import _lib
+    W = 2048
+    xyzi, raw = synth.synth_scan(91, "os1-128")
+    xyzi, raw = xyzi[:150_000].copy(), raw[:150_000].copy()
+    row_edges = np.linspace(theta_range[0], theta_range[1], H)
+    k = np.arange(300)
+    for j, d in enumerate((0.0, 1e-7, -1e-7, 1e-15, -1e-15, 5e-6, -5e-6, 1e-5)):     # elevations on / around row edges
+        th = row_edges[(k * 3 + j) % H] + d
+        sl = slice(j * 300, (j + 1) * 300)
+        rho = np.linalg.norm(xyzi[sl, :2], axis=1).astype(np.float64)
+        xyzi[sl, 2] = (rho * np.tan(th)).astype(np.float32)
+    scans = [(xyzi, raw), synth.synth_scan(92, "hdl64", n_points=40_000)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    dx, dr, dl = to_dev(np.concatenate([s[0] for s in scans]), np.concatenate([s[1] for s in scans]), cuda)
+    fused = ops.project_batch(dx, dr, offs, H, W, lut=dl, theta_range=theta_range)
+    prev = _lib.lib().slu_debug_project_exact(1)
+    try:
+        exact = ops.project_batch(dx, dr, offs, H, W, lut=dl, theta_range=theta_range)
+    finally:
+        _lib.lib().slu_debug_project_exact(prev)
+    for key in ("pix", "winner", "img", "label", "theta", "diag"):
+        assert torch.equal(fused[key], exact[key]), key
+    for b, (a, r) in enumerate(scans):
+        pc = np.concatenate([a.astype(np.float64), build_id_lut()[(r & 0xFFFF).astype(np.int64)].astype(np.float64)[:, None]], axis=1)
+        row, col, _ = oproj.projection_indices(pc, H, W, theta_range=theta_range)
+        assert np.array_equal(fused["pix"][offs[b]:offs[b + 1]].cpu().numpy().astype(np.int64), row * W + col)

@@ -64,6 +64,10 @@ for sensor, B in (("hdl64", 1), ("hdl64", 16), ("os1-128", 1), ("os1-128", 16)):
     ws = res["workspace"]
     n = int(offs[-1])
     add(f"projection {sensor} B={B}", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws), 20 * n + 24 * B * H * W, B, "4 launches")
+    if sensor == "os1-128":      # config 3 as the reference exercises it: SemanticCUDAL, 128 rows, fixed +-pi/8 elevation range
+        tr = (-np.pi / 8, np.pi / 8)
+        add(f"projection {sensor} B={B}, fixed theta range (CUDAL)", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws, theta_range=tr),
+            20 * n + 24 * B * H * W, B, "init + fused point pass + ties + resolve")
     lab_img, pix = res["label"], res["pix"]
     add(f"back-projection {sensor} B={B}", lambda: ops.backproject(lab_img, pix, offs), 8 * n + 8 * B * H * W, B)
 
