@@ -53,6 +53,9 @@ typedef void* slu_stream_t;
 
 int         slu_version(void);
 const char* slu_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process so far (all threads, all devices):
+ * the difference across a region is that region's launch count (bench.py reports it as gpu_launches) */
+int64_t     slu_launch_count(void);
 /* sm count and compute capability of `device`; fails with SLU_E_DEVICE if it is not cc 10.x */
 int         slu_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
 
@@ -230,6 +233,12 @@ int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const floa
                       int64_t n, int C, int has_ignore, int64_t ignore,
                       int n_bins, const float* h_edges,
                       int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream);
+/* The same with int32 prediction / label maps (12 B/px instead of 20): for callers that keep their reduced maps in
+ * 32 bits.  Counters and semantics are identical; the results are bit-identical to slu_confusion_ece on widened inputs. */
+int slu_confusion_ece_i32(const int32_t* d_pred, const int32_t* d_labels, const float* d_conf,
+                          int64_t n, int C, int has_ignore, int64_t ignore,
+                          int n_bins, const float* h_edges,
+                          int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream);
 /* A/B switch (tests, profiles): 1 = always run the generic warp-aggregated histogram kernel instead of the
  * streaming one slu_confusion_ece picks for 16-byte aligned inputs.  Results are bit-identical either way. */
 int slu_debug_hist_generic(int on);
@@ -317,6 +326,13 @@ int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int Hd, int Wd,
                       const uint8_t* h_flip, float norm_factor,
                       float* d_range, float* d_refl, float* d_xyz, float* d_normals, int64_t* d_sem,
                       int32_t* d_rowmap, int resize_rows, slu_stream_t stream);
+
+/* Surface normals straight from planar xyz (no resize / flip): build_normal_xyz, src/dataset/utils.py:30-59, as the
+ * loaders call it on the projected image (src/dataset/dataloader_semantic_KITTI.py:85).  The x, y, z planes of scan b start
+ * at d_xyz + b * batch_stride elements (3*H*W for a packed [B,3,H,W] tensor; 6*H*W reads the first three planes of the
+ * projection image [B,6,H,W] in place).  d_normals [B,3,H*W]. */
+int slu_frame_normals(const float* d_xyz, int B, int H, int W, int64_t batch_stride, float norm_factor,
+                      float* d_normals, slu_stream_t stream);
 
 /* Organised clouds (Ouster / SemanticTHAB: the sensor delivers H x W points, pixel n = point n, no projection;
  * src/inference_ouster.py:59-62, documentation/dataset.md:109).

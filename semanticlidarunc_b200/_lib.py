@@ -25,6 +25,7 @@ _i, _i64, _f, _d = C.c_int, C.c_int64, C.c_float, C.c_double
 SIGNATURES = {
     "slu_version": (_i, []),
     "slu_last_error": (C.c_char_p, []),
+    "slu_launch_count": (_i64, []),
     "slu_device_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "slu_reduce_metrics": (_i, [_p, _p, _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i64, _i, _p,
                                 _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "slu_logit_regularizer": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _p, _p, _p]),
     "slu_diag_special": (_i, [_p, _i64, _p, _p]),
     "slu_confusion_ece": (_i, [_p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
+    "slu_confusion_ece_i32": (_i, [_p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
     "slu_debug_hist_generic": (_i, [_i]),
     "slu_score_hist": (_i, [_p, _p, _p, _i64, _i, _p, _i, _p, _p]),
     "slu_class_score_hist": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
@@ -49,6 +51,7 @@ SIGNATURES = {
     "slu_project_batch": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p,
                                _p, _p, _p, _p, _p, _p, _p]),
     "slu_project_points": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "slu_frame_normals": (_i, [_p, _i, _i, _i, _i64, _f, _p, _p]),
     "slu_organized_planes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "slu_frame_tensors": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _i, _p]),
     "slu_backproject": (_i, [_p, _p, _p, _i64, _i, _i64, _p, _p]),
@@ -109,6 +112,36 @@ def ptr(t):
 
 def stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    """Kernels libslu has launched in this process so far (slu_launch_count)."""
+    return int(lib().slu_launch_count())
+
+
+def device_guard(fn):
+    """Run an ops entry point on the device its tensor arguments live on.
+
+    The library launches on the CURRENT device and stream; a tensor on another GPU would otherwise be handed to a
+    kernel on the wrong device.  All CUDA tensor arguments must share one device (ValueError otherwise); when that
+    device is not the current one the call runs under `torch.cuda.device(dev)`, so `stream_ptr()` is that device's
+    current stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in (*args, *kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise ValueError(f"{fn.__name__}: tensor arguments live on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
 
 
 def as_buffer(t: torch.Tensor, dtype, name: str) -> torch.Tensor:

@@ -2,11 +2,15 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <atomic>
 #include "slu_common.cuh"
 
 namespace slu {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -51,6 +55,8 @@ bool one_step_bin_search_ok(const float* e, int n_bins) {
 extern "C" int slu_version(void) { return SLU_VERSION; }
 
 extern "C" const char* slu_last_error(void) { return slu::g_err; }
+
+extern "C" int64_t slu_launch_count(void) { return (int64_t)slu::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int slu_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
     int n = 0;

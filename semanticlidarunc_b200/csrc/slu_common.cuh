@@ -10,6 +10,7 @@ namespace slu {
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 int sm_count_current_device();
+void note_launch();                 // counts kernel launches made by the library (slu_launch_count)
 
 #define SLU_CUDA(call)                                            \
     do {                                                          \
@@ -19,6 +20,7 @@ int sm_count_current_device();
 
 #define SLU_LAUNCH_CHECK(what)                                      \
     do {                                                            \
+        slu::note_launch();                                         \
         cudaError_t e__ = cudaGetLastError();                       \
         if (e__ != cudaSuccess) return slu::cuda_fail(e__, what);   \
     } while (0)

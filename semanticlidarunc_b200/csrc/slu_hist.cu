@@ -10,6 +10,7 @@
 // shared memory take one atomic per DISTINCT key per warp (__match_any_sync), which is what makes
 // spatially coherent label maps cheap; one global atomic per non-zero cell per CTA at the end.
 #include <math.h>
+#include <type_traits>
 #include "slu_common.cuh"
 
 namespace slu {
@@ -18,9 +19,10 @@ constexpr int HIST_THREADS = 256;
 constexpr int HIST_UNROLL = 4;
 constexpr int HIST_SMEM_CELLS = 64 * 64;     // confusion matrices up to C=64 live in shared memory
 
+// IT = index type of the prediction / label maps: long long (the reference's int64 tensors) or int (12 B/px instead of 20)
 struct HistParams {
-    const long long* pred;
-    const long long* labels;
+    const void* pred;
+    const void* labels;
     const float* conf;
     long long n;
     int C;
@@ -32,8 +34,10 @@ struct HistParams {
     unsigned long long* bins;
 };
 
-template <bool SMEM_CM>
+template <bool SMEM_CM, typename IT>
 __global__ void __launch_bounds__(HIST_THREADS) confusion_ece_kernel(const __grid_constant__ HistParams p) {
+    const IT* __restrict__ g_pred = reinterpret_cast<const IT*>(p.pred);
+    const IT* __restrict__ g_lab = reinterpret_cast<const IT*>(p.labels);
     __shared__ unsigned cm[SMEM_CM ? HIST_SMEM_CELLS : 1];
     __shared__ unsigned bin_n[SLU_MAX_BINS], bin_c[SLU_MAX_BINS];
     __shared__ unsigned long long bin_s[SLU_MAX_BINS];
@@ -55,8 +59,8 @@ __global__ void __launch_bounds__(HIST_THREADS) confusion_ece_kernel(const __gri
         for (int u = 0; u < HIST_UNROLL; ++u) {
             const long long i = base + (long long)u * HIST_THREADS + tid;
             const bool in = i < p.n;
-            pr[u] = in ? __ldg(p.pred + i) : -1;
-            lb[u] = in ? __ldg(p.labels + i) : -1;
+            pr[u] = in ? (long long)__ldg(g_pred + i) : -1;
+            lb[u] = in ? (long long)__ldg(g_lab + i) : -1;
             cf[u] = (in && p.conf) ? __ldg(p.conf + i) : 0.f;
         }
 #pragma unroll
@@ -130,8 +134,25 @@ static V2Layout v2_layout(int cells, int n_bins, bool want_cm, bool want_bins) {
     return L;
 }
 
+template <typename IT> struct Load4;
+template <> struct Load4<long long> {
+    static __device__ __forceinline__ void ld(const long long* base, long long g, long long* o) {
+        const longlong2* q = reinterpret_cast<const longlong2*>(base);
+        const longlong2 a = __ldcs(q + 2 * g), b = __ldcs(q + 2 * g + 1);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+};
+template <> struct Load4<int> {
+    static __device__ __forceinline__ void ld(const int* base, long long g, int* o) {
+        const int4 a = __ldcs(reinterpret_cast<const int4*>(base) + g);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    }
+};
+
+template <typename IT>
 __global__ void __launch_bounds__(V2_THREADS) confusion_ece_stream_kernel(const __grid_constant__ HistParams p, int cm_copies,
                                                                          int cm_bytes, long long first_px, long long n_px) {
+    typedef typename std::conditional<sizeof(IT) == 8, unsigned long long, unsigned>::type UT;
     extern __shared__ __align__(16) unsigned char v2_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cells = p.C * p.C;
@@ -150,22 +171,21 @@ __global__ void __launch_bounds__(V2_THREADS) confusion_ece_stream_kernel(const 
     const float nb_f = (float)p.n_bins;
     const float e_first = p.bins ? p.edges[0] : 0.f, e_last = p.bins ? p.edges[p.n_bins] : 0.f;
 
-    const longlong2* pred2 = reinterpret_cast<const longlong2*>(p.pred + first_px);
-    const longlong2* lab2 = reinterpret_cast<const longlong2*>(p.labels + first_px);
+    const IT* pred_b = reinterpret_cast<const IT*>(p.pred) + first_px;
+    const IT* lab_b = reinterpret_cast<const IT*>(p.labels) + first_px;
+    const IT ignore = (IT)p.ignore;
     const float4* conf4 = reinterpret_cast<const float4*>(p.conf ? p.conf + first_px : nullptr);
     const long long n_groups = n_px / V2_PX;                    // the host passes n_px % 4 == 0
     const long long stride = (long long)gridDim.x * V2_THREADS;
     for (long long g0 = (long long)blockIdx.x * V2_THREADS + tid; g0 < n_groups; g0 += stride * V2_STEPS) {
-        long long pr[V2_STEPS][V2_PX], lb[V2_STEPS][V2_PX];
+        IT pr[V2_STEPS][V2_PX], lb[V2_STEPS][V2_PX];
         float cf[V2_STEPS][V2_PX];
 #pragma unroll
         for (int s = 0; s < V2_STEPS; ++s) {
             const long long g = g0 + s * stride;
             if (g < n_groups) {
-                const longlong2 a = __ldcs(pred2 + 2 * g), b = __ldcs(pred2 + 2 * g + 1);
-                const longlong2 c = __ldcs(lab2 + 2 * g), d = __ldcs(lab2 + 2 * g + 1);
-                pr[s][0] = a.x; pr[s][1] = a.y; pr[s][2] = b.x; pr[s][3] = b.y;
-                lb[s][0] = c.x; lb[s][1] = c.y; lb[s][2] = d.x; lb[s][3] = d.y;
+                Load4<IT>::ld(pred_b, g, pr[s]);
+                Load4<IT>::ld(lab_b, g, lb[s]);
                 if (conf4) { const float4 f = __ldcs(conf4 + g); cf[s][0] = f.x; cf[s][1] = f.y; cf[s][2] = f.z; cf[s][3] = f.w; }
                 else { cf[s][0] = cf[s][1] = cf[s][2] = cf[s][3] = 0.f; }
             } else {
@@ -180,7 +200,7 @@ __global__ void __launch_bounds__(V2_THREADS) confusion_ece_stream_kernel(const 
 #pragma unroll
                 for (int u = 0; u < V2_PX; ++u) {
                     // 0 <= label < C and 0 <= pred < C (evaluator.py:49) as two unsigned compares
-                    const bool ok = (unsigned long long)lb[s][u] < (unsigned long long)p.C && (unsigned long long)pr[s][u] < (unsigned long long)p.C;
+                    const bool ok = (UT)lb[s][u] < (UT)p.C && (UT)pr[s][u] < (UT)p.C;
                     key[u] = ok ? (int)lb[s][u] * p.C + (int)pr[s][u] : -1;
                 }
                 if (key[0] == key[1] && key[1] == key[2] && key[2] == key[3]) {      // the common case on real label maps
@@ -203,7 +223,7 @@ __global__ void __launch_bounds__(V2_THREADS) confusion_ece_stream_kernel(const 
                     // the host has checked that floor(v * n_bins) is within one bin of the truth for these edges
                     k += (c >= hi && k < p.n_bins - 1) ? 1 : 0;
                     k -= (c < lo && k > 0) ? 1 : 0;
-                    const bool ok = raw == raw && c >= e_first && c <= e_last && !(p.has_ignore && lb[s][u] == p.ignore);
+                    const bool ok = raw == raw && c >= e_first && c <= e_last && !(p.has_ignore && lb[s][u] == ignore);
                     const int cell = (ok ? k : p.n_bins) * V2_THREADS + tid;
                     bnc[cell] += 0x10000u + (pr[s][u] == lb[s][u] ? 1u : 0u);
                     bsum[cell] += __float2ull_rn(c * 4294967296.0f);
@@ -331,11 +351,12 @@ extern "C" int slu_score_hist(const float* d_score, const int64_t* d_pred, const
     return 0;
 }
 
-extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const float* d_conf,
-                                 int64_t n, int C, int has_ignore, int64_t ignore,
-                                 int n_bins, const float* h_edges,
-                                 int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
-    using namespace slu;
+namespace slu {
+template <typename IT>
+static int confusion_ece_impl(const IT* d_pred, const IT* d_labels, const float* d_conf,
+                              int64_t n, int C, int has_ignore, int64_t ignore,
+                              int n_bins, const float* h_edges,
+                              int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
     if (n < 0) return fail(SLU_E_ARG, "n=%lld < 0", (long long)n);
     if (n == 0) return 0;
     if (!d_pred || !d_labels) return fail(SLU_E_ARG, "d_pred / d_labels is NULL");
@@ -348,9 +369,10 @@ extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels,
             if (!(h_edges[i] < h_edges[i + 1])) return fail(SLU_E_ARG, "bin edges must increase strictly");
     }
     if (!d_confmat && !d_ece_bins) return 0;
+    if (sizeof(IT) == 4 && has_ignore && (ignore < INT32_MIN || ignore > INT32_MAX)) has_ignore = 0;   // no int32 label can match
     HistParams p{};
-    p.pred = reinterpret_cast<const long long*>(d_pred);
-    p.labels = reinterpret_cast<const long long*>(d_labels);
+    p.pred = d_pred;
+    p.labels = d_labels;
     p.conf = d_conf;
     p.n = n; p.C = C; p.has_ignore = has_ignore; p.ignore = ignore;
     p.n_bins = d_ece_bins ? n_bins : 0;
@@ -371,7 +393,7 @@ extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels,
         int dev = 0;
         SLU_CUDA(cudaGetDevice(&dev));
         if (dev < 64 && !attr_set[dev]) {
-            SLU_CUDA(cudaFuncSetAttribute(confusion_ece_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            SLU_CUDA(cudaFuncSetAttribute(confusion_ece_stream_kernel<IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
             attr_set[dev] = true;
         }
         const int per_sm = L.total <= 56 * 1024 ? 4 : (L.total <= 75 * 1024 ? 3 : 2);
@@ -382,23 +404,40 @@ extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels,
             if (seg / V2_PX > groups_cap) seg = groups_cap * V2_PX;
             const long long want = (seg / V2_PX + V2_THREADS * V2_STEPS - 1) / (V2_THREADS * V2_STEPS);
             const long long cap = (long long)per_sm * sms;
-            confusion_ece_stream_kernel<<<(unsigned)(want < cap ? want : cap), V2_THREADS, L.total, st>>>(p, L.cm_copies, L.cm_bytes, done, seg);
+            confusion_ece_stream_kernel<IT><<<(unsigned)(want < cap ? want : cap), V2_THREADS, L.total, st>>>(p, L.cm_copies, L.cm_bytes, done, seg);
             SLU_LAUNCH_CHECK("confusion_ece_stream_kernel");
             done += seg;
         }
         if (done == n) return 0;
-        p.pred += done; p.labels += done; if (p.conf) p.conf += done; p.n = n - done;      // < 4 trailing pixels
+        p.pred = d_pred + done; p.labels = d_labels + done; if (p.conf) p.conf += done; p.n = n - done;      // < 4 trailing pixels
     }
     const long long chunk = (long long)HIST_THREADS * HIST_UNROLL;
     const long long want = (p.n + chunk - 1) / chunk;
     const long long cap = 8LL * sms;                       // 8 resident CTAs of 256 threads per SM
     const int grid = (int)(want < cap ? want : cap);
     if (C * C <= HIST_SMEM_CELLS)
-        confusion_ece_kernel<true><<<grid, HIST_THREADS, 0, st>>>(p);
+        confusion_ece_kernel<true, IT><<<grid, HIST_THREADS, 0, st>>>(p);
     else
-        confusion_ece_kernel<false><<<grid, HIST_THREADS, 0, st>>>(p);
+        confusion_ece_kernel<false, IT><<<grid, HIST_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("confusion_ece_kernel");
     return 0;
+}
+}  // namespace slu
+
+extern "C" int slu_confusion_ece(const int64_t* d_pred, const int64_t* d_labels, const float* d_conf,
+                                 int64_t n, int C, int has_ignore, int64_t ignore,
+                                 int n_bins, const float* h_edges,
+                                 int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
+    return slu::confusion_ece_impl<long long>(reinterpret_cast<const long long*>(d_pred), reinterpret_cast<const long long*>(d_labels),
+                                              d_conf, n, C, has_ignore, ignore, n_bins, h_edges, d_confmat, d_ece_bins, stream);
+}
+
+/* int32 prediction / label maps: 12 B/px instead of 20 and 32-bit validity tests; same counters, bit-identical results */
+extern "C" int slu_confusion_ece_i32(const int32_t* d_pred, const int32_t* d_labels, const float* d_conf,
+                                     int64_t n, int C, int has_ignore, int64_t ignore,
+                                     int n_bins, const float* h_edges,
+                                     int64_t* d_confmat, int64_t* d_ece_bins, slu_stream_t stream) {
+    return slu::confusion_ece_impl<int>(d_pred, d_labels, d_conf, n, C, has_ignore, ignore, n_bins, h_edges, d_confmat, d_ece_bins, stream);
 }
 
 /* A/B switch for tests and profiles: 1 = always use the generic (warp-aggregated) histogram kernel. */

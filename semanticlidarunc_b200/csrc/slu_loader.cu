@@ -31,6 +31,7 @@ struct FrameParams {
     float* range;            // [B,1,Hd*Wd]
     float* refl;             // [B,1,Hd*Wd]
     float* xyz;              // [B,3,Hd*Wd]
+    long long xyz_bstride;   // elements between the xyz planes of consecutive scans (3*Hd*Wd; 6*HW when reading the image)
     float* normals;          // [B,3,Hd*Wd]
     long long* sem;          // [B,1,Hd*Wd]
 };
@@ -106,7 +107,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 __global__ void __launch_bounds__(FR_THREADS) frame_normals_kernel(const __grid_constant__ FrameParams p) {
     const int b = blockIdx.y;
     const long long HW = (long long)p.Hd * p.Wd;
-    const float* base = p.xyz + (long long)b * 3 * HW;
+    const float* base = p.xyz + (long long)b * p.xyz_bstride;
     float* out = p.normals + (long long)b * 3 * HW;
     // with dropped rows and no resize the image really has rowmap[0] rows: reflect at that border
     const int h_eff = (p.rowmap && p.keep_native_h) ? p.rowmap[(long long)b * (p.Hs + 1)] : p.Hd;
@@ -240,6 +241,7 @@ extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int 
     const float scale = 1.0f / norm_factor;
     p.tap_c = 10.0f * scale; p.tap_s = 3.0f * scale;
     p.range = d_range; p.refl = d_refl; p.xyz = d_xyz; p.normals = d_normals;
+    p.xyz_bstride = 3LL * Hd * Wd;
     p.sem = reinterpret_cast<long long*>(d_sem);
     p.rowmap = d_rowmap;
     p.keep_native_h = (d_rowmap && !resize_rows) ? 1 : 0;
@@ -262,5 +264,32 @@ extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int 
         frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
         SLU_LAUNCH_CHECK("frame_normals_kernel");
     }
+    return 0;
+}
+
+/* Normals straight from planar xyz (no resize, no flip): the x, y, z planes of scan b start at d_xyz + b * batch_stride
+ * (3*H*W for a packed [B,3,H,W] tensor, 6*H*W for the first three planes of the projection image [B,6,H,W]). */
+extern "C" int slu_frame_normals(const float* d_xyz, int B, int H, int W, int64_t batch_stride, float norm_factor,
+                                 float* d_normals, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_xyz || !d_normals) return fail(SLU_E_ARG, "d_xyz / d_normals is NULL");
+    if (B < 1 || B > 65535 || H < 1 || W < 1) return fail(SLU_E_RANGE, "B=%d H=%d W=%d unsupported", B, H, W);
+    if (batch_stride < 3LL * H * W) return fail(SLU_E_ARG, "batch_stride smaller than three planes");
+    if (!(norm_factor > 0.f)) return fail(SLU_E_ARG, "norm_factor must be > 0");
+    FrameParams p{};
+    p.B = B; p.Hs = H; p.Ws = W; p.Hd = H; p.Wd = W;
+    const float scale = 1.0f / norm_factor;
+    p.tap_c = 10.0f * scale; p.tap_s = 3.0f * scale;
+    p.xyz = const_cast<float*>(d_xyz);
+    p.xyz_bstride = batch_stride;
+    p.normals = d_normals;
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    const long long HW = (long long)H * W;
+    long long gx = (HW + FR_THREADS - 1) / FR_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;
+    if (gx > cap) gx = cap;
+    frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    SLU_LAUNCH_CHECK("frame_normals_kernel");
     return 0;
 }

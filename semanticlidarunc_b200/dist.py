@@ -39,8 +39,27 @@ def pack_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None) 
     return torch.cat(parts).to(torch.int64)
 
 
+def allreduce_packed(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum a packed int64 counter buffer over all ranks, in place (no-op without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def reduced_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None, group=None):
+    """(confmat, ece_bins) summed over all ranks with a single all-reduce of a packed COPY.  The arguments are
+    left untouched, so live accumulators can keep accumulating and be reduced again later."""
+    buf = allreduce_packed(pack_counts(confmat, ece_bins), group=group)
+    n = confmat.numel()
+    return buf[:n].view_as(confmat), (None if ece_bins is None else buf[n:].view_as(ece_bins))
+
+
 def allreduce_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None, group=None) -> None:
-    """Sum the evaluation counters over all ranks, in place, with a single all-reduce."""
+    """Sum the evaluation counters over all ranks IN PLACE with a single all-reduce.
+
+    The arguments afterwards hold GLOBAL sums: do not keep accumulating into them and do not reduce them a second
+    time (every count would be multiplied by the world size) -- end-of-sweep use only.  For live accumulators use
+    `reduced_counts`, which reduces a copy."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     buf = pack_counts(confmat, ece_bins)

@@ -88,12 +88,53 @@ class AUROCAggregator:
         preds, labels = preds.to(dev, non_blocking=True), labels.to(dev, non_blocking=True)
         score_map, pred = self._scores_and_pred(preds)
         if score_override is not None:
-            score_map = score_override.to(dev)          # expected in [0,1] (H_norm / MI_norm maps); clamped otherwise
+            score_map = self._unit_range(score_override.to(dev), preds.size(1))
         ops.score_hist(score_map, pred, labels, self._accumulator(dev),
                        ignore=() if self.ignore_index is None else (self.ignore_index,))
 
+    @staticmethod
+    def _unit_range(score: torch.Tensor, num_classes: int) -> torch.Tensor:
+        """The histogram covers [0,1].  The reference uses an override verbatim and only its RANKS matter
+        (src/metrics/auroc.py:124-126), so a score that leaves [0,1] -- an un-normalised entropy or MI, at most
+        ln C -- is mapped into it monotonically instead of saturating in the last bin: divide by ln C when that
+        suffices, otherwise squash with x / (1 + x).  Negative scores raise (no entropy-like score is negative)."""
+        lo, hi = torch.aminmax(torch.nan_to_num(score.detach().float(), nan=0.0))
+        lo, hi = float(lo), float(hi)
+        if lo < -1e-6:
+            raise ValueError(f"score_override has negative values (min {lo}); AUROCAggregator expects a non-negative uncertainty score")
+        if hi <= 1.0:
+            return score
+        if hi <= math.log(num_classes) * (1 + 1e-6):
+            return score / math.log(num_classes)
+        return score / (1.0 + score)
+
+    @property
+    def _scores(self) -> torch.Tensor:
+        """Host view for code that reads the reference's per-pixel buffer (the sanity prints of Tester.test_epoch,
+        src/models/tester.py:672-677): bin-centre scores, one per counted pixel, thinned proportionally to at most
+        `max_samples` (default 1 000 000) entries.  `_is_error` is aligned with it."""
+        return self._expanded()[0]
+
+    @property
+    def _is_error(self) -> torch.Tensor:
+        return self._expanded()[1]
+
+    def _expanded(self):
+        if self._hist is None:
+            return torch.empty(0), torch.empty(0, dtype=torch.uint8)
+        h = self._hist.cpu().numpy()
+        cap = int(self.max_samples) if self.max_samples else 1_000_000
+        total = int(h.sum())
+        if total > cap:
+            h = np.floor(h * (cap / total) + 0.5).astype(np.int64)
+        centres = ((np.arange(h.shape[1]) + 0.5) / h.shape[1]).astype(np.float32)
+        scores = np.concatenate([np.repeat(centres, h[0]), np.repeat(centres, h[1])])
+        err = np.concatenate([np.zeros(int(h[0].sum()), np.uint8), np.ones(int(h[1].sum()), np.uint8)])
+        return torch.from_numpy(scores), torch.from_numpy(err)
+
     def add_maps(self, score_map: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor):
-        """Accumulate from maps the fused kernel already produced (no second pass over the class axis)."""
+        """Accumulate from maps the fused kernel already produced (no second pass over the class axis).  The score
+        must already lie in [0,1] (the kernels' *_norm maps do); nothing is checked here, so the call never synchronises."""
         ops.score_hist(score_map, pred, labels, self._accumulator(score_map.device),
                        ignore=() if self.ignore_index is None else (self.ignore_index,))
 

@@ -12,7 +12,8 @@ point.  Differences, all deliberate:
     ece.py:93-111) is accepted and ignored, so results equal the reference with max_samples=None;
   * the per-bin sums are exact integers, where np.histogram accumulates float32 weights
     (ece.py:136-138); ECE agrees to ~1e-6 relative, not bit for bit;
-  * binning="adaptive" needs all samples and is not supported;
+  * binning="adaptive" (equal-mass edges) reads its quantile edges off a fine [2,60000] confidence histogram kept
+    beside the counters, i.e. at a confidence resolution of 1/60000 instead of from every stored sample;
   * compute(save_plot_path=None) returns fig=None instead of raising UnboundLocalError (ece.py:212).
 The private `_conf/_correct` arrays the reference Tester caches (src/models/tester.py:334-337) do
 not exist; `state_dict()/load_state_dict()` carry the counters instead.
@@ -35,9 +36,6 @@ class ECEAggregator:
         assert plot_style in {"classic", "classic+hist", "gap"}
         assert mode in {"alpha", "logits", "probs"}
         assert n_bins >= 2
-        if binning == "adaptive":
-            raise NotImplementedError("adaptive (equal-mass) binning needs every sample; the streaming "
-                                      "histogram supports binning='uniform' only")
         if n_bins > _lib.MAX_BINS:
             raise ValueError(f"n_bins={n_bins} > {_lib.MAX_BINS}")
         self.n_bins = int(n_bins)
@@ -49,6 +47,10 @@ class ECEAggregator:
         self.plot_style = plot_style
         self._bins = None           # [3,n_bins] int64 on the GPU
         self._edges = ops.uniform_edges(self.n_bins)
+        # binning="adaptive" (equal-mass edges, src/metrics/ece.py:118-126) needs the confidence distribution: a fine
+        # [2, 60000] (correct | wrong) histogram of the confidences is kept beside the uniform bins and the quantile
+        # edges are read off its CDF at compute() -- resolution 1/60000 in confidence instead of every sample
+        self._fine = None
 
     # -- state ---------------------------------------------------------------------------------
     def _accumulator(self, dev=None) -> torch.Tensor:
@@ -59,6 +61,8 @@ class ECEAggregator:
     def reset(self):
         if self._bins is not None:
             self._bins.zero_()
+        if self._fine is not None:
+            self._fine.zero_()
 
     @property
     def _seen(self) -> int:
@@ -80,18 +84,51 @@ class ECEAggregator:
         assert preds.dim() == 4 and labels.dim() == 3
         dev = preds.device if preds.is_cuda else (labels.device if labels.is_cuda else _lib.require_cuda())
         kind, conf_mode = _MODES[self.mode]
-        ops.reduce_metrics(preds.to(dev, non_blocking=True), labels.to(dev, non_blocking=True), kind=kind,
-                           conf_mode=conf_mode, eps=self.eps, ignore_index=self.ignore_index,
-                           edges=self._edges, ece_bins=self._accumulator(dev), want=())
+        labels = labels.to(dev, non_blocking=True)
+        r = ops.reduce_metrics(preds.to(dev, non_blocking=True), labels, kind=kind,
+                               conf_mode=conf_mode, eps=self.eps, ignore_index=self.ignore_index,
+                               edges=self._edges, ece_bins=self._accumulator(dev),
+                               want=("conf", "pred") if self.binning == "adaptive" else ())
+        if self.binning == "adaptive":
+            if self._fine is None:
+                self._fine = ops.new_score_hist(dev)
+            ops.score_hist(r["conf"], r["pred"], labels, self._fine,
+                           ignore=() if self.ignore_index is None else (self.ignore_index,))
 
     def add_bins(self, ece_bins: torch.Tensor):
         """Merge counters produced elsewhere (the fused MC path, another rank)."""
         self._accumulator(ece_bins.device if ece_bins.is_cuda else None).add_(ece_bins.to(self._accumulator().device))
 
     # -- result --------------------------------------------------------------------------------
+    def _adaptive_stats(self) -> pd.DataFrame:
+        h = self._fine.cpu().numpy().astype(np.float64)
+        M = h.shape[1]
+        tot = h[0] + h[1]
+        N = tot.sum()
+        cdf = np.cumsum(tot) / N
+        q = np.linspace(0.0, 1.0, self.n_bins + 1)
+        edges = np.minimum((np.searchsorted(cdf, q, side="left") + 1) / M, 1.0)
+        edges[0], edges[-1] = 0.0, 1.0
+        edges = np.unique(edges)
+        if edges.size < self.n_bins + 1:                      # many identical confidences: fall back, as ece.py:124-125
+            edges = np.linspace(0.0, 1.0, self.n_bins + 1)
+        centres = (np.arange(M) + 0.5) / M
+        which = np.clip(np.searchsorted(edges, centres, side="right") - 1, 0, edges.size - 2)
+        n = np.bincount(which, weights=tot, minlength=edges.size - 1)
+        c = np.bincount(which, weights=h[0], minlength=edges.size - 1)
+        sconf = np.bincount(which, weights=tot * centres, minlength=edges.size - 1)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            acc = np.where(n > 0, c / n, np.nan)
+            avg = np.where(n > 0, sconf / n, np.nan)
+        lows, highs = edges[:-1].astype(np.float32), edges[1:].astype(np.float32)
+        return pd.DataFrame({"low": lows, "high": highs, "center": 0.5 * (lows + highs), "width": highs - lows,
+                             "n": n.astype(int), "pct": 100.0 * n / max(1, int(N)), "acc": acc, "conf": avg})
+
     def _stats_df(self) -> pd.DataFrame:
         if self._bins is None or self._seen == 0:
             return pd.DataFrame(columns=["low", "high", "center", "width", "n", "pct", "acc", "conf"])
+        if self.binning == "adaptive" and self._fine is not None:
+            return self._adaptive_stats()
         _, _, n, acc, avg = ops.ece_from_bins(self._bins)
         lows, highs = self._edges[:-1], self._edges[1:]
         return pd.DataFrame({"low": lows, "high": highs, "center": 0.5 * (lows + highs), "width": highs - lows,

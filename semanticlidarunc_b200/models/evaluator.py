@@ -120,8 +120,13 @@ class UncertaintyAccuracyAggregator:
         dev = uncertainty.device if uncertainty.is_cuda else _lib.require_cuda()
         if self._hist is None:
             self._hist = ops.new_score_hist(dev, self.n_score_bins)
-        ops.score_hist(uncertainty.detach().to(dev), preds.detach().to(dev), labels.detach().to(dev), self._hist,
-                       ignore=tuple(ignore_ids))
+        labels = labels.detach().to(dev)
+        ignore = tuple(int(v) for v in ignore_ids)
+        if len(ignore) > 4:                         # the kernel takes four ids: fold longer lists into the score (NaN = skipped)
+            drop = torch.isin(labels, torch.tensor(ignore, device=dev, dtype=labels.dtype))
+            uncertainty = torch.where(drop, torch.full_like(uncertainty, float("nan")), uncertainty.to(dev))
+            ignore = ()
+        ops.score_hist(uncertainty.detach().to(dev), preds.detach().to(dev), labels, self._hist, ignore=ignore)
 
     def make_bins(self, num_bins: int | None = None, bin_width: float | None = None, bin_edges=None) -> np.ndarray:
         if bin_edges is not None:
@@ -151,6 +156,46 @@ class UncertaintyAccuracyAggregator:
         labels = [f"[{l:.2f}, {hh:.2f})" if i < len(lows) - 1 else f"[{l:.2f}, {hh:.2f}]" for i, (l, hh) in enumerate(zip(lows, highs))]
         return pd.DataFrame({"low": lows, "high": highs, "label": labels, "n": n.astype(int),
                              "pct": 100.0 * n / max(1.0, n.sum()), "accuracy": acc})
+
+
+    def plot_accuracy_vs_uncertainty_bins(self, num_bins: int = 10, bin_width: float | None = None, bin_edges=None,
+                                          figsize=(14, 5), title="Pixel Accuracy vs Predictive-Uncertainty (binned)",
+                                          x_label="Normalized predictive-entropy bin", y_label="Accuracy",
+                                          show_percent_on_bars: bool = True, annotate_min_pct: float = 0.1,
+                                          annotate_every: int = 1, percent_fmt: str = "{:.1f}%", save_path: str | None = None,
+                                          show: bool = False, close_fig: bool = True, dpi: int = 200,
+                                          cmap_name: str = "viridis", color_norm: str = "linear"):
+        """Same call as src/models/evaluator.py:752-870.  The statistics come from the device histogram; the bar chart
+        is drawn only when matplotlib is installed (host-side plotting is not part of the hot path).  Returns the stats."""
+        stats = self.binned_accuracy(num_bins=num_bins, bin_width=bin_width, bin_edges=bin_edges)
+        if stats.empty or stats["n"].sum() == 0:
+            print("No data to plot.")
+            return None
+        plt = _pyplot()
+        if plt is not None and save_path:
+            fig, ax = plt.subplots(figsize=figsize, dpi=dpi)
+            ax.bar(np.arange(len(stats)), stats["accuracy"].fillna(0.0).to_numpy(), width=0.9)
+            ax.set_xticks(np.arange(len(stats)))
+            ax.set_xticklabels(stats["label"], rotation=45, ha="right")
+            if show_percent_on_bars:
+                for i, (a, pc) in enumerate(zip(stats["accuracy"], stats["pct"])):
+                    if pc >= annotate_min_pct and i % max(1, annotate_every) == 0 and a == a:
+                        ax.text(i, a, percent_fmt.format(pc), ha="center", va="bottom", fontsize=8)
+            ax.set_ylim(0, 1); ax.set_xlabel(x_label); ax.set_ylabel(y_label); ax.set_title(title)
+            fig.tight_layout(); fig.savefig(save_path, dpi=dpi, bbox_inches="tight")
+            if close_fig:
+                plt.close(fig)
+        return stats
+
+
+def _pyplot():
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        return plt
+    except Exception:
+        return None
 
 
 class UncertaintyPerClassAggregator:
@@ -223,3 +268,83 @@ class UncertaintyPerClassAggregator:
         if not rows:
             return pd.DataFrame(columns=["class_id", "class", "uncertainty"])
         return pd.concat(rows, ignore_index=True)
+
+    def density(self, bins: int = 2048, bandwidth="silverman"):
+        """Per-class smoothed densities on a [0,1] grid: the histogram convolved with a Gaussian whose width follows
+        Silverman's / Scott's rule (or a float in x units), reflected at both ends -- what plot_ridgeline_fast draws
+        (src/models/evaluator.py:413-538).  Returns (grid [bins], {class_id: density [bins]})."""
+        grid = (np.arange(bins) + 0.5) / bins
+        if self._hist is None:
+            return grid, {}
+        h = self._hist.cpu().numpy().astype(np.float64)
+        M = self.n_score_bins
+        centres = (np.arange(M) + 0.5) / M
+        stats = self.class_stats().set_index("class_id")
+        out = {}
+        for c in range(self.num_classes):
+            n = h[c].sum()
+            if n == 0:
+                continue
+            mean = float(stats.loc[c, "mean"])
+            std = float(np.sqrt(max(1e-12, (h[c] * (centres - mean) ** 2).sum() / n)))
+            if isinstance(bandwidth, str):
+                iqr = float(stats.loc[c, "q75"] - stats.loc[c, "q25"])
+                sig = min(std, iqr / 1.349) if iqr > 0 else std
+                bw = (0.9 if bandwidth == "silverman" else 1.059) * sig * n ** (-0.2)
+            else:
+                bw = float(bandwidth)
+            bw = max(bw, 1.0 / bins)
+            coarse = np.bincount(np.minimum((centres * bins).astype(np.int64), bins - 1), weights=h[c], minlength=bins)
+            half = int(min(bins, np.ceil(4 * bw * bins)))
+            k = np.exp(-0.5 * ((np.arange(-half, half + 1) / bins) / bw) ** 2)
+            k /= k.sum()
+            padded = np.concatenate([coarse[:half][::-1], coarse, coarse[-half:][::-1]]) if half > 0 else coarse
+            dens = np.convolve(padded, k, mode="same")[half:half + bins] if half > 0 else coarse
+            out[c] = dens / max(dens.sum() / bins, 1e-30)
+        return grid, out
+
+    def plot_ridgeline_fast(self, class_names: list, color_map: dict, ignore_ids=(), figsize=(14, 9),
+                            title="Normalized Uncertainty per Class (Ridgeline)", x_label="Normalized uncertainty",
+                            bins: int = 2048, bandwidth="silverman", fill_alpha: float = 0.9, line_width: float = 1.0,
+                            save_path: str | None = None, dpi: int = 200):
+        """Same call as src/models/evaluator.py:413-538; densities from the device histogram, drawn only when matplotlib
+        is installed.  Returns (grid, densities)."""
+        grid, dens = self.density(bins=min(int(bins), 8192), bandwidth=bandwidth)
+        ids = [c for c in dens if c not in set(ignore_ids)]
+        if not ids:
+            print("No data to plot.")
+            return grid, {}
+        plt = _pyplot()
+        if plt is not None and save_path:
+            fig, ax = plt.subplots(figsize=figsize, dpi=dpi)
+            for row, c in enumerate(ids):
+                y = dens[c] / max(dens[c].max(), 1e-30) * 0.9
+                col = np.array(color_map[c]) / 255.0
+                ax.fill_between(grid, row, row + y, color=col, alpha=fill_alpha, linewidth=line_width)
+            ax.set_yticks(np.arange(len(ids)) + 0.2); ax.set_yticklabels([class_names[c] for c in ids])
+            ax.set_xlim(0, 1); ax.set_xlabel(x_label); ax.set_title(title)
+            fig.tight_layout(); fig.savefig(save_path, dpi=dpi, bbox_inches="tight"); plt.close(fig)
+        return grid, {c: dens[c] for c in ids}
+
+
+def plot_iou_sorted_by_uncertainty(unc_agg, result_dict: dict, class_names: list, color_map: dict, ignore_ids=(0,),
+                                   figsize=(18, 6), title="mIoU per class, sorted by mean uncertainty", y_label="mIoU",
+                                   save_path: str | None = None, dpi: int = 200):
+    """Same call as src/models/evaluator.py:546-630: per-class IoU ordered by the class's mean uncertainty (exact means from
+    the aggregator's fixed-point sums).  Returns the ordered DataFrame; draws only when matplotlib is installed."""
+    st = unc_agg.class_stats()
+    st = st[~st["class_id"].isin(set(ignore_ids))].copy()
+    if st.empty:
+        print("No data to plot.")
+        return st
+    st["class"] = [class_names[int(c)] for c in st["class_id"]]
+    st["iou"] = [float(result_dict.get(n, float("nan"))) for n in st["class"]]
+    st = st.sort_values("mean").reset_index(drop=True)
+    plt = _pyplot()
+    if plt is not None and save_path:
+        fig, ax = plt.subplots(figsize=figsize, dpi=dpi)
+        ax.bar(np.arange(len(st)), st["iou"], color=[np.array(color_map[int(c)]) / 255.0 for c in st["class_id"]])
+        ax.set_xticks(np.arange(len(st))); ax.set_xticklabels(st["class"], rotation=45, ha="right")
+        ax.set_ylabel(y_label); ax.set_title(title)
+        fig.tight_layout(); fig.savefig(save_path, dpi=dpi, bbox_inches="tight"); plt.close(fig)
+    return st

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import math
 
+import numpy as np
 import torch
 
 from .. import _lib, ops
@@ -137,6 +138,51 @@ def get_epistemic_fraction(alpha, eps=None, min_h=None):
 def get_eu_minus_au_fraction(alpha, eps=None, min_h=None):
     auf, euf = _fractions(alpha, eps, min_h)
     return (euf - auf).clamp(-1.0, 1.0)                   # :238-246
+
+
+def _colour(x: np.ndarray, lo: float, hi: float, mask):
+    """float map -> BGR uint8 image with OpenCV's TURBO colour map; `mask` rows (y, x) are blacked out."""
+    import cv2
+    x = np.clip((x - lo) / (hi - lo + 1e-12), 0, 1)
+    img = cv2.applyColorMap((x * 255).astype(np.uint8), cv2.COLORMAP_TURBO)
+    if mask is not None:
+        img[mask[:, 0], mask[:, 1]] = [0, 0, 0]
+    return img
+
+
+def build_uncertainty_layers(alpha: torch.Tensor, names: list, idx: int = 0, h_mask_thresh: float = 0.0, eps=None, mask=None) -> dict:
+    """Visualisation layers of ONE sample (:294-335): every requested map comes out of a single evidential kernel call on
+    alpha[idx]; quantile clipping (2 % / 98 %) and the TURBO colour map run on the host image, as in the reference."""
+    eps = get_eps_value() if eps is None else eps
+    a = _cuda(alpha.detach())[idx:idx + 1]
+    C = a.shape[1]
+    r = ops.evidential_reduce(a, from_outputs=False, eps=eps, normalize=False, want=("H", "AU", "EU"))
+    H, AU, EU = r["H"][0], r["AU"][0], r["EU"][0]
+    denom = torch.clamp(H, min=1e-6)
+    maps = {}
+    if "H_norm" in names:
+        maps["H_norm"] = H / math.log(C)
+    if "AU_norm" in names:
+        maps["AU_norm"] = get_aleatoric_uncertainty_norm(a, eps)[0]
+    if "EU_norm" in names:
+        maps["EU_norm"] = get_epistemic_uncertainty_norm(a, eps)[0]
+    if "alpha0" in names:
+        maps["alpha0"] = a.sum(dim=1)[0] + eps
+    if "AU_frac" in names:
+        maps["AU_frac"] = (AU / denom).clamp(0.0, 1.0)
+    if "EU_frac" in names:
+        maps["EU_frac"] = (EU / denom).clamp(0.0, 1.0)
+    out = {}
+    for k, m in maps.items():
+        x = m.float().cpu().numpy()
+        lo, hi = np.quantile(x, 0.02), np.quantile(x, 0.98)
+        if hi <= lo:
+            lo, hi = x.min(), x.max() + 1e-6
+        out[k] = _colour(x, lo, hi, mask)
+    if "EU_minus_AU_frac" in names:
+        d = ((EU / denom).clamp(0.0, 1.0) - (AU / denom).clamp(0.0, 1.0)).clamp(-1.0, 1.0)
+        out["EU_minus_AU_frac"] = _colour(d.float().cpu().numpy(), -1.0, 1.0, mask)
+    return out
 
 
 @torch.no_grad()

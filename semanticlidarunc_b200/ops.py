@@ -33,6 +33,7 @@ def new_ece_bins(n_bins: int, device) -> torch.Tensor:
     return torch.zeros((3, n_bins), dtype=torch.int64, device=device)
 
 
+@_lib.device_guard
 def reduce_metrics(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, kind: str = "logits",
                    conf_mode: int = CONF_RAW, eps: float = 1e-12, ignore_index: Optional[int] = None,
                    edges: Optional[Sequence[float]] = None,
@@ -92,6 +93,7 @@ def reduce_metrics(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, ki
     return out
 
 
+@_lib.device_guard
 def evidential_reduce(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *, from_outputs: bool,
                       temperature: float = 1.0, eps: float = 1e-8, eps_metrics: float = 1e-12, normalize: bool = True,
                       ignore_index: Optional[int] = None, edges=None,
@@ -138,6 +140,7 @@ def evidential_reduce(x: torch.Tensor, labels: Optional[torch.Tensor] = None, *,
     return out
 
 
+@_lib.device_guard
 def dirichlet_loss(alpha: torch.Tensor, target: torch.Tensor, *, ignore=(), keep_mask: Optional[torch.Tensor] = None,
                    eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_mse: bool = True, want_kl: bool = True,
                    want_grad: bool = True, sums: Optional[torch.Tensor] = None) -> dict:
@@ -176,6 +179,7 @@ def dirichlet_loss(alpha: torch.Tensor, target: torch.Tensor, *, ignore=(), keep
 TERM_NLL, TERM_DIGAMMA_CE, TERM_BRIER = 2, 3, 4
 
 
+@_lib.device_guard
 def dirichlet_term(alpha: torch.Tensor, target: torch.Tensor, term: int, *, ignore=(), keep_mask: Optional[torch.Tensor] = None,
                    eps: float = 1e-12, s_ref: Optional[float] = None, want_grad: bool = True) -> dict:
     """One alternative data-fit term (slu_dirichlet_term): sums float64[2] (sum | n_valid) and grad [B,C,H,W]."""
@@ -220,6 +224,7 @@ def _mask_args(target, keep_mask, ignore, shape, device):
     return target, keep_mask, h_ign, len(ign)
 
 
+@_lib.device_guard
 def evidence_term(alpha: torch.Tensor, target: Optional[torch.Tensor], term: int, params, *, ignore=(),
                   keep_mask: Optional[torch.Tensor] = None, want_grad: bool = True) -> dict:
     """One of the TERM_COMP_KL / WRONG_LOW / EVID_BAND / EVID_REG / KL_CONF terms (slu_evidence_term):
@@ -239,6 +244,7 @@ def evidence_term(alpha: torch.Tensor, target: Optional[torch.Tensor], term: int
     return {"sums": sums, "grad": grad}
 
 
+@_lib.device_guard
 def logit_regularizer(logits: torch.Tensor, *, threshold: Optional[float] = None, target: Optional[torch.Tensor] = None,
                       ignore=(), keep_mask: Optional[torch.Tensor] = None, want_grad: bool = True) -> dict:
     """z^2 or relu(z - threshold)^2 summed over valid elements (slu_logit_regularizer): sums float64[2]
@@ -258,6 +264,7 @@ def logit_regularizer(logits: torch.Tensor, *, threshold: Optional[float] = None
     return {"sums": sums, "grad": grad}
 
 
+@_lib.device_guard
 def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse: float = 1.0, w_kl: float = 0.05,
                           ignore=(), keep_mask: Optional[torch.Tensor] = None, temperature: float = 1.0,
                           eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8, want_grad: bool = True,
@@ -297,6 +304,7 @@ def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse:
     return {"sums": sums, "grad": grad}
 
 
+@_lib.device_guard
 def special_functions(x: torch.Tensor) -> torch.Tensor:
     """[n,3] = lgamma, digamma, trigamma of x > 0 as the loss kernels evaluate them (slu_diag_special)."""
     _lib.require_cuda()
@@ -306,13 +314,17 @@ def special_functions(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_lib.device_guard
 def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch.Tensor] = None, *,
                   num_classes: int, ignore_index: Optional[int] = None, edges=None,
                   confmat: Optional[torch.Tensor] = None, ece_bins: Optional[torch.Tensor] = None) -> None:
-    """Standalone stage 4 (slu_confusion_ece) on flat int64 pred/labels (+ float32 conf)."""
+    """Standalone stage 4 on flat pred/labels (+ float32 conf): int64 maps (the reference's dtype, slu_confusion_ece)
+    or, when BOTH are int32, the 12 B/px variant slu_confusion_ece_i32; the counters are identical."""
     _lib.require_cuda()
-    pred = _lib.as_buffer(pred, torch.int64, "pred").reshape(-1)
-    labels = _lib.as_buffer(labels, torch.int64, "labels").reshape(-1)
+    i32 = pred.dtype == torch.int32 and labels.dtype == torch.int32
+    it = torch.int32 if i32 else torch.int64
+    pred = _lib.as_buffer(pred, it, "pred").reshape(-1)
+    labels = _lib.as_buffer(labels, it, "labels").reshape(-1)
     if pred.numel() != labels.numel():
         raise ValueError("pred and labels differ in size")
     if conf is not None:
@@ -324,9 +336,10 @@ def confusion_ece(pred: torch.Tensor, labels: torch.Tensor, conf: Optional[torch
         n_bins = ece_bins.size(1)
         e = uniform_edges(n_bins) if edges is None else np.asarray(edges, dtype=np.float32)
         h_edges = _lib.edges_array(e)
-    rc = _lib.lib().slu_confusion_ece(_lib.ptr(pred), _lib.ptr(labels), _lib.ptr(conf), pred.numel(), int(num_classes),
-                                      0 if ignore_index is None else 1, 0 if ignore_index is None else int(ignore_index),
-                                      n_bins, h_edges, _lib.ptr(confmat), _lib.ptr(ece_bins), _lib.stream_ptr())
+    fn = _lib.lib().slu_confusion_ece_i32 if i32 else _lib.lib().slu_confusion_ece
+    rc = fn(_lib.ptr(pred), _lib.ptr(labels), _lib.ptr(conf), pred.numel(), int(num_classes),
+            0 if ignore_index is None else 1, 0 if ignore_index is None else int(ignore_index),
+            n_bins, h_edges, _lib.ptr(confmat), _lib.ptr(ece_bins), _lib.stream_ptr())
     _lib.check(rc, "slu_confusion_ece")
 
 
@@ -338,6 +351,7 @@ def new_score_hist(device, n_score_bins: int = SCORE_BINS) -> torch.Tensor:
     return torch.zeros((2, n_score_bins), dtype=torch.int64, device=device)
 
 
+@_lib.device_guard
 def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, ignore=()) -> None:
     """Accumulate (score, pred != label) pairs into `hist` (slu_score_hist)."""
     _lib.require_cuda()
@@ -355,6 +369,7 @@ def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hi
     _lib.check(rc, "slu_score_hist")
 
 
+@_lib.device_guard
 def class_score_hist(score: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, sum_fx: torch.Tensor) -> None:
     """Accumulate scores per label class (slu_class_score_hist): hist [C,M] int64, sum_fx [C] int64 (2^-32 units)."""
     _lib.require_cuda()
@@ -372,6 +387,7 @@ def _offsets_array(offsets):
     return off, off.ctypes.data_as(_lib.C.c_void_p)
 
 
+@_lib.device_guard
 def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets, H: int, W: int, *,
                   lut: Optional[torch.Tensor] = None, theta_range=None, farthest_wins: bool = False,
                   yaw_deg=None, want_img: bool = True, want_label: bool = True,
@@ -428,6 +444,7 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
     return {"img": img, "label": label, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
 
 
+@_lib.device_guard
 def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthest_wins: bool = False,
                    want_img: bool = True) -> dict:
     """Generic stage 1 (slu_project_points): pc [N,Cin] float64 CUDA -> img [H,W,Cin] float32."""
@@ -453,6 +470,7 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
     return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag}
 
 
+@_lib.device_guard
 def organized_planes(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], H: int, W: int, *, lut: Optional[torch.Tensor] = None,
                      flip=None, col_shift=None, yaw_deg=None) -> dict:
     """Organised clouds (slu_organized_planes): xyzi [B*H*W,4] float32 -> img [B,6,H,W] planes, missing [B]."""
@@ -483,6 +501,7 @@ def organized_planes(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], H: i
     return {"img": img, "missing": missing}
 
 
+@_lib.device_guard
 def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True,
                   drop_empty_rows: bool = False) -> dict:
     """Loader glue on the device (slu_frame_tensors): img [B,6,H,W] planes -> the loaders' five tensors,
@@ -516,6 +535,22 @@ def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float 
     return out
 
 
+@_lib.device_guard
+def frame_normals(xyz: torch.Tensor, norm_factor: float = 0.25) -> torch.Tensor:
+    """build_normal_xyz on the device (slu_frame_normals): xyz [B,3,H,W] or the projection image [B,6,H,W] (its first
+    three planes are read in place) -> normals [B,3,H,W]."""
+    _lib.require_cuda()
+    xyz = _lib.as_buffer(xyz, torch.float32, "xyz")
+    if xyz.dim() != 4 or xyz.size(1) not in (3, 6):
+        raise ValueError("xyz must be [B,3,H,W] or the projection image [B,6,H,W]")
+    B, Cx, H, W = xyz.shape
+    out = torch.empty((B, 3, H, W), dtype=torch.float32, device=xyz.device)
+    rc = _lib.lib().slu_frame_normals(_lib.ptr(xyz), B, H, W, Cx * H * W, float(norm_factor), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "slu_frame_normals")
+    return out
+
+
+@_lib.device_guard
 def backproject(label_img: torch.Tensor, pix: torch.Tensor, offsets) -> torch.Tensor:
     """Stage 2 (slu_backproject): label_img [B,H,W] int64, pix [n_total] int32 -> [n_total] int64."""
     _lib.require_cuda()

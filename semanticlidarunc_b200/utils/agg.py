@@ -50,7 +50,9 @@ class _RunningMean:
             if not torch.is_tensor(mask):
                 raise TypeError("mask must be a torch.Tensor or None")
             keep = torch.broadcast_to(mask.to(x.device), x.shape)
-            contrib = torch.stack([(x * keep).sum(dtype=torch.float64), keep.sum(dtype=torch.float64)])
+            # the reference sums x[mask] (src/utils/agg.py:52): a NaN / Inf at a masked-out pixel must not reach the sum
+            contrib = torch.stack([torch.where(keep.bool(), x, torch.zeros_like(x)).sum(dtype=torch.float64),
+                                   keep.sum(dtype=torch.float64)])
         if self._pair is None:
             self._pair = contrib
         elif self._pair.device == contrib.device:

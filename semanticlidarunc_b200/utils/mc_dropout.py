@@ -1,14 +1,55 @@
 """MC-dropout reductions with the reference's names (src/utils/mc_dropout.py:121-133 and the
 closures of src/models/tester.py:419-451), computed by the fused kernel.
 
-`mc_forward` / dropout toggling stay the reference's PyTorch code (the backbone only supplies the
-logits, BASELINE.json north_star) and are not re-implemented here.
+`mc_forward` and the dropout toggles are the backbone's side of the interface (the network only supplies the
+logits, BASELINE.json north_star); they are provided with the reference's names and behaviour
+(src/utils/mc_dropout.py:13-35,99-119) so that `utils.mc_dropout` can be swapped as a whole module.
 """
 from __future__ import annotations
+
+import contextlib
 
 import torch
 
 from .. import ops
+
+_DROPOUT_TYPES = (torch.nn.Dropout, torch.nn.Dropout2d, torch.nn.Dropout3d, torch.nn.AlphaDropout,
+                  torch.nn.FeatureAlphaDropout)
+
+
+def set_dropout_mode(module: torch.nn.Module, train: bool) -> None:
+    """Switch the dropout layers (and nothing else: batch-norm statistics stay frozen) to train / eval."""
+    for m in module.modules():
+        if isinstance(m, _DROPOUT_TYPES):
+            m.train(train)
+
+
+@contextlib.contextmanager
+def dropout_sampling(module: torch.nn.Module, enable: bool = True):
+    """Dropout layers sample inside the block and are put back to eval afterwards."""
+    if enable:
+        set_dropout_mode(module, True)
+    try:
+        yield
+    finally:
+        if enable:
+            set_dropout_mode(module, False)
+
+
+@torch.no_grad()
+def mc_forward(model: torch.nn.Module, inputs, T: int = 30) -> torch.Tensor:
+    """T stochastic forward passes with the model in eval mode and only its dropout layers sampling:
+    [T,B,C,H,W] raw model outputs, written straight into one preallocated tensor (the layout
+    slu_reduce_metrics streams) instead of a list + cat."""
+    model.eval()
+    out = None
+    with dropout_sampling(model, enable=True):
+        for t in range(int(T)):
+            y = model(*inputs)
+            if out is None:
+                out = torch.empty((int(T),) + tuple(y.shape), dtype=y.dtype, device=y.device)
+            out[t].copy_(y)
+    return out
 
 
 @torch.no_grad()

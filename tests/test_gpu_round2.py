@@ -1,0 +1,174 @@
+"""Round-2 additions: launch counter, stand-alone normals, int32 histogram entry point, ScanEvaluator (all outputs on the
+host path, idempotent summary, graph capture), AUROC score overrides outside [0,1], long ignore lists."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import metrics as om
+from oracle import projection as oproj
+from oracle import uncertainty as ou
+from semanticlidarunc_b200 import _lib, ops, synth
+from semanticlidarunc_b200.dataset.definitions import build_id_lut
+from semanticlidarunc_b200.pipeline import ScanEvaluator
+
+pytestmark = pytest.mark.gpu
+
+
+def test_launch_counter_counts_kernels(cuda):
+    x, lab = synth.synth_mc_logits(1, 3, 1, 20, 8, 128)
+    n0 = _lib.launch_count()
+    ops.reduce_metrics(x.to(cuda), lab.to(cuda), kind="logits")
+    assert _lib.launch_count() - n0 == 1
+    n0 = _lib.launch_count()
+    ops.confusion_ece(torch.zeros(10, dtype=torch.int64, device=cuda), torch.zeros(10, dtype=torch.int64, device=cuda), None,
+                      num_classes=3, confmat=ops.new_confmat(3, cuda))
+    assert _lib.launch_count() - n0 == 1
+
+
+def test_frame_normals_equals_loader_normals(cuda):
+    """slu_frame_normals on the projection image in place == the normals slu_frame_tensors derives from its xyz copy,
+    and == the oracle's build_normal_xyz where the normal is well conditioned."""
+    from tests.helpers import normals_condition_mask
+    scans = [synth.synth_scan(i, "tiny") for i in range(3)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])]).astype(np.int64)
+    xyzi = torch.from_numpy(np.concatenate([s[0] for s in scans])).to(cuda)
+    raw = torch.from_numpy(np.concatenate([s[1] for s in scans]).view(np.int32)).to(cuda)
+    proj = ops.project_batch(xyzi, raw, offs, 16, 256, lut=torch.from_numpy(build_id_lut()).to(cuda))
+    a = ops.frame_normals(proj["img"])
+    b = ops.frame_tensors(proj["img"])["normals"]
+    assert torch.equal(a, b)
+    c = ops.frame_normals(proj["img"][:, :3].contiguous())
+    assert torch.equal(a, c)
+    xyz = proj["img"][0, :3].cpu().numpy()
+    ref = oproj.build_normal_xyz(np.ascontiguousarray(xyz.transpose(1, 2, 0))).transpose(2, 0, 1)
+    m = normals_condition_mask(xyz)
+    assert np.abs(a[0].cpu().numpy() - ref)[:, m].max() < 5e-5
+
+
+@pytest.mark.parametrize("n", [17, 4096, 300001])
+def test_int32_histogram_entry_point_equals_int64(cuda, n):
+    g = torch.Generator().manual_seed(n)
+    C = 20
+    pred = torch.randint(-1, C + 1, (n,), generator=g)
+    lab = torch.randint(-1, C + 1, (n,), generator=g)
+    conf = torch.rand(n, generator=g)
+    conf[::97] = float("nan")
+    cm64, b64 = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    cm32, b32 = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    ops.confusion_ece(pred.to(cuda), lab.to(cuda), conf.to(cuda), num_classes=C, ignore_index=0, confmat=cm64, ece_bins=b64)
+    ops.confusion_ece(pred.int().to(cuda), lab.int().to(cuda), conf.to(cuda), num_classes=C, ignore_index=0, confmat=cm32, ece_bins=b32)
+    assert torch.equal(cm64, cm32) and torch.equal(b64, b32)
+    assert torch.equal(cm64.cpu(), om.confusion_counts(pred, lab, C))
+
+
+def _batch(cuda, n_scans, T=3, H=16, W=256, C=20):
+    scans = [synth.synth_scan(10 + i, "tiny") for i in range(n_scans)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])]).astype(np.int64)
+    xyzi = torch.from_numpy(np.concatenate([s[0] for s in scans])).to(cuda)
+    raw = torch.from_numpy(np.concatenate([s[1] for s in scans]).view(np.int32)).to(cuda)
+    logits, _ = synth.synth_mc_logits(7, T, n_scans, C, H, W)
+    return scans, offs, xyzi, raw, logits
+
+
+def test_scan_evaluator_host_path_returns_every_map_and_matches_device_path(cuda):
+    H, W, C, T = 16, 256, 20, 3
+    scans, offs, xyzi, raw, logits = _batch(cuda, 4, T, H, W, C)
+    ev = ScanEvaluator(H, W, C, device=cuda)
+    dev_out = ev.step_device(xyzi, raw, offs, logits.to(cuda))
+    assert dev_out["normals"].shape == (4, 3, H, W)
+    cm_dev = ev.confmat.clone()
+    ev.reset()
+    host = [(torch.from_numpy(s[0]).pin_memory(), torch.from_numpy(s[1].view(np.int32)).pin_memory(),
+             logits[:, i:i + 1].contiguous().pin_memory()) for i, s in enumerate(scans)]
+    outs = ev.step_host(host)
+    assert torch.equal(ev.confmat, cm_dev)
+    for i, o in enumerate(outs):
+        assert set(o) == {"point_labels", "pred", "conf", "H_norm", "MI_norm"}
+        assert not o["pred"].is_cuda and o["point_labels"].numel() == scans[i][0].shape[0]
+        assert torch.equal(o["pred"], dev_out["pred"][i].cpu())
+        assert torch.equal(o["H_norm"], dev_out["H_norm"][i].cpu()) and torch.equal(o["MI_norm"], dev_out["MI_norm"][i].cpu())
+        assert torch.equal(o["conf"], dev_out["conf"][i].cpu())
+        assert torch.equal(o["point_labels"], dev_out["point_labels"][offs[i]:offs[i + 1]].cpu())
+        ref = ou.mc_reduce(logits[:, i:i + 1])
+        assert (o["H_norm"] - ref["H_norm"][0]).abs().max() < 1e-5
+    # pinned result buffers are per batch position, not per distinct point count: a second call reuses them
+    ids = [id(s["pred"]) for s in ev._host_out]
+    ev.step_host(host[:2])
+    assert [id(s["pred"]) for s in ev._host_out] == ids
+    h2d, d2h = ev.host_bytes_per_scan(scans[0][0].shape[0], T)
+    assert h2d == scans[0][0].shape[0] * 20 + T * C * H * W * 4 and d2h == scans[0][0].shape[0] * 8 + H * W * 20
+
+
+def test_summary_is_idempotent_and_leaves_accumulators_alone(cuda):
+    H, W, C = 16, 256, 20
+    scans, offs, xyzi, raw, logits = _batch(cuda, 2)
+    ev = ScanEvaluator(H, W, C, device=cuda)
+    ev.step_device(xyzi, raw, offs, logits.to(cuda))
+    a = ev.summary()
+    cm = ev.confmat.clone()
+    b = ev.summary()
+    assert np.array_equal(a["confmat"], b["confmat"]) and a["mIoU"] == b["mIoU"] or (np.isnan(a["mIoU"]) and np.isnan(b["mIoU"]))
+    assert torch.equal(ev.confmat, cm)
+    ev.step_device(xyzi, raw, offs, logits.to(cuda))
+    assert int(ev.confmat.sum()) == 2 * int(cm.sum())
+
+
+def test_scan_evaluator_capture_replay(cuda):
+    H, W, C = 16, 256, 20
+    scans, offs, xyzi, raw, logits = _batch(cuda, 3)
+    lg = logits.to(cuda)
+    ev = ScanEvaluator(H, W, C, device=cuda)
+    eager = ev.step_device(xyzi, raw, offs, lg)
+    cm1 = ev.confmat.clone()
+    ev.reset()
+    out = ev.capture(xyzi, raw, offs, lg)
+    assert int(ev.confmat.sum()) == 0
+    l0 = ev.launches
+    ev.replay()
+    torch.cuda.synchronize()
+    assert ev.launches - l0 >= 6
+    assert torch.equal(ev.confmat, cm1)
+    for k in ("pred", "H_norm", "MI_norm", "conf", "point_labels", "normals"):
+        assert torch.equal(out[k], eager[k]), k
+    lg.mul_(0.5)                                            # new data written INTO the static input
+    ev.replay()
+    torch.cuda.synchronize()
+    ref = ops.reduce_metrics(lg, eager["label"], kind="logits", conf_mode=ops.CONF_RENORM)
+    assert torch.equal(out["H_norm"], ref["H_norm"])
+
+
+def test_auroc_override_outside_unit_range_is_rescaled_not_saturated(cuda):
+    from semanticlidarunc_b200.metrics.auroc import AUROCAggregator
+    g = torch.Generator().manual_seed(0)
+    C = 20
+    probs = torch.softmax(torch.randn(1, C, 16, 64, generator=g) * 2, dim=1)
+    labels = torch.randint(1, C, (1, 16, 64), generator=g)
+    ent = -(probs * probs.clamp_min(1e-12).log()).sum(1)                # un-normalised entropy, up to ln C > 1
+    a = AUROCAggregator(mode="probs", score="entropy_norm")
+    a.update(probs.to(cuda), labels.to(cuda), score_override=ent.to(cuda))
+    b = AUROCAggregator(mode="probs", score="entropy_norm")
+    b.update(probs.to(cuda), labels.to(cuda), score_override=(ent / np.log(C)).to(cuda))
+    pred = probs.argmax(1)
+    ref = om.auroc_error_detection(ent.reshape(-1).numpy(), (pred != labels).reshape(-1).numpy())
+    assert a.compute()[0] == pytest.approx(b.compute()[0], abs=1e-9)
+    assert a.compute()[0] == pytest.approx(ref, abs=2e-4)
+    with pytest.raises(ValueError):
+        a.update(probs.to(cuda), labels.to(cuda), score_override=(-ent).to(cuda))
+    s, e = a._scores, a._is_error
+    assert s.numel() == e.numel() == 16 * 64 and abs(float(e.float().mean()) - float((pred != labels).float().mean())) < 1e-6
+
+
+def test_accuracy_aggregator_accepts_long_ignore_lists(cuda):
+    from semanticlidarunc_b200.models.evaluator import UncertaintyAccuracyAggregator
+    g = torch.Generator().manual_seed(1)
+    lab = torch.randint(0, 20, (2, 16, 64), generator=g)
+    pred = torch.randint(0, 20, (2, 16, 64), generator=g)
+    unc = torch.rand(2, 16, 64, generator=g)
+    ign = (0, 2, 3, 4, 5, 7, 8)
+    a = UncertaintyAccuracyAggregator()
+    a.update(lab.to(cuda), pred.to(cuda), unc.to(cuda), ignore_ids=ign)
+    keep = ~torch.isin(lab, torch.tensor(ign))
+    assert a._seen == int(keep.sum())
+    st = a.binned_accuracy(num_bins=10)
+    n_ref, acc_ref = om.binned_accuracy(unc[keep].numpy(), (pred == lab)[keep].numpy(), 10)
+    assert np.array_equal(st["n"].to_numpy(), n_ref)

@@ -54,3 +54,17 @@ def test_running_mean_decorator_on_cpu_tensors():
     twice.add(4.0)
     assert abs(twice.mean(reset=True) - 44.0 / 9) < 1e-12 and twice.mean() == 0.0
     twice.sync_ddp()                                         # no process group: a no-op
+
+
+def test_running_mean_ignores_non_finite_values_outside_the_mask():
+    """src/utils/agg.py:52 sums x[mask]: NaN / Inf at masked-out pixels must not poison the running mean."""
+    import torch
+    from semanticlidarunc_b200.utils.agg import mean_aggregator
+
+    @mean_aggregator()
+    def ident(x):
+        return x
+
+    x = torch.tensor([1.0, float("nan"), 3.0, float("inf")])
+    ident.accumulate(x, mask=torch.tensor([True, False, True, False]))
+    assert ident.mean() == 2.0
