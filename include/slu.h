@@ -134,6 +134,10 @@ int slu_evidential_reduce(const float* d_outputs, const float* d_alpha_in, const
                           float* d_alpha_out, int64_t* d_pred, float* d_conf, float* d_h, float* d_au,
                           float* d_eu, float* d_mi, int64_t* d_confmat, int64_t* d_ece_bins,
                           slu_stream_t stream);
+/* A/B switch (tests, profiles): 1 = one pixel per thread instead of the packed (two adjacent pixels per thread, FFMA2 /
+ * FMUL2 / FADD2) kernel slu_evidential_reduce picks for even HW and aligned buffers.  Returns the previous value; a
+ * negative argument only queries. */
+int slu_debug_no_packed_evidential(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * Evidential loss terms, forward + backward in one pass (training-step data path, config 5).
@@ -169,6 +173,26 @@ int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, c
 /* Number of valid pixels (validity as in slu_dirichlet_loss), ADDED to d_count[0] (float64). */
 int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t n_px,
                     const int64_t* h_ignore, int n_ignore, double* d_count, slu_stream_t stream);
+
+/* Training-step form of slu_evidential_loss_fused: no host arithmetic and no memset between steps.
+ *   d_count  [1] float64  number of valid pixels the masked mean runs over.  precounted == 0: the call counts the valid
+ *            pixels of (d_target, mask) into it (it must hold 0 on entry and is reset to 0 by the kernel);
+ *            precounted != 0: the caller has written the (all-reduced, GLOBAL) count -- slu_count_valid + one all-reduce,
+ *            possibly on another stream, ordered before this call -- and owns the buffer.
+ *   d_state  [3] float64  scratch (partial sums, CTA ticket): zero before the FIRST use, left zeroed by every call, so the
+ *            same buffers serve every following step and every replay of a captured CUDA graph.
+ *   d_loss4  [4] float32  out: loss = w_mse * mse + w_kl * kl | mse | kl | n_valid, written by the last CTA to finish
+ *            (with a global count these are this rank's SHARES of the global means).
+ *   d_grad_outputs [B,C+1,HW] or NULL: d(loss)/d(outputs), already divided by the count. */
+int slu_evidential_loss_step(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
+                             int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                             float temperature, float eps_alpha, float eps_mse, float eps_kl,
+                             float w_mse, float w_kl, int precounted, double* d_count, double* d_state,
+                             float* d_loss4, float* d_grad_outputs, slu_stream_t stream);
+/* A/B switch (tests, profiles): 1 = the loss kernels run one pixel per thread instead of the packed (two adjacent pixels
+ * per thread, FFMA2 / FMUL2 / FADD2) variants they pick for even HW and aligned buffers.  Returns the previous value;
+ * a negative argument only queries. */
+int slu_debug_no_packed_loss(int on);
 
 /* Alternative data-fit terms, one per call, forward + analytic backward.
  * Replaces: NLLDirichletCategorical (src/losses/dirichlet_losses.py:73-119), DigammaDirichletCE (:122-167),

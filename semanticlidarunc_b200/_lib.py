@@ -36,6 +36,9 @@ SIGNATURES = {
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "slu_dirichlet_loss": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p]),
     "slu_evidential_loss_fused": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p]),
+    "slu_evidential_loss_step": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p, _p, _p, _p]),
+    "slu_debug_no_packed_loss": (_i, [_i]),
+    "slu_debug_no_packed_evidential": (_i, [_i]),
     "slu_count_valid": (_i, [_p, _p, _i64, _p, _i, _p, _p]),
     "slu_dirichlet_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _p]),
     "slu_evidence_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _p, _i, _p, _p, _p]),

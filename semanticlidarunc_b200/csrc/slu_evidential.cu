@@ -19,6 +19,7 @@
 #include <math.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
+#include "slu_packed.cuh"
 
 namespace slu {
 
@@ -183,6 +184,149 @@ __global__ void __launch_bounds__(EV_THREADS, EV_MINB) evidential_kernel(const _
     atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV_THREADS);
 }
 
+// ---- packed variant: a thread owns TWO adjacent pixels (slu_packed.cuh) -------------------------------------------------
+// Same formulas, every per-class operation issued once for both pixels (FFMA2 / FMUL2 / FADD2); MUFU evaluations, arg-max
+// compares and the histogram updates stay per pixel.  Needs HW even, 8-byte aligned inputs / maps, 16-byte aligned labels
+// and pred (the dispatcher checks; otherwise the one-pixel kernel above runs).
+constexpr int EV2_THREADS = 128;
+#ifndef SLU_EV2_MINB
+#define SLU_EV2_MINB 5
+#endif
+static int g_ev_no_packed = 0;
+
+template <int CP, bool EXACT, bool MI>
+__global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kernel(const __grid_constant__ EvParams p) {
+    __shared__ AtomicHist hs;
+    const int tid = threadIdx.x;
+    atomic_hist_zero(hs, p.C, tid, EV2_THREADS);
+    for (int i = tid; i <= p.n_bins; i += EV2_THREADS) hs.edges[i] = p.edges[i];
+    __syncthreads();
+    int since_flush = 0;
+
+    const long long pairs = p.n_px >> 1;
+    const long long chunks = (pairs + EV2_THREADS - 1) / EV2_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        if (p.labels && ++since_flush > ATOMIC_HIST_MAX_PX / (2 * EV2_THREADS)) {      // CTA-uniform: keep the split sums below 2^32
+            __syncthreads();
+            atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV2_THREADS);
+            __syncthreads();
+            atomic_hist_zero(hs, p.C, tid, EV2_THREADS);
+            __syncthreads();
+            since_flush = 1;
+        }
+        const long long pi = ch * EV2_THREADS + tid;
+        const bool live = pi < pairs;
+        const long long g = (live ? pi : pairs - 1) << 1;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        f2 a[CP];
+        int pred0 = 0, pred1 = 0;
+        if (p.outputs) {
+            const float* base = p.outputs + ((long long)b * (p.C + 1)) * p.HW + px;
+            f2 z[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) z[c] = (EXACT || c < p.C) ? ldg_stream2(base + (long long)c * p.HW) : f2(-1.0e30f);
+            const f2 sl = ldg_stream2(base + (long long)p.C * p.HW) * p.inv_temp;
+            // softplus (ATen: x > 20 ? x : log1p(exp(x)))
+            const f2 scale(sl.v.x > 20.f ? sl.v.x : log1pf(expf(sl.v.x)), sl.v.y > 20.f ? sl.v.y : log1pf(expf(sl.v.y)));
+            f2 m = z[0];
+#pragma unroll
+            for (int c = 1; c < CP; ++c) m = max2(m, z[c]);
+            f2 S(0.f);
+            const f2 m2 = m * 1.4426950408889634f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) { z[c] = ex2_2(fma2(z[c], 1.4426950408889634f, -m2)); S += z[c]; }
+            const f2 invS = rcp_rn2(S);
+            float best0 = -1.f, best1 = -1.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const f2 pc = z[c] * invS;
+                if (EXACT || c < p.C) {                                                   // tester.py:493-495
+                    if (pc.v.x > best0) { best0 = pc.v.x; pred0 = c; }
+                    if (pc.v.y > best1) { best1 = pc.v.y; pred1 = c; }
+                }
+                a[c] = alpha_from_probs2(scale, pc, p.eps);                             // probability_helper.py:104
+            }
+        } else {
+            const float* base = p.alpha_in + ((long long)b * p.C) * p.HW + px;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) a[c] = (EXACT || c < p.C) ? ldg_stream2(base + (long long)c * p.HW) : f2(0.f);
+        }
+        // sums and arg max over alpha
+        f2 asum(0.f);
+        float amax0 = 0.f, amax1 = 0.f;
+        int aarg0 = 0, aarg1 = 0;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (EXACT || c < p.C) {
+                asum += a[c];
+                const float u = a[c].v.x, w = a[c].v.y;
+                const bool g0 = (c == 0) | (u > amax0) | ((u != u) & (amax0 == amax0));   // torch.argmax: first maximum, NaN maximal
+                const bool g1 = (c == 0) | (w > amax1) | ((w != w) & (amax1 == amax1));
+                amax0 = g0 ? u : amax0; aarg0 = g0 ? c : aarg0;
+                amax1 = g1 ? w : amax1; aarg1 = g1 ? c : aarg1;
+            }
+        }
+        if (p.alpha_out && live) {
+            float* ao = p.alpha_out + ((long long)b * p.C) * p.HW + px;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) st2(ao + (long long)c * p.HW, a[c]);
+        }
+        if (!p.outputs) { pred0 = aarg0; pred1 = aarg1; }
+        const f2 a0 = asum + p.eps;                        // probability_helper.py:119,127
+        const f2 a0m = asum + p.eps_m;                     // auroc.py:57
+        const bool want_unc = p.h || p.au || p.eu || MI;
+        f2 H(0.f), AU(0.f), Hm(0.f), EHm(0.f);
+        if (want_unc) {                                    // warp-uniform
+            const f2 x0 = a0 + 1.0f;
+            const PsiG2 q0 = psi_g2(x0);
+            const bool same0 = a0m.v.x == a0.v.x && a0m.v.y == a0.v.y;     // alpha >= 1: both eps vanish in fp32
+            PsiG2 q0m = q0;
+            if (MI && !same0) q0m = psi_g2(a0m + 1.0f);
+            const f2 inv0 = rcp_rn2(a0), inv0m = (MI && !same0) ? rcp_rn2(a0m) : inv0;
+            f2 H2(0.f), Hm2(0.f);                          // entropies in log2 units
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (EXACT || c < p.C) {
+                    const f2 ph = a[c] * inv0;
+                    const f2 xc = a[c] + 1.0f;
+                    const PsiG2 q = psi_g2(xc);
+                    const f2 d = psi_diff2(xc, q, q0);
+                    H2 = fma2(-ph, lg2_2(ph + p.eps), H2);                    // :121
+                    AU = fma2(-ph, d, AU);                                    // :128-130
+                    if (MI) {
+                        const f2 pm = a[c] * inv0m;
+                        const f2 pmc = max2(pm, p.eps_m);
+                        Hm2 = fma2(-pmc, lg2_2(pmc), Hm2);                    // auroc.py:59
+                        EHm = fma2(-pm, same0 ? d : psi_diff2(xc, q, q0m), EHm);   // auroc.py:60-61
+                    }
+                }
+            }
+            H = H2 * 0.6931471805599453f;
+            Hm = Hm2 * 0.6931471805599453f;
+        }
+        const float conf0 = __fdiv_rn(amax0, asum.v.x + p.eps_m), conf1 = __fdiv_rn(amax1, asum.v.y + p.eps_m);   // ece.py:57-58,75
+        if (live) {
+            if (p.pred) *reinterpret_cast<longlong2*>(p.pred + g) = make_longlong2(pred0, pred1);
+            if (p.conf) st2(p.conf + g, f2(conf0, conf1));
+            if (p.h) st2(p.h + g, f2(__fdiv_rn(H.v.x, p.logC), __fdiv_rn(H.v.y, p.logC)));
+            if (p.au) st2(p.au + g, AU);
+            if (p.eu) st2(p.eu + g, H - AU);
+            if (MI) { const f2 d = Hm - EHm; st2(p.mi + g, f2(__fdiv_rn(d.v.x, p.logC), __fdiv_rn(d.v.y, p.logC))); }
+        }
+        if (p.labels && live) {     // confusion: tester's argmax of the shape softmax; ECE: argmax of alpha/alpha0 (ece.py:75,84)
+            const longlong2 lb = *reinterpret_cast<const longlong2*>(p.labels + g);
+            atomic_hist_add(hs, p.C, p.n_bins, p.confmat != nullptr, p.bins != nullptr, p.bins_one_step != 0, lb.x, pred0, aarg0,
+                            conf0, p.has_ignore != 0, p.ignore);
+            atomic_hist_add(hs, p.C, p.n_bins, p.confmat != nullptr, p.bins != nullptr, p.bins_one_step != 0, lb.y, pred1, aarg1,
+                            conf1, p.has_ignore != 0, p.ignore);
+        }
+    }
+    __syncthreads();
+    atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV2_THREADS);
+}
+
 template <int CP>
 static int launch_ev(const EvParams& p, cudaStream_t st) {
     const int sms = sm_count_current_device();
@@ -191,6 +335,22 @@ static int launch_ev(const EvParams& p, cudaStream_t st) {
     const long long cap = 5LL * sms;                       // 48 registers: five resident CTAs of 256 threads
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
     const bool exact = p.C == CP, mi = p.mi != nullptr;
+    const uintptr_t al8 = reinterpret_cast<uintptr_t>(p.outputs) | reinterpret_cast<uintptr_t>(p.alpha_in) |
+                          reinterpret_cast<uintptr_t>(p.alpha_out) | reinterpret_cast<uintptr_t>(p.conf) |
+                          reinterpret_cast<uintptr_t>(p.h) | reinterpret_cast<uintptr_t>(p.au) |
+                          reinterpret_cast<uintptr_t>(p.eu) | reinterpret_cast<uintptr_t>(p.mi);
+    const uintptr_t al16 = reinterpret_cast<uintptr_t>(p.labels) | reinterpret_cast<uintptr_t>(p.pred);
+    if (!g_ev_no_packed && (p.HW & 1) == 0 && (al8 & 7) == 0 && (al16 & 15) == 0) {
+        const long long chunks2 = ((p.n_px >> 1) + EV2_THREADS - 1) / EV2_THREADS;
+        const long long cap2 = (long long)SLU_EV2_MINB * sms;
+        const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
+        if (exact && mi) evidential_x2_kernel<CP, true, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+        else if (exact) evidential_x2_kernel<CP, true, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+        else if (mi) evidential_x2_kernel<CP, false, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+        else evidential_x2_kernel<CP, false, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("evidential_x2_kernel");
+        return 0;
+    }
     if (exact && mi) evidential_kernel<CP, true, true><<<grid, EV_THREADS, 0, st>>>(p);
     else if (exact) evidential_kernel<CP, true, false><<<grid, EV_THREADS, 0, st>>>(p);
     else if (mi) evidential_kernel<CP, false, true><<<grid, EV_THREADS, 0, st>>>(p);
@@ -244,4 +404,11 @@ extern "C" int slu_evidential_reduce(const float* d_outputs, const float* d_alph
         case 28: return launch_ev<28>(p, st);
         default: return launch_ev<32>(p, st);
     }
+}
+
+/* A/B switch (tests, profiles): 1 = slu_evidential_reduce always runs one pixel per thread (no packed f32x2 variant). */
+extern "C" int slu_debug_no_packed_evidential(int on) {
+    const int prev = slu::g_ev_no_packed;
+    if (on >= 0) slu::g_ev_no_packed = on ? 1 : 0;
+    return prev;
 }

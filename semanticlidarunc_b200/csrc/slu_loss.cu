@@ -21,6 +21,7 @@
 #include <math.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
+#include "slu_packed.cuh"
 
 namespace slu {
 
@@ -163,12 +164,154 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) dirichlet_loss_kernel
     }
 }
 
+// ---- packed variant of dirichlet_loss_kernel: two adjacent pixels per thread (slu_packed.cuh) -------------------------
+constexpr int DL2_THREADS = 128;
+#ifndef SLU_DL2_MINB
+#define SLU_DL2_MINB 4
+#endif
+static int g_no_packed = 0;        // A/B switch (slu_debug_no_packed_loss): 1 = always run the one-pixel-per-thread kernels
+
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(DL2_THREADS, SLU_DL2_MINB) dirichlet_loss_x2_kernel(const __grid_constant__ LossParams p) {
+    const int tid = threadIdx.x;
+    double acc_mse = 0.0, acc_kl = 0.0;
+    unsigned n_valid = 0;
+    const long long pairs = p.n_px >> 1;
+    const long long chunks = (pairs + DL2_THREADS - 1) / DL2_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long pi = ch * DL2_THREADS + tid;
+        if (pi >= pairs) continue;
+        const long long g = pi << 1;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const longlong2 tg = *reinterpret_cast<const longlong2*>(p.target + g);
+        bool v0, v1;
+        if (p.keep) {
+            v0 = p.keep[g] != 0; v1 = p.keep[g + 1] != 0;
+        } else {
+            v0 = true; v1 = true;
+#pragma unroll
+            for (int i = 0; i < MAX_IGNORE; ++i)
+                if (i < p.n_ignore) { if (tg.x == p.ignore[i]) v0 = false; if (tg.y == p.ignore[i]) v1 = false; }
+        }
+        const float* base = p.alpha + ((long long)b * p.C) * p.HW + px;
+        float* gm = p.grad_mse ? p.grad_mse + ((long long)b * p.C) * p.HW + px : nullptr;
+        float* gk = p.grad_kl ? p.grad_kl + ((long long)b * p.C) * p.HW + px : nullptr;
+        if (!v0 && !v1) {
+            for (int c = 0; c < p.C; ++c) {
+                if (gm) st2(gm + (long long)c * p.HW, f2(0.f));
+                if (gk) st2(gk + (long long)c * p.HW, f2(0.f));
+            }
+            continue;
+        }
+        n_valid += (v0 ? 1u : 0u) + (v1 ? 1u : 0u);
+        f2 a[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) a[c] = (EXACT || c < p.C) ? ldg_stream2(base + (long long)c * p.HW) : f2(0.f);
+        const int y0 = (int)tg.x, y1 = (int)tg.y;
+        if (p.want_mse) {
+            f2 a0(0.f), s2(0.f), ay(0.f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                a0 += a[c];
+                s2 = fma2(a[c], a[c], s2);
+                ay = f2(c == y0 ? a[c].v.x : ay.v.x, c == y1 ? a[c].v.y : ay.v.y);
+            }
+            const f2 D = a0 + p.eps_mse, invD(1.0f / D.v.x, 1.0f / D.v.y);
+            const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG(1.0f / G.v.x, 1.0f / G.v.y);
+            f2 sq(0.f), sp2(0.f), var(0.f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (EXACT || c < p.C) {
+                    const f2 pc = a[c] * invD;
+                    const f2 d = f2(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f) - pc;
+                    sq = fma2(d, d, sq);
+                    sp2 = fma2(pc, pc, sp2);
+                    var = fma2(a[c] * (a0 - a[c]), invG, var);
+                }
+            }
+            const f2 mse = sq + var;
+            if (v0) acc_mse += (double)mse.v.x;
+            if (v1) acc_mse += (double)mse.v.y;
+            if (gm) {
+                const f2 N = fma2(a0, a0, -s2);
+                const f2 Gp = fma2(a0 * 2.0f, a0 + 1.0f, fma2(a0, a0, p.eps_mse));
+                const f2 common = fma2((fma2(ay, invD, -sp2)) * 2.0f, invD, fma2(a0 * 2.0f, invG, -(N * Gp * invG * invG)));
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) {
+                        const f2 pc = a[c] * invD;
+                        const f2 yc(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f);
+                        const f2 o = fma2((yc - pc) * -2.0f, invD, fma2(a[c] * -2.0f, invG, common));
+                        st2(gm + (long long)c * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
+                    }
+                }
+            }
+        }
+        if (p.want_kl) {
+            f2 s(0.f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) s += max2(f2(c == y0 ? 1.0f : a[c].v.x, c == y1 ? 1.0f : a[c].v.y), p.eps_kl);
+            const LDT2 fs = ldt_pos2<false>(s);
+            f2 kl = fs.lg;
+            const f2 tail = (s - (float)p.C) * fs.tri;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (EXACT || c < p.C) {
+                    const bool t0 = c == y0, t1 = c == y1;
+                    const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+                    const LDT2 f = ldt_pos2<false>(ac);
+                    kl = kl - f.lg;
+                    kl = fma2(ac - 1.0f, f.psi - fs.psi, kl);
+                    if (gk) {
+                        const f2 gj = fma2(ac - 1.0f, f.tri, -tail);
+                        st2(gk + (long long)c * p.HW, f2((v0 && !t0 && a[c].v.x > p.eps_kl) ? gj.v.x : 0.f,
+                                                         (v1 && !t1 && a[c].v.y > p.eps_kl) ? gj.v.y : 0.f));
+                    }
+                }
+            }
+            if (v0) acc_kl += (double)kl.v.x;
+            if (v1) acc_kl += (double)kl.v.y;
+        }
+    }
+    __shared__ double s_m[DL2_THREADS / 32], s_k[DL2_THREADS / 32];
+    __shared__ unsigned s_n[DL2_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
+        acc_kl += __shfl_xor_sync(0xffffffffu, acc_kl, o);
+        n_valid += __shfl_xor_sync(0xffffffffu, n_valid, o);
+    }
+    if ((tid & 31) == 0) { s_m[tid >> 5] = acc_mse; s_k[tid >> 5] = acc_kl; s_n[tid >> 5] = n_valid; }
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0, k = 0.0, n = 0.0;
+        for (int i = 0; i < DL2_THREADS / 32; ++i) { m += s_m[i]; k += s_k[i]; n += (double)s_n[i]; }
+        if (p.want_mse) atomicAdd(&p.sums[0], m);
+        if (p.want_kl) atomicAdd(&p.sums[1], k);
+        atomicAdd(&p.sums[2], n);
+    }
+}
+
 template <int CP>
 static int launch_loss(const LossParams& p, cudaStream_t st) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
     const long long cap = 6LL * sms;
+    const bool packed = !g_no_packed && (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.alpha) | reinterpret_cast<uintptr_t>(p.grad_mse) |
+                          reinterpret_cast<uintptr_t>(p.grad_kl)) & 7) == 0;
+    if (packed) {
+        const long long chunks2 = ((p.n_px >> 1) + DL2_THREADS - 1) / DL2_THREADS;
+        const long long cap2 = (long long)SLU_DL2_MINB * sms;
+        const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
+        if (p.C == CP) dirichlet_loss_x2_kernel<CP, true><<<grid2, DL2_THREADS, 0, st>>>(p);
+        else dirichlet_loss_x2_kernel<CP, false><<<grid2, DL2_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("dirichlet_loss_x2_kernel");
+        return 0;
+    }
     if (p.C == CP) dirichlet_loss_kernel<CP, true><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
     else dirichlet_loss_kernel<CP, false><<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("dirichlet_loss_kernel");
@@ -197,7 +340,31 @@ struct FusedParams {
     float inv_temp, eps_alpha, eps_mse, eps_kl, w_mse, w_kl;
     double* sums;                  // [3] sum mse | sum kl | n_valid   (n_valid written by the count kernel)
     float* grad;                   // [B,C+1,HW] or NULL
+    // step mode (slu_evidential_loss_step): the last CTA turns the sums into the final loss values and cleans up
+    const double* count;           // [1] number of valid pixels the mean runs over (NULL: sums[2])
+    float* loss4;                  // [4] total | mse | kl | n_valid, or NULL
+    unsigned long long* ticket;    // CTA arrival counter inside the caller's state block, left at 0
+    double* own_count;             // when the call owns the count buffer: reset to 0 by the last CTA
 };
+
+// Last CTA to arrive: loss values from the finished sums, then the state block is zeroed again, so the same buffers
+// serve the next step (and every replay of a captured graph) without a memset.
+__device__ __forceinline__ void fused_step_epilogue(const FusedParams& p, double n_valid) {
+    __threadfence();
+    const unsigned long long t = atomicAdd(p.ticket, 1ull);
+    if (t != (unsigned long long)gridDim.x - 1ull) return;
+    __threadfence();
+    const double m = atomicAdd(&p.sums[0], 0.0), k = atomicAdd(&p.sums[1], 0.0);
+    const double n = fmax(n_valid, 1.0);
+    const double mse = m / n, kl = k / n;
+    p.loss4[0] = (float)((double)p.w_mse * mse + (double)p.w_kl * kl);
+    p.loss4[1] = (float)mse;
+    p.loss4[2] = (float)kl;
+    p.loss4[3] = (float)n_valid;
+    p.sums[0] = 0.0; p.sums[1] = 0.0;
+    *p.ticket = 0ull;
+    if (p.own_count) *p.own_count = 0.0;
+}
 
 __device__ __forceinline__ bool px_valid(const FusedParams& p, long long g, long long tgt) {
     if (p.keep) return p.keep[g] != 0;
@@ -226,7 +393,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) count_valid_kernel(const __grid_
 template <int CP, bool EXACT>
 __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) evidential_loss_fused_kernel(const __grid_constant__ FusedParams p) {
     const int tid = threadIdx.x;
-    const float inv_n = (float)(1.0 / fmax(p.sums[2], 1.0));
+    const double n_valid = p.count ? *p.count : p.sums[2];
+    const float inv_n = (float)(1.0 / fmax(n_valid, 1.0));
     double acc_mse = 0.0, acc_kl = 0.0;
     const long long chunks = (p.n_px + LOSS_THREADS - 1) / LOSS_THREADS;
     for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
@@ -329,6 +497,140 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) evidential_loss_fused
         for (int i = 0; i < LOSS_THREADS / 32; ++i) { mm += s_m[i]; kk += s_k[i]; }
         atomicAdd(&p.sums[0], mm);
         atomicAdd(&p.sums[1], kk);
+        if (p.loss4) fused_step_epilogue(p, n_valid);
+    }
+}
+
+// ---- packed variant: a thread owns TWO adjacent pixels (slu_packed.cuh) -------------------------------------------------
+// Same algebra as evidential_loss_fused_kernel, every per-class operation issued once for both pixels (FFMA2 / FMUL2 /
+// FADD2); MUFU evaluations, the one-hot compares and the validity selects stay per pixel.  Needs HW even and 16-byte
+// aligned target / 8-byte aligned outputs and gradient (the dispatcher checks; otherwise the scalar kernel runs).
+constexpr int LOSS2_THREADS = 128;
+#ifndef SLU_LOSS2_MINB
+#define SLU_LOSS2_MINB 4
+#endif
+
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss_fused_x2_kernel(const __grid_constant__ FusedParams p) {
+    const int tid = threadIdx.x;
+    const double n_valid = p.count ? *p.count : p.sums[2];
+    const float inv_n = (float)(1.0 / fmax(n_valid, 1.0));
+    double acc_mse = 0.0, acc_kl = 0.0;
+    const long long pairs = p.n_px >> 1;                       // HW is even: a pair never straddles two scans
+    const long long chunks = (pairs + LOSS2_THREADS - 1) / LOSS2_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long pi = ch * LOSS2_THREADS + tid;
+        if (pi >= pairs) continue;
+        const long long g = pi << 1;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const longlong2 tg = *reinterpret_cast<const longlong2*>(p.target + g);
+        const bool v0 = px_valid(p, g, tg.x), v1 = px_valid(p, g + 1, tg.y);
+        const float* base = p.outputs + ((long long)b * (p.C + 1)) * p.HW + px;
+        float* go = p.grad ? p.grad + ((long long)b * (p.C + 1)) * p.HW + px : nullptr;
+        if (!v0 && !v1) {
+            if (go) for (int c = 0; c <= p.C; ++c) st2(go + (long long)c * p.HW, f2(0.f));
+            continue;
+        }
+        const int y0 = (int)tg.x, y1 = (int)tg.y;
+        f2 pr[CP], a[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) pr[c] = (EXACT || c < p.C) ? ldg_stream2(base + (long long)c * p.HW) : f2(-1.0e30f);
+        const f2 sl = ldg_stream2(base + (long long)p.C * p.HW) * p.inv_temp;
+        f2 scale, dscale;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            scale[h] = sl[h] > 20.f ? sl[h] : log1pf(expf(sl[h]));
+            dscale[h] = sl[h] > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl[h]));       // d softplus
+        }
+        f2 m = pr[0];
+#pragma unroll
+        for (int c = 1; c < CP; ++c) m = max2(m, pr[c]);
+        const f2 m2 = m * 1.4426950408889634f;
+        f2 S(0.f);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) { pr[c] = ex2_2(fma2(pr[c], 1.4426950408889634f, -m2)); S += pr[c]; }
+        const f2 invS = rcp_rn2(S);
+        f2 a0(0.f), s2(0.f), ay(0.f), s(0.f);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            pr[c] = pr[c] * invS;
+            a[c] = (EXACT || c < p.C) ? alpha_from_probs2(scale, pr[c], p.eps_alpha) : f2(0.f);
+            a0 += a[c];
+            s2 = fma2(a[c], a[c], s2);
+            const bool t0 = c == y0, t1 = c == y1;
+            ay = f2(t0 ? a[c].v.x : ay.v.x, t1 ? a[c].v.y : ay.v.y);
+            if (EXACT || c < p.C) s += max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+        }
+        // ---- MSE term
+        const f2 D = a0 + p.eps_mse, invD(1.0f / D.v.x, 1.0f / D.v.y);
+        const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG(1.0f / G.v.x, 1.0f / G.v.y);
+        f2 sq(0.f), sp2(0.f), var(0.f);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (EXACT || c < p.C) {
+                const f2 pc = a[c] * invD;
+                const f2 d = f2(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f) - pc;
+                sq = fma2(d, d, sq);
+                sp2 = fma2(pc, pc, sp2);
+                var = fma2(a[c] * (a0 - a[c]), invG, var);
+            }
+        }
+        const f2 mse = sq + var;
+        const f2 N = fma2(a0, a0, -s2);
+        const f2 Gp = fma2(a0 * 2.0f, a0 + 1.0f, fma2(a0, a0, p.eps_mse));
+        const f2 common = fma2((fma2(ay, invD, -sp2)) * 2.0f, invD, fma2(a0 * 2.0f, invG, -(N * Gp * invG * invG)));
+        // ---- KL term
+        const LDT2 fs = ldt_pos2<true>(s);
+        f2 kl = fs.lg;
+        const f2 tail = (s - (float)p.C) * fs.tri;
+        f2 gp_sum(0.f);
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (EXACT || c < p.C) {
+                const bool t0 = c == y0, t1 = c == y1;
+                const f2 pc = a[c] * invD;
+                const f2 yc(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f);
+                f2 gc = fma2((yc - pc) * -2.0f, invD, fma2(a[c] * -2.0f, invG, common)) * p.w_mse;
+                const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+                const LDT2 f = ldt_pos2<true>(ac);
+                kl = kl - f.lg;
+                kl = fma2(ac - 1.0f, f.psi - fs.psi, kl);
+                const f2 gkl = fma2(fma2(ac - 1.0f, f.tri, -tail), p.w_kl, gc);
+                gc = f2((!t0 && a[c].v.x > p.eps_kl) ? gkl.v.x : gc.v.x, (!t1 && a[c].v.y > p.eps_kl) ? gkl.v.y : gc.v.y);
+                a[c] = gc * inv_n;               // a[] now holds d(loss)/d(alpha_c)
+                gp_sum = fma2(a[c], pr[c], gp_sum);
+            }
+        }
+        if (v0) { acc_mse += (double)mse.v.x; acc_kl += (double)kl.v.x; }
+        if (v1) { acc_mse += (double)mse.v.y; acc_kl += (double)kl.v.y; }
+        if (go) {
+            const f2 keep(v0 ? 1.0f : 0.0f, v1 ? 1.0f : 0.0f);
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) {
+                    const f2 o = scale * pr[c] * (a[c] - gp_sum);
+                    st2(go + (long long)c * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
+                }
+            const f2 o = gp_sum * dscale * p.inv_temp;
+            st2(go + (long long)p.C * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
+            (void)keep;
+        }
+    }
+    __shared__ double s_m[LOSS2_THREADS / 32], s_k[LOSS2_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
+        acc_kl += __shfl_xor_sync(0xffffffffu, acc_kl, o);
+    }
+    if ((tid & 31) == 0) { s_m[tid >> 5] = acc_mse; s_k[tid >> 5] = acc_kl; }
+    __syncthreads();
+    if (tid == 0) {
+        double mm = 0.0, kk = 0.0;
+        for (int i = 0; i < LOSS2_THREADS / 32; ++i) { mm += s_m[i]; kk += s_k[i]; }
+        atomicAdd(&p.sums[0], mm);
+        atomicAdd(&p.sums[1], kk);
+        if (p.loss4) fused_step_epilogue(p, n_valid);
     }
 }
 
@@ -340,8 +642,19 @@ static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) 
     const long long cap = 6LL * sms;
     const unsigned grid = (unsigned)(chunks < cap ? chunks : cap);
     if (!precounted) {
-        count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p, p.sums + 2);
+        count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p, p.count ? const_cast<double*>(p.count) : p.sums + 2);
         SLU_LAUNCH_CHECK("count_valid_kernel");
+    }
+    const bool packed = !g_no_packed && (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.outputs) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.grad) & 7) == 0;
+    if (packed) {
+        const long long chunks2 = ((p.n_px >> 1) + LOSS2_THREADS - 1) / LOSS2_THREADS;
+        const long long cap2 = (long long)SLU_LOSS2_MINB * sms;
+        const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
+        if (p.C == CP) evidential_loss_fused_x2_kernel<CP, true><<<grid2, LOSS2_THREADS, 0, st>>>(p);
+        else evidential_loss_fused_x2_kernel<CP, false><<<grid2, LOSS2_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("evidential_loss_fused_x2_kernel");
+        return 0;
     }
     if (p.C == CP) evidential_loss_fused_kernel<CP, true><<<grid, LOSS_THREADS, 0, st>>>(p);
     else evidential_loss_fused_kernel<CP, false><<<grid, LOSS_THREADS, 0, st>>>(p);
@@ -605,4 +918,48 @@ extern "C" int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_ma
     count_valid_kernel<<<(unsigned)(chunks < cap ? chunks : cap), LOSS_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, d_count);
     SLU_LAUNCH_CHECK("count_valid_kernel");
     return 0;
+}
+
+/* The training-step form of slu_evidential_loss_fused: final loss values written by the kernel, self-cleaning state. */
+extern "C" int slu_evidential_loss_step(const float* d_outputs, const int64_t* d_target, const uint8_t* d_keep_mask,
+                                        int B, int C, int64_t HW, const int64_t* h_ignore, int n_ignore,
+                                        float temperature, float eps_alpha, float eps_mse, float eps_kl,
+                                        float w_mse, float w_kl, int precounted, double* d_count, double* d_state,
+                                        float* d_loss4, float* d_grad_outputs, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_outputs || !d_target || !d_count || !d_state || !d_loss4) return fail(SLU_E_ARG, "d_outputs / d_target / d_count / d_state / d_loss4 is NULL");
+    if (B < 1 || HW < 1) return fail(SLU_E_ARG, "B=%d HW=%lld must be >= 1", B, (long long)HW);
+    if (C < 3 || C > SLU_MAX_CLASSES) return fail(SLU_E_RANGE, "C=%d outside [3,%d]", C, SLU_MAX_CLASSES);
+    if (n_ignore < 0 || n_ignore > MAX_IGNORE || (n_ignore > 0 && !h_ignore)) return fail(SLU_E_RANGE, "n_ignore=%d outside [0,%d]", n_ignore, MAX_IGNORE);
+    if (!(temperature > 0.f)) return fail(SLU_E_ARG, "temperature must be > 0");
+    if ((reinterpret_cast<uintptr_t>(d_state) & 7) != 0) return fail(SLU_E_ALIGN, "d_state not 8-byte aligned");
+    FusedParams p{};
+    p.outputs = d_outputs; p.target = reinterpret_cast<const long long*>(d_target); p.keep = d_keep_mask;
+    p.B = B; p.C = C; p.HW = HW; p.n_px = (long long)B * HW;
+    for (int i = 0; i < n_ignore; ++i) p.ignore[i] = h_ignore[i];
+    p.n_ignore = n_ignore;
+    p.inv_temp = 1.0f / temperature; p.eps_alpha = eps_alpha; p.eps_mse = eps_mse; p.eps_kl = eps_kl;
+    p.w_mse = w_mse; p.w_kl = w_kl;
+    p.sums = d_state; p.grad = d_grad_outputs;
+    p.count = d_count; p.loss4 = d_loss4;
+    p.ticket = reinterpret_cast<unsigned long long*>(d_state + 2);
+    p.own_count = precounted ? nullptr : d_count;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch ((C + 3) / 4 * 4) {
+        case 4: return launch_fused<4>(p, precounted != 0, st);
+        case 8: return launch_fused<8>(p, precounted != 0, st);
+        case 12: return launch_fused<12>(p, precounted != 0, st);
+        case 16: return launch_fused<16>(p, precounted != 0, st);
+        case 20: return launch_fused<20>(p, precounted != 0, st);
+        case 24: return launch_fused<24>(p, precounted != 0, st);
+        case 28: return launch_fused<28>(p, precounted != 0, st);
+        default: return launch_fused<32>(p, precounted != 0, st);
+    }
+}
+
+/* A/B switch (tests, profiles): 1 = the loss kernels always run one pixel per thread (no packed f32x2 variant). */
+extern "C" int slu_debug_no_packed_loss(int on) {
+    const int prev = slu::g_no_packed;
+    if (on >= 0) slu::g_no_packed = on ? 1 : 0;
+    return prev;
 }

@@ -39,10 +39,53 @@ def build_normal_xyz(xyz, norm_factor=0.25, ksize=3):
     return n.cpu().numpy() if is_np else n
 
 
+_WS = {}          # device -> projection workspace, reused across calls (the drop-in is called once per scan)
+_PIN = {}         # (H, W, Cin) -> pinned host image buffer + pinned meta buffer
+
+
 def project_device(pc: torch.Tensor, height=64, width=2048, theta_range=None, sort_largest_first=False):
     """pc [N,Cin] CUDA tensor -> dict(img [H,W,Cin] f32, pix [N] i32, winner [H,W] i32, theta [1,2] f64, diag)."""
-    return ops.project_points(pc.to(torch.float64), height, width, theta_range=theta_range,
-                              farthest_wins=sort_largest_first)
+    dev = pc.device
+    res = ops.project_points(pc.to(torch.float64), height, width, theta_range=theta_range,
+                             farthest_wins=sort_largest_first, workspace=_WS.get(dev))
+    _WS[dev] = res["workspace"]
+    return res
+
+
+def _host_bins(pc64: np.ndarray, height: int, width: int, theta_range):
+    """Per-point pixel index in numpy, the reference's own arithmetic (src/dataset/utils.py:313-339: arctan2, linspace,
+    digitize - 1 with the negative index wrapping round).  Only used to settle points the device flags as sitting within
+    a few ulps of a bin edge."""
+    x, y, z = pc64[:, 0], pc64[:, 1], pc64[:, 2]
+    phi = np.arctan2(y, x)
+    theta = -np.arctan2(np.sqrt(x ** 2 + y ** 2), z) + np.pi / 2
+    tmin, tmax = (theta.min(), theta.max()) if theta_range is None else theta_range
+    row = (np.digitize(theta, np.linspace(tmin, tmax, height)[::-1]) - 1) % height
+    col = (np.digitize(phi, np.linspace(-np.pi, np.pi, width)[::-1]) - 1) % width
+    return row * width + col
+
+
+def _settle_edge_points(pc64: np.ndarray, img: np.ndarray, pix: np.ndarray, height, width, theta_range, farthest_wins):
+    """Bit-exactness by construction: CUDA's and numpy's atan2 are both good to ~2 ulp, so a point within 4 ulp of a bin
+    edge (the kernel counts them; ~1e-14 of all points) could land on either side.  When a scan has such points, every
+    point's bin is recomputed with numpy and the pixels whose membership changed are re-resolved on the host.
+    Returns the number of points that changed pixel."""
+    host = _host_bins(pc64, height, width, theta_range)
+    changed = np.nonzero(host != pix)[0]
+    if changed.size == 0:
+        return 0
+    r = np.sqrt(pc64[:, 0] ** 2 + pc64[:, 1] ** 2 + pc64[:, 2] ** 2)
+    flat = img.reshape(height * width, -1)
+    for q in np.unique(np.concatenate([host[changed], pix[changed].astype(np.int64)])):
+        members = np.nonzero(host == q)[0]
+        if members.size == 0:
+            flat[q] = 0.0
+        else:
+            rr = r[members]
+            best = members[rr == (rr.max() if farthest_wins else rr.min())].min()     # lowest index among exact ties
+            flat[q] = pc64[best].astype(np.float32)
+    pix[changed] = host[changed]
+    return int(changed.size)
 
 
 def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, sort_largest_first=False,
@@ -53,16 +96,33 @@ def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, so
     (np.concatenate of float32 xyzi with int64 labels); this path always computes in float64.
     `th` and `max_range` are dead parameters in the reference and are ignored here too.
     `bins_h` (caller-supplied row edges) is not supported on the device path.
-    `alpha` [H,W] float64 depends only on the bin edges; pass return_alpha=False to skip building it
-    (every reference caller discards it).
-    """
+    `alpha` [H,W] float64 depends only on the bin edges and every reference caller discards it: pass
+    return_alpha=False to skip building it (None is returned in its place).
+    One H2D copy of the cloud, one D2H copy of the image into a reused pinned buffer, one synchronisation.  Points the
+    kernel flags as within 4 ulp of a bin edge are settled with numpy's own arithmetic (`_settle_edge_points`); the
+    count of the last call is left in `spherical_projection.last_near_edge` / `.last_settled`."""
     if bins_h is not None:
         raise NotImplementedError("caller-supplied bins_h is not supported by the CUDA projection")
     dev = _lib.require_cuda()
-    pc_t = torch.as_tensor(np.ascontiguousarray(pc, dtype=np.float64)).to(dev, non_blocking=True)
+    pc64 = np.ascontiguousarray(pc, dtype=np.float64)
+    pc_t = torch.from_numpy(pc64).to(dev, non_blocking=True)
     res = project_device(pc_t, height, width, theta_range, sort_largest_first)
-    pj_img = res["img"].cpu().numpy()
-    tmin, tmax = (float(v) for v in res["theta"][0].cpu())
+    key = (height, width, pc64.shape[1])
+    if key not in _PIN:
+        _PIN[key] = (torch.empty((height, width, pc64.shape[1]), dtype=torch.float32, pin_memory=True),
+                     torch.empty(4, dtype=torch.float64, pin_memory=True))
+    h_img, h_meta = _PIN[key]
+    h_img.copy_(res["img"], non_blocking=True)
+    meta = torch.cat([res["theta"].reshape(-1), res["diag"].reshape(-1).to(torch.float64)])
+    h_meta.copy_(meta, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    pj_img = h_img.numpy().copy()
+    tmin, tmax, _, near_edge = (float(v) for v in h_meta)
+    spherical_projection.last_near_edge, spherical_projection.last_settled = int(near_edge), 0
+    if near_edge > 0:
+        pix = res["pix"].cpu().numpy()
+        spherical_projection.last_settled = _settle_edge_points(pc64, pj_img, pix, height, width, theta_range,
+                                                                sort_largest_first)
     if theta_range is not None:
         tmin, tmax = theta_range
     alpha = None
@@ -71,3 +131,7 @@ def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, so
         bw = np.linspace(-np.pi, np.pi, width)[::-1]
         alpha = np.sqrt(np.square(bh)[:, None] + np.square(bw)[None, :])
     return pj_img, alpha, (tmin, tmax), (-np.pi, np.pi)
+
+
+spherical_projection.last_near_edge = 0
+spherical_projection.last_settled = 0

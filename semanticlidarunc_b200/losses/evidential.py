@@ -4,6 +4,20 @@ src/configs/SemanticKitti_default.yaml:50-62) as ONE forward+backward kernel pas
 
 Use this when the term weights are fixed; when GradNorm needs `autograd.grad` per term
 (src/utils/grad_norm.py:52) use the per-term modules in dirichlet_losses.py / regularizers.py.
+
+Three ways in, same kernel (slu_evidential_loss_step; the loss values are written by its last CTA, no host arithmetic):
+
+  crit(outputs, target)                       autograd: `loss.backward()` flows into the backbone (one extra pass for
+                                              autograd's upstream-gradient multiply)
+  crit.forward_backward(outputs, target)      no autograd node: returns (loss4, grad); feed the backbone with
+                                              `outputs.backward(grad)` -- the gradient is final, nothing re-reads it
+  crit.capture(outputs, target); crit.replay()  the same as ONE CUDA graph over static buffers (count kernel, the NCCL
+                                              all-reduce of the count when sharded, loss kernel)
+
+Batch-sharded training (BASELINE.json configs[4], `group=`): the only thing ranks exchange is the valid-pixel count.
+`prefetch_count(target)` launches the count kernel and its all-reduce on a SIDE stream as soon as the labels exist
+(they do not depend on the network), so the collective overlaps whatever the main stream does next (loader kernels,
+the backbone's forward) instead of sitting between the count and the loss kernel.
 """
 from __future__ import annotations
 
@@ -14,50 +28,50 @@ from .. import ops
 from ._mask import split_ignore
 
 
-def _count_reducer(group):
-    """all-reduce of the valid-pixel count over `group` (True = the default group), or None when not sharded"""
+def _group_of(group):
+    """(process group or None for the default group, world size); (None, 1) when not sharded"""
     import torch.distributed as dist
     if group is None or group is False or not (dist.is_available() and dist.is_initialized()):
-        return None
+        return None, 1
     g = None if group is True else group
-    if dist.get_world_size(g) == 1:
+    return g, dist.get_world_size(g)
+
+
+def _count_reducer(group):
+    """all-reduce of the valid-pixel count over `group` (True = the default group) as a callable, or None when not
+    sharded -- the one collective of the batch-sharded loss (also what ops.evidential_loss_fused(count_reduce=) takes)"""
+    import torch.distributed as dist
+    g, world = _group_of(group)
+    if world == 1:
         return None
     return lambda count: dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
 
 
 class _FusedEvidentialLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, outputs, target, w_mse, w_kl, ignore_index, temperature, eps, group):
-        ids, keep = split_ignore(ignore_index)
-        if len(ids) > 8:
-            keep = ~torch.isin(target, torch.as_tensor(ids, device=target.device, dtype=target.dtype))
-            ids = ()
-        r = ops.evidential_loss_fused(outputs.detach(), target, w_mse=w_mse, w_kl=w_kl, ignore=ids, keep_mask=keep,
-                                      temperature=temperature, eps_alpha=eps, eps_mse=eps, eps_kl=eps,
-                                      want_grad=ctx.needs_input_grad[0], count_reduce=_count_reducer(group))
-        n = r["sums"][2].clamp_min(1.0)
-        mse, kl = r["sums"][0] / n, r["sums"][1] / n
+    def forward(ctx, outputs, target, crit):
+        r = crit._step(outputs.detach(), target, want_grad=ctx.needs_input_grad[0])
         if ctx.needs_input_grad[0]:
             ctx.save_for_backward(r["grad"])
-        total = (w_mse * mse + w_kl * kl).to(outputs.dtype)
-        mse, kl = mse.to(outputs.dtype), kl.to(outputs.dtype)
+        l4 = r["loss4"]
+        total, mse, kl = l4[0].to(outputs.dtype), l4[1].to(outputs.dtype), l4[2].to(outputs.dtype)
         ctx.mark_non_differentiable(mse, kl)
         return total, mse, kl
 
     @staticmethod
     def backward(ctx, g_total, _g_mse, _g_kl):
         (grad,) = ctx.saved_tensors
-        return grad * g_total.to(grad.dtype), None, None, None, None, None, None, None
+        return grad * g_total.to(grad.dtype), None, None
 
 
 class EvidentialLoss(nn.Module):
     """forward(outputs [B,C+1,H,W], target [B,H,W] | [B,1,H,W]) -> (loss, mse.detach(), kl.detach()).
 
-    Batch-sharded training (BASELINE.json configs[4]): with `group=True` (or a process group) every rank passes its
-    shard of the batch; the valid-pixel counts are all-reduced (one float64 over NCCL) between the count kernel and the
-    loss kernel, so each rank's `loss`, `mse`, `kl` are its SHARE of the global masked mean (their sum over ranks is the
-    single-process value) and the gradient it writes is exactly the single-process gradient of its shard.  No other
-    collective is needed; summing the backbone's parameter gradients stays the DDP wrapper's job (use sum, not mean)."""
+    Batch-sharded training: with `group=True` (or a process group) every rank passes its shard of the batch; the
+    valid-pixel counts are all-reduced (one float64 over NCCL), so each rank's `loss`, `mse`, `kl` are its SHARE of the
+    global masked mean (their sum over ranks is the single-process value) and the gradient it writes is bit for bit the
+    single-process gradient of its shard.  No other collective is needed; summing the backbone's parameter gradients
+    stays the DDP wrapper's job (use sum, not mean)."""
 
     def __init__(self, w_mse: float = 1.0, w_kl: float = 0.05, ignore_index=None, temperature: float = 1.0, eps: float = 1e-8,
                  group=None):
@@ -65,9 +79,109 @@ class EvidentialLoss(nn.Module):
         self.w_mse, self.w_kl = float(w_mse), float(w_kl)
         self.ignore_index, self.temperature, self.eps = ignore_index, float(temperature), float(eps)
         self.group = group
+        self._bufs = {}              # per device: count float64[1], state float64[3]
+        self._side = {}              # per device: side stream of the count prefetch
+        self._prefetched = None      # (event, count buffer) of a pending prefetch_count()
+        self._graph = None
 
-    def forward(self, outputs: torch.Tensor, target: torch.Tensor):
+    # ---- plumbing ------------------------------------------------------------------------------------------------
+    def _buffers(self, dev):
+        if dev not in self._bufs:
+            self._bufs[dev] = (torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(3, dtype=torch.float64, device=dev))
+        return self._bufs[dev]
+
+    def _mask(self, target):
+        ids, keep = split_ignore(self.ignore_index)
+        if len(ids) > 8:
+            keep = ~torch.isin(target, torch.as_tensor(ids, device=target.device, dtype=target.dtype))
+            ids = ()
+        return ids, keep
+
+    @staticmethod
+    def _target3(target):
         if target.dim() == 4 and target.size(1) == 1:
             target = target[:, 0]
-        return _FusedEvidentialLoss.apply(outputs, target.long(), self.w_mse, self.w_kl, self.ignore_index,
-                                          self.temperature, self.eps, self.group)
+        return target if target.dtype == torch.int64 else target.long()
+
+    # ---- the sharded count, off the critical path ------------------------------------------------------------------
+    @torch.no_grad()
+    def prefetch_count(self, target: torch.Tensor):
+        """Count the valid pixels of `target` and all-reduce the count over the group on a side stream, now.  The next
+        forward / forward_backward on the same target waits for it with a stream event instead of running the count
+        and the collective in line.  No-op without a group."""
+        g, world = _group_of(self.group)
+        if world == 1:
+            return
+        import torch.distributed as dist
+        target = self._target3(target)
+        dev = target.device
+        count, _ = self._buffers(dev)
+        ids, keep = self._mask(target)
+        main = torch.cuda.current_stream(dev)
+        if dev not in self._side:
+            self._side[dev] = torch.cuda.Stream(device=dev)
+        side = self._side[dev]
+        side.wait_stream(main)                       # the labels are produced on the main stream
+        with torch.cuda.stream(side):
+            count.zero_()
+            ops.count_valid(target, count, ignore=ids, keep_mask=keep)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        target.record_stream(side)
+        self._prefetched = (ev, dev)
+
+    def _step(self, outputs, target, want_grad=True, loss4=None, grad=None):
+        target = self._target3(target)
+        dev = outputs.device
+        count, state = self._buffers(dev)
+        ids, keep = self._mask(target)
+        g, world = _group_of(self.group)
+        precounted = world > 1
+        if precounted:
+            if self._prefetched is not None and self._prefetched[1] == dev:
+                torch.cuda.current_stream(dev).wait_event(self._prefetched[0])
+                self._prefetched = None
+            else:                                    # in line: count kernel -> all-reduce -> loss kernel
+                import torch.distributed as dist
+                count.zero_()
+                ops.count_valid(target, count, ignore=ids, keep_mask=keep)
+                dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
+        return ops.evidential_loss_step(outputs, target, count, state, w_mse=self.w_mse, w_kl=self.w_kl, ignore=ids,
+                                        keep_mask=keep, temperature=self.temperature, eps_alpha=self.eps, eps_mse=self.eps,
+                                        eps_kl=self.eps, precounted=precounted, want_grad=want_grad, loss4=loss4, grad=grad)
+
+    # ---- the three entry points ----------------------------------------------------------------------------------
+    def forward(self, outputs: torch.Tensor, target: torch.Tensor):
+        return _FusedEvidentialLoss.apply(outputs, self._target3(target), self)
+
+    @torch.no_grad()
+    def forward_backward(self, outputs: torch.Tensor, target: torch.Tensor, loss4=None, grad=None):
+        """(loss4, grad) without an autograd node: loss4 float32[4] = loss | mse | kl | n_valid, grad = d(loss)/d(outputs)
+        (final: already divided by the global count).  Continue into the backbone with `outputs.backward(grad)`."""
+        r = self._step(outputs.detach(), target, want_grad=True, loss4=loss4, grad=grad)
+        return r["loss4"], r["grad"]
+
+    def capture(self, outputs: torch.Tensor, target: torch.Tensor):
+        """Record forward_backward for THESE tensors into a CUDA graph (count kernel, the count all-reduce when sharded,
+        loss kernel).  `outputs` / `target` become the graph's static inputs; returns the static (loss4, grad)."""
+        dev = outputs.device
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.forward_backward(outputs, target)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.forward_backward(outputs, target)
+            self._graph = (g, out)
+        return out
+
+    def replay(self):
+        if self._graph is None:
+            raise RuntimeError("capture() first")
+        self._graph[0].replay()
+        return self._graph[1]

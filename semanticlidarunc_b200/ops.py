@@ -305,6 +305,60 @@ def evidential_loss_fused(outputs: torch.Tensor, target: torch.Tensor, *, w_mse:
 
 
 @_lib.device_guard
+def evidential_loss_step(outputs: torch.Tensor, target: torch.Tensor, count: torch.Tensor, state: torch.Tensor, *,
+                         w_mse: float = 1.0, w_kl: float = 0.05, ignore=(), keep_mask: Optional[torch.Tensor] = None,
+                         temperature: float = 1.0, eps_alpha: float = 1e-8, eps_mse: float = 1e-8, eps_kl: float = 1e-8,
+                         precounted: bool = False, want_grad: bool = True, loss4: Optional[torch.Tensor] = None,
+                         grad: Optional[torch.Tensor] = None) -> dict:
+    """Training-step form of the fused loss (slu_evidential_loss_step): head output [B,C+1,H,W] -> loss4 float32[4]
+    (loss | mse | kl | n_valid, written by the kernel) and d(loss)/d(outputs).  `count` float64[1] and `state` float64[3]
+    are caller-owned, zero-initialised once; the kernel leaves them clean for the next step.  With precounted=True
+    `count` already holds the (global) number of valid pixels (`count_valid` + all-reduce)."""
+    _lib.require_cuda()
+    outputs = _lib.as_buffer(outputs, torch.float32, "outputs")
+    if outputs.dim() != 4:
+        raise ValueError("outputs must be [B,C+1,H,W]")
+    B, C1, H, W = outputs.shape
+    if target.dim() == 4 and target.size(1) == 1:
+        target = target[:, 0]
+    if tuple(target.shape) != (B, H, W):
+        raise ValueError(f"target shape {tuple(target.shape)} != {(B, H, W)}")
+    target = _lib.as_buffer(target, torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask, torch.bool, "keep_mask")
+    if count.dtype != torch.float64 or count.numel() != 1 or state.dtype != torch.float64 or state.numel() != 3:
+        raise ValueError("count must be float64[1] and state float64[3]")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    if loss4 is None:
+        loss4 = torch.empty(4, dtype=torch.float32, device=outputs.device)
+    if grad is None and want_grad:
+        grad = torch.empty_like(outputs)
+    rc = _lib.lib().slu_evidential_loss_step(_lib.ptr(outputs), _lib.ptr(target), _lib.ptr(keep_mask), B, C1 - 1, H * W,
+                                             h_ign, len(ign), float(temperature), float(eps_alpha), float(eps_mse),
+                                             float(eps_kl), float(w_mse), float(w_kl), int(bool(precounted)), _lib.ptr(count),
+                                             _lib.ptr(state), _lib.ptr(loss4), _lib.ptr(grad) if want_grad else None,
+                                             _lib.stream_ptr())
+    _lib.check(rc, "slu_evidential_loss_step")
+    return {"loss4": loss4, "grad": grad if want_grad else None}
+
+
+@_lib.device_guard
+def count_valid(target: torch.Tensor, count: torch.Tensor, *, ignore=(), keep_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ADD the number of valid pixels of `target` (ignore list / keep mask as in the losses) to count float64[1]
+    (slu_count_valid)."""
+    _lib.require_cuda()
+    target = _lib.as_buffer(target, torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask, torch.bool, "keep_mask")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    _lib.check(_lib.lib().slu_count_valid(_lib.ptr(target), _lib.ptr(keep_mask), target.numel(), h_ign, len(ign),
+                                          _lib.ptr(count), _lib.stream_ptr()), "slu_count_valid")
+    return count
+
+
+@_lib.device_guard
 def special_functions(x: torch.Tensor) -> torch.Tensor:
     """[n,3] = lgamma, digamma, trigamma of x > 0 as the loss kernels evaluate them (slu_diag_special)."""
     _lib.require_cuda()
@@ -446,8 +500,9 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
 
 @_lib.device_guard
 def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthest_wins: bool = False,
-                   want_img: bool = True) -> dict:
-    """Generic stage 1 (slu_project_points): pc [N,Cin] float64 CUDA -> img [H,W,Cin] float32."""
+                   want_img: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
+    """Generic stage 1 (slu_project_points): pc [N,Cin] float64 CUDA -> img [H,W,Cin] float32.
+    `workspace`: a uint8 CUDA tensor from an earlier call (returned under "workspace") is reused when large enough."""
     _lib.require_cuda()
     pc = _lib.as_buffer(pc, torch.float64, "pc")
     if pc.dim() != 2 or pc.size(1) < 3:
@@ -455,7 +510,8 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
     N, Cin = pc.shape
     dev = pc.device
     need = _lib.lib().slu_project_workspace_bytes(N, 1, H * W)
-    workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
+    if workspace is None or workspace.numel() < need or workspace.device != dev:
+        workspace = torch.empty(int(need), dtype=torch.uint8, device=dev)
     img = torch.empty((H, W, Cin), dtype=torch.float32, device=dev) if want_img else None
     pix = torch.empty((N,), dtype=torch.int32, device=dev)
     winner = torch.empty((H, W), dtype=torch.int32, device=dev)
@@ -467,7 +523,7 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
                                        _lib.ptr(workspace), _lib.ptr(img), _lib.ptr(pix), _lib.ptr(winner),
                                        _lib.ptr(theta), _lib.ptr(diag), _lib.stream_ptr())
     _lib.check(rc, "slu_project_points")
-    return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag}
+    return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
 
 
 @_lib.device_guard

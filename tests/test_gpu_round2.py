@@ -172,3 +172,119 @@ def test_accuracy_aggregator_accepts_long_ignore_lists(cuda):
     st = a.binned_accuracy(num_bins=10)
     n_ref, acc_ref = om.binned_accuracy(unc[keep].numpy(), (pred == lab)[keep].numpy(), 10)
     assert np.array_equal(st["n"].to_numpy(), n_ref)
+
+
+# ---------------------------------------------------------------------------------------------- packed (f32x2) kernels
+def _switch(name, on):
+    return getattr(_lib.lib(), name)(int(on))
+
+
+@pytest.mark.parametrize("C", [20, 7])
+@pytest.mark.parametrize("from_outputs", [True, False])
+def test_packed_evidential_kernel_agrees_with_one_pixel_kernel(cuda, C, from_outputs):
+    B, H, W = 3, 8, 130
+    x, lab = synth.synth_evidential_logits(3, B, C, H, W)
+    x, lab = x.to(cuda), lab.to(cuda)
+    if not from_outputs:
+        x = ops.evidential_reduce(x, from_outputs=True, want=("alpha",))["alpha"]
+    want = ("alpha", "pred", "conf", "H", "AU", "EU", "MI")
+    res = []
+    for off in (0, 1):
+        _switch("slu_debug_no_packed_evidential", off)
+        cm, bins = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+        n0 = _lib.launch_count()
+        r = ops.evidential_reduce(x, lab, from_outputs=from_outputs, ignore_index=0, confmat=cm, ece_bins=bins, want=want)
+        assert _lib.launch_count() - n0 == 1
+        res.append((r, cm, bins))
+    _switch("slu_debug_no_packed_evidential", 0)
+    (a, cma, ba), (b, cmb, bb) = res
+    assert torch.equal(a["alpha"], b["alpha"]) and torch.equal(a["pred"], b["pred"]) and torch.equal(a["conf"], b["conf"])
+    assert torch.equal(cma, cmb) and torch.equal(ba[:2], bb[:2])
+    for k in ("H", "AU", "EU", "MI"):
+        assert (a[k] - b[k]).abs().max().item() < 2e-6, k
+
+
+@pytest.mark.parametrize("C", [20, 6])
+def test_packed_loss_kernels_agree_with_one_pixel_kernels(cuda, C):
+    B, H, W = 2, 8, 258
+    x, lab = synth.synth_evidential_logits(5, B, C, H, W)
+    x, lab = x.to(cuda), lab.to(cuda)
+    alpha = ops.evidential_reduce(x, from_outputs=True, want=("alpha",))["alpha"]
+    alpha[0, 1, 0, :8] = 0.25                              # concentrations below 1: the out-of-line special-function path
+    out = {}
+    for off in (0, 1):
+        _switch("slu_debug_no_packed_loss", off)
+        out[off] = (ops.evidential_loss_fused(x, lab, ignore=(0,)), ops.dirichlet_loss(alpha, lab, ignore=(0,)))
+    _switch("slu_debug_no_packed_loss", 0)
+    (fa, da), (fb, db) = out[0], out[1]
+    assert fa["sums"][2] == fb["sums"][2] and da["sums"][2] == db["sums"][2]
+    np.testing.assert_allclose(fa["sums"].cpu().numpy(), fb["sums"].cpu().numpy(), rtol=2e-6)
+    np.testing.assert_allclose(da["sums"].cpu().numpy(), db["sums"].cpu().numpy(), rtol=2e-6)
+    for ga, gb in ((fa["grad"], fb["grad"]), (da["grad_mse"], db["grad_mse"]), (da["grad_kl"], db["grad_kl"])):
+        scale = gb.abs().max().item()
+        assert (ga - gb).abs().max().item() <= 1e-5 * scale
+        assert torch.equal(ga == 0, gb == 0)               # masked pixels / the true class: exact zeros in both
+
+
+def test_loss_step_api_self_cleaning_state_and_graph(cuda):
+    from semanticlidarunc_b200.losses.evidential import EvidentialLoss
+    B, C, H, W = 2, 20, 16, 128
+    x, lab = synth.synth_evidential_logits(9, B, C, H, W)
+    x, lab = x.to(cuda), lab.to(cuda)
+    ref = ops.evidential_loss_fused(x, lab, ignore=(0,))
+    n = float(ref["sums"][2])
+    crit = EvidentialLoss(1.0, 0.05, ignore_index=0)
+    for _ in range(3):                                     # the same buffers serve every step
+        l4, g = crit.forward_backward(x, lab)
+        assert torch.equal(g, ref["grad"])
+        assert float(l4[3]) == n
+        assert float(l4[1]) == pytest.approx(float(ref["sums"][0]) / n, rel=1e-6)
+        assert float(l4[2]) == pytest.approx(float(ref["sums"][1]) / n, rel=1e-6)
+        assert float(l4[0]) == pytest.approx((float(ref["sums"][0]) + 0.05 * float(ref["sums"][1])) / n, rel=1e-6)
+    count, state = crit._buffers(x.device)
+    assert float(count) == 0.0 and bool((state == 0).all())
+    # autograd path: same values, gradient = kernel gradient times the upstream gradient
+    xo = x.clone().requires_grad_(True)
+    loss, mse, kl = crit(xo, lab)
+    (2.0 * loss).backward()
+    assert torch.equal(xo.grad, 2.0 * ref["grad"]) and float(loss) == float(l4[0])
+    # one CUDA graph over static buffers
+    xs = x.clone()
+    l4s, gs = crit.capture(xs, lab)
+    crit.replay(); torch.cuda.synchronize()
+    assert torch.equal(gs, ref["grad"]) and torch.equal(l4s, l4)
+    xs.mul_(0.5); crit.replay(); torch.cuda.synchronize()
+    ref2 = ops.evidential_loss_fused(x * 0.5, lab, ignore=(0,))
+    assert torch.equal(gs, ref2["grad"])
+
+
+# ---------------------------------------------------------------------------------------------- edge points settled on the host
+def test_drop_in_projection_settles_points_on_bin_edges_like_numpy(cuda):
+    """Points planted exactly ON column / row edges and 1-2 ulp either side of them: the literal drop-in must return
+    numpy's (the reference's) image whatever side CUDA's atan2 lands on; the kernel flags such scans and the host settles
+    them (dataset/utils.py::_settle_edge_points)."""
+    from semanticlidarunc_b200.dataset.utils import spherical_projection
+    H, W = 16, 256
+    xyzi, raw = synth.synth_scan(21, "tiny")
+    pc = np.concatenate([xyzi.astype(np.float64), np.arange(xyzi.shape[0], dtype=np.float64)[:, None] + 1.0], axis=1)
+    edges_w = np.linspace(-np.pi, np.pi, W)
+    rng = np.random.default_rng(0)
+    planted = []
+    for k, e in enumerate(edges_w[5:250:7]):
+        for ulps in (-2, -1, 0, 1, 2):
+            phi = e
+            for _ in range(abs(ulps)):
+                phi = np.nextafter(phi, np.inf if ulps > 0 else -np.inf)
+            r, el = rng.uniform(5, 60), rng.uniform(-0.3, 0.1)
+            planted.append([r * np.cos(el) * np.cos(phi), r * np.cos(el) * np.sin(phi), r * np.sin(el), 0.5, 0.0])
+    planted = np.asarray(planted)
+    planted[:, 4] = np.arange(len(planted)) + 1e6
+    pc2 = np.concatenate([pc, planted], axis=0)
+    img, _, (tmin, tmax), _ = spherical_projection(pc2, H, W)
+    ref, _, (rmin, rmax), _ = oproj.spherical_projection(pc2, H, W)
+    assert (tmin, tmax) == (rmin, rmax)
+    assert np.array_equal(img, ref)
+    assert spherical_projection.last_near_edge > 0          # the planted points were seen as ambiguous ...
+    # ... and a scan without them is not touched by the host at all
+    img0, *_ = spherical_projection(pc, H, W)
+    assert spherical_projection.last_near_edge == 0 and np.array_equal(img0, oproj.spherical_projection(pc, H, W)[0])
