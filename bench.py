@@ -636,7 +636,7 @@ def run_reference(args):
         res = ref_arm.time_reference(scans, logits, H=H, W=W, C=C, steps=steps, warmup=warm, scans_per_step=per_step,
                                      workers=workers, budget_s=args.reference_budget_s)
         v, done_steps, kind = res["scans_per_s"], res["steps"], "reference"
-        sample = (f"{per_step} scans per step x {done_steps} steps through the UNMODIFIED reference (archive of /root/reference/src: "
+        sample = (f"{per_step} scans per step x {done_steps} steps through the UNMODIFIED reference (oracle/_ref archive of the reference src tree: "
                   f"SemanticKitti.__getitem__ in {workers} DataLoader workers, Tester's MC block closures, IoUEvaluator, ECEAggregator; "
                   f"back-projection by definition), torch threads={torch.get_num_threads()}, mIoU={res['mIoU']:.4f} ece={res['ece']:.4f}")
     else:
