@@ -280,6 +280,13 @@ int slu_debug_hist_generic(int on);
  */
 int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
                    int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream);
+/* The same accumulation into 2^20 HYBRID bins, d_hist [2, 2^20]: scores pile up at both ends of [0,1] (confident pixels
+ * near 0, near-uniform ones near 1), where a uniform grid ties thousands of pixels per bin.  Monotone bin key:
+ *   s >= 1/16 : floor(s * 2^20)                                   (step 9.5e-7)
+ *   s <  1/16 : 2048 mantissa bins per binary octave, 32 octaves down to 2^-36 (relative step 4.9e-4); smaller -> bin 0.
+ * Used by the AUROC aggregator, whose result depends on the ORDER of the scores only. */
+int slu_score_hist_hybrid(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                          const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream);
 
 /* Per-class score histogram: replaces the per-class host arrays of UncertaintyPerClassAggregator.update
  * (src/models/evaluator.py:211-262).  d_hist [C, n_score_bins] int64 and d_sum_fx [C] int64 (sum of scores in

@@ -48,6 +48,7 @@ SIGNATURES = {
     "slu_confusion_ece_i32": (_i, [_p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
     "slu_debug_hist_generic": (_i, [_i]),
     "slu_score_hist": (_i, [_p, _p, _p, _i64, _i, _p, _i, _p, _p]),
+    "slu_score_hist_hybrid": (_i, [_p, _p, _p, _i64, _p, _i, _p, _p]),
     "slu_class_score_hist": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
     "slu_project_workspace_bytes": (_i64, [_i64, _i, _i64]),
     "slu_debug_project_exact": (_i, [_i]),

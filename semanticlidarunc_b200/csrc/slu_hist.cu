@@ -271,6 +271,21 @@ static int g_hist_force_generic = 0;
 // (src/models/evaluator.py:660-701) and UncertaintyAggregator (src/metrics/aurc.py:273-304): every valid pixel adds 1 to
 // hist[is_error][floor(clamp(score,0,1) * M)].  M is large (default 60000), so the histogram lives in global memory
 // (2*M int64 ~ 1 MB, L2-resident) and is updated with fire-and-forget RED atomics; 20 B/px read.
+// Hybrid bins (M = 2^20): scores pile up at BOTH ends of [0,1] (confident pixels near 0, near-uniform ones near 1), where a
+// uniform grid ties thousands of pixels in one bin.  Monotone key: s >= 1/16 -> floor(s * 2^20) (step 9.5e-7 up to 1);
+// s < 1/16 -> 2048 mantissa bins per binary octave over 32 octaves down to 2^-36 (relative step 4.9e-4), below that bin 0.
+// 65536 + 983040 = 2^20 bins in all.
+__device__ __forceinline__ int hybrid_score_bin(float s) {
+    if (s >= 0.0625f) {
+        const int k = (int)((double)s * 1048576.0);
+        return k > 1048575 ? 1048575 : k;
+    }
+    const unsigned bits = __float_as_uint(s);
+    const int e = (int)(bits >> 23) - 91;                 // biased exponent of 2^-36 is 91
+    return e < 0 ? 0 : e * 2048 + (int)((bits >> 12) & 0x7ffu);
+}
+
+template <bool HYBRID>
 __global__ void __launch_bounds__(HIST_THREADS) score_hist_kernel(const float* __restrict__ score, const long long* __restrict__ pred,
                                                                   const long long* __restrict__ labels, long long n, int M,
                                                                   int n_ignore, long long ig0, long long ig1, long long ig2, long long ig3,
@@ -285,9 +300,14 @@ __global__ void __launch_bounds__(HIST_THREADS) score_hist_kernel(const float* _
         if (n_ignore > 2 && lb == ig2) valid = false;
         if (n_ignore > 3 && lb == ig3) valid = false;
         if (!valid) continue;
-        const double c = (double)fminf(fmaxf(s, 0.f), 1.f) * (double)M;       // exact product: bin = #{k/M <= s} - 1
-        int bin = (int)c;
-        bin = bin > M - 1 ? M - 1 : bin;
+        int bin;
+        if (HYBRID) {
+            bin = hybrid_score_bin(fminf(fmaxf(s, 0.f), 1.f));
+        } else {
+            const double c = (double)fminf(fmaxf(s, 0.f), 1.f) * (double)M;   // exact product: bin = #{k/M <= s} - 1
+            bin = (int)c;
+            bin = bin > M - 1 ? M - 1 : bin;
+        }
         atomicAdd(&hist[(pr != lb ? (long long)M : 0ll) + bin], 1ull);
     }
 }
@@ -330,8 +350,21 @@ extern "C" int slu_class_score_hist(const float* d_score, const int64_t* d_label
     return 0;
 }
 
+namespace slu {
+static int score_hist_impl(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                           int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream, bool hybrid);
+}
 extern "C" int slu_score_hist(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
                               int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream) {
+    return slu::score_hist_impl(d_score, d_pred, d_labels, n, n_score_bins, h_ignore, n_ignore, d_hist, stream, false);
+}
+/* Same accumulation into the 2^20 HYBRID bins (uniform above 1/16, 2048 bins per binary octave below): d_hist [2, 2^20]. */
+extern "C" int slu_score_hist_hybrid(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                                     const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream) {
+    return slu::score_hist_impl(d_score, d_pred, d_labels, n, 1 << 20, h_ignore, n_ignore, d_hist, stream, true);
+}
+static int slu::score_hist_impl(const float* d_score, const int64_t* d_pred, const int64_t* d_labels, int64_t n,
+                                int n_score_bins, const int64_t* h_ignore, int n_ignore, int64_t* d_hist, slu_stream_t stream, bool hybrid) {
     using namespace slu;
     if (n < 0) return fail(SLU_E_ARG, "n < 0");
     if (n == 0) return 0;
@@ -344,9 +377,14 @@ extern "C" int slu_score_hist(const float* d_score, const int64_t* d_pred, const
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
     const long long want = (n + HIST_THREADS - 1) / HIST_THREADS;
     const long long cap = 8LL * sms;
-    score_hist_kernel<<<(unsigned)(want < cap ? want : cap), HIST_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        d_score, reinterpret_cast<const long long*>(d_pred), reinterpret_cast<const long long*>(d_labels), n, n_score_bins,
-        n_ignore, ig[0], ig[1], ig[2], ig[3], reinterpret_cast<unsigned long long*>(d_hist));
+    if (hybrid)
+        score_hist_kernel<true><<<(unsigned)(want < cap ? want : cap), HIST_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            d_score, reinterpret_cast<const long long*>(d_pred), reinterpret_cast<const long long*>(d_labels), n, n_score_bins,
+            n_ignore, ig[0], ig[1], ig[2], ig[3], reinterpret_cast<unsigned long long*>(d_hist));
+    else
+        score_hist_kernel<false><<<(unsigned)(want < cap ? want : cap), HIST_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            d_score, reinterpret_cast<const long long*>(d_pred), reinterpret_cast<const long long*>(d_labels), n, n_score_bins,
+            n_ignore, ig[0], ig[1], ig[2], ig[3], reinterpret_cast<unsigned long long*>(d_hist));
     SLU_LAUNCH_CHECK("score_hist_kernel");
     return 0;
 }

@@ -62,18 +62,18 @@ def _host_bins(pc64: np.ndarray, height: int, width: int, theta_range):
     tmin, tmax = (theta.min(), theta.max()) if theta_range is None else theta_range
     row = (np.digitize(theta, np.linspace(tmin, tmax, height)[::-1]) - 1) % height
     col = (np.digitize(phi, np.linspace(-np.pi, np.pi, width)[::-1]) - 1) % width
-    return row * width + col
+    return row * width + col, (float(tmin), float(tmax))
 
 
 def _settle_edge_points(pc64: np.ndarray, img: np.ndarray, pix: np.ndarray, height, width, theta_range, farthest_wins):
     """Bit-exactness by construction: CUDA's and numpy's atan2 are both good to ~2 ulp, so a point within 4 ulp of a bin
     edge (the kernel counts them; ~1e-14 of all points) could land on either side.  When a scan has such points, every
     point's bin is recomputed with numpy and the pixels whose membership changed are re-resolved on the host.
-    Returns the number of points that changed pixel."""
-    host = _host_bins(pc64, height, width, theta_range)
+    Returns (number of points that changed pixel, numpy's (theta_min, theta_max))."""
+    host, trange = _host_bins(pc64, height, width, theta_range)
     changed = np.nonzero(host != pix)[0]
     if changed.size == 0:
-        return 0
+        return 0, trange
     r = np.sqrt(pc64[:, 0] ** 2 + pc64[:, 1] ** 2 + pc64[:, 2] ** 2)
     flat = img.reshape(height * width, -1)
     for q in np.unique(np.concatenate([host[changed], pix[changed].astype(np.int64)])):
@@ -85,7 +85,7 @@ def _settle_edge_points(pc64: np.ndarray, img: np.ndarray, pix: np.ndarray, heig
             best = members[rr == (rr.max() if farthest_wins else rr.min())].min()     # lowest index among exact ties
             flat[q] = pc64[best].astype(np.float32)
     pix[changed] = host[changed]
-    return int(changed.size)
+    return int(changed.size), trange
 
 
 def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, sort_largest_first=False,
@@ -121,8 +121,8 @@ def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, so
     spherical_projection.last_near_edge, spherical_projection.last_settled = int(near_edge), 0
     if near_edge > 0:
         pix = res["pix"].cpu().numpy()
-        spherical_projection.last_settled = _settle_edge_points(pc64, pj_img, pix, height, width, theta_range,
-                                                                sort_largest_first)
+        spherical_projection.last_settled, (tmin, tmax) = _settle_edge_points(pc64, pj_img, pix, height, width, theta_range,
+                                                                              sort_largest_first)
     if theta_range is not None:
         tmin, tmax = theta_range
     alpha = None

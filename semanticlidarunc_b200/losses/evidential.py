@@ -85,7 +85,7 @@ class EvidentialLoss(nn.Module):
         self._graph = None
 
     # ---- plumbing ------------------------------------------------------------------------------------------------
-    def _buffers(self, dev):
+    def _work_buffers(self, dev):
         if dev not in self._bufs:
             self._bufs[dev] = (torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(3, dtype=torch.float64, device=dev))
         return self._bufs[dev]
@@ -115,7 +115,7 @@ class EvidentialLoss(nn.Module):
         import torch.distributed as dist
         target = self._target3(target)
         dev = target.device
-        count, _ = self._buffers(dev)
+        count, _ = self._work_buffers(dev)
         ids, keep = self._mask(target)
         main = torch.cuda.current_stream(dev)
         if dev not in self._side:
@@ -134,7 +134,7 @@ class EvidentialLoss(nn.Module):
     def _step(self, outputs, target, want_grad=True, loss4=None, grad=None):
         target = self._target3(target)
         dev = outputs.device
-        count, state = self._buffers(dev)
+        count, state = self._work_buffers(dev)
         ids, keep = self._mask(target)
         g, world = _group_of(self.group)
         precounted = world > 1

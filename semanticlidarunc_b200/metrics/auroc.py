@@ -3,12 +3,15 @@
 Same constructor `(mode, score, ignore_index, max_samples, seed, eps)`, `update(preds, labels,
 score_override=None)`, `compute(save_plot_path, title, dpi)`, `reset()`.  The reference keeps every
 (score, is_error) pair on the host and argsorts them at compute(); here `update` is the fused
-uncertainty kernel (score map) plus one histogram kernel, and the state is `[2, 60000]` int64 counts.
+uncertainty kernel (score map) plus one histogram kernel, and the state is `[2, 2^20]` int64 counts in the
+HYBRID bins of slu_score_hist_hybrid (uniform steps of 2^-20 above 1/16, 2048 bins per binary octave below:
+entropy-like scores pile up at both ends of [0,1]).
 
-AUROC from the histogram treats the samples of one fine bin as tied (the reference orders exact ties
+AUROC from the histogram treats the samples of one bin as tied (the reference orders exact ties
 arbitrarily); the difference is at most half the probability that a wrong and a correct pixel share a
-bin of width 1/60000 -- below 1e-5 for continuous scores, and far below the sampling noise of the
-reference's `max_samples` subsample, which is accepted and ignored here (every pixel is counted).
+bin -- below 1e-4 even when a third of the pixels sit within 1e-3 of the maximum entropy, and far below the
+sampling noise of the reference's `max_samples` subsample, which is accepted and ignored here (every pixel is
+counted).  Any other `n_score_bins` selects a uniform grid of that size.
 """
 from __future__ import annotations
 
@@ -22,8 +25,9 @@ from .. import _lib, ops
 _MODES = {"alpha": ("alpha", ops.CONF_RAW), "logits": ("logits", ops.CONF_RAW), "probs": ("probs", ops.CONF_RENORM)}
 
 
-def roc_from_hist(hist: np.ndarray):
-    """(fpr, tpr, thresholds, auroc) for 'high score => error', from [2,M] counts (row 1 = errors)."""
+def roc_from_hist(hist: np.ndarray, lower_edges=None):
+    """(fpr, tpr, thresholds, auroc) for 'high score => error', from [2,M] counts (row 1 = errors).  `lower_edges`: the
+    bins' lower edges (default: a uniform grid)."""
     ok, err = hist[0].astype(np.float64), hist[1].astype(np.float64)
     P, N = err.sum(), ok.sum()
     if P == 0 or N == 0:
@@ -33,13 +37,14 @@ def roc_from_hist(hist: np.ndarray):
     fps = np.cumsum(ok[::-1])
     tpr = np.concatenate(([0.0], tps / P, [1.0]))
     fpr = np.concatenate(([0.0], fps / N, [1.0]))
-    thr = np.concatenate(([np.inf], (np.arange(M)[::-1]) / M, [-np.inf]))
+    low = np.arange(M) / M if lower_edges is None else np.asarray(lower_edges)[:M]
+    thr = np.concatenate(([np.inf], low[::-1], [-np.inf]))
     return fpr, tpr, thr, float(np.trapezoid(tpr, fpr))
 
 
 class AUROCAggregator:
     def __init__(self, mode="alpha", score="entropy_norm", ignore_index=None, max_samples=None, seed=0, eps=1e-12,
-                 n_score_bins: int = ops.SCORE_BINS):
+                 n_score_bins: int = ops.HYBRID_BINS):
         assert mode in {"alpha", "logits", "probs"}
         assert score in {"entropy", "entropy_norm", "mi", "mi_norm", "1-maxprob"}
         self.mode, self.score = mode, score
@@ -47,6 +52,7 @@ class AUROCAggregator:
         self.max_samples = max_samples
         self.eps = float(eps)
         self.n_score_bins = int(n_score_bins)
+        self.hybrid = self.n_score_bins == ops.HYBRID_BINS
         self._hist = None
 
     def _accumulator(self, dev=None):
@@ -90,7 +96,7 @@ class AUROCAggregator:
         if score_override is not None:
             score_map = self._unit_range(score_override.to(dev), preds.size(1))
         ops.score_hist(score_map, pred, labels, self._accumulator(dev),
-                       ignore=() if self.ignore_index is None else (self.ignore_index,))
+                       ignore=() if self.ignore_index is None else (self.ignore_index,), hybrid=self.hybrid)
 
     @staticmethod
     def _unit_range(score: torch.Tensor, num_classes: int) -> torch.Tensor:
@@ -127,7 +133,8 @@ class AUROCAggregator:
         total = int(h.sum())
         if total > cap:
             h = np.floor(h * (cap / total) + 0.5).astype(np.int64)
-        centres = ((np.arange(h.shape[1]) + 0.5) / h.shape[1]).astype(np.float32)
+        edges = ops.hybrid_bin_lower_edges() if self.hybrid else np.arange(h.shape[1] + 1) / h.shape[1]
+        centres = (0.5 * (edges[:-1] + edges[1:])).astype(np.float32)
         scores = np.concatenate([np.repeat(centres, h[0]), np.repeat(centres, h[1])])
         err = np.concatenate([np.zeros(int(h[0].sum()), np.uint8), np.ones(int(h[1].sum()), np.uint8)])
         return torch.from_numpy(scores), torch.from_numpy(err)
@@ -136,12 +143,12 @@ class AUROCAggregator:
         """Accumulate from maps the fused kernel already produced (no second pass over the class axis).  The score
         must already lie in [0,1] (the kernels' *_norm maps do); nothing is checked here, so the call never synchronises."""
         ops.score_hist(score_map, pred, labels, self._accumulator(score_map.device),
-                       ignore=() if self.ignore_index is None else (self.ignore_index,))
+                       ignore=() if self.ignore_index is None else (self.ignore_index,), hybrid=self.hybrid)
 
     def compute(self, save_plot_path: str | None = None, title: str = "ROC: error detection", dpi: int = 200):
         if self._hist is None or self._seen == 0:
             return float("nan"), {}
-        fpr, tpr, thr, auroc = roc_from_hist(self._hist.cpu().numpy())
+        fpr, tpr, thr, auroc = roc_from_hist(self._hist.cpu().numpy(), ops.hybrid_bin_lower_edges() if self.hybrid else None)
         if math.isnan(auroc):
             return auroc, {}
         fig = None

@@ -405,9 +405,23 @@ def new_score_hist(device, n_score_bins: int = SCORE_BINS) -> torch.Tensor:
     return torch.zeros((2, n_score_bins), dtype=torch.int64, device=device)
 
 
+HYBRID_BINS = 1 << 20      # bins of the hybrid scheme (slu_score_hist_hybrid)
+
+
+def hybrid_bin_lower_edges() -> np.ndarray:
+    """float64 lower edges of the 2^20 hybrid bins plus the closing 1.0 (length 2^20 + 1): 2048 mantissa bins per binary
+    octave from 2^-36 to 1/16 (bin 0 starts at 0), then uniform steps of 2^-20."""
+    e = np.arange(32, dtype=np.float64)[:, None] - 36.0
+    low = (np.exp2(e) * (1.0 + np.arange(2048, dtype=np.float64)[None, :] / 2048.0)).reshape(-1)
+    low[0] = 0.0
+    return np.concatenate([low, np.arange(65536, HYBRID_BINS + 1, dtype=np.float64) / HYBRID_BINS])
+
+
 @_lib.device_guard
-def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, ignore=()) -> None:
-    """Accumulate (score, pred != label) pairs into `hist` (slu_score_hist)."""
+def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hist: torch.Tensor, ignore=(),
+               hybrid: bool = False) -> None:
+    """Accumulate (score, pred != label) pairs into `hist` [2,M] (slu_score_hist; hybrid=True: the 2^20 hybrid bins of
+    slu_score_hist_hybrid, M must be HYBRID_BINS)."""
     _lib.require_cuda()
     score = _lib.as_buffer(score, torch.float32, "score").reshape(-1)
     pred = _lib.as_buffer(pred, torch.int64, "pred").reshape(-1)
@@ -418,8 +432,14 @@ def score_hist(score: torch.Tensor, pred: torch.Tensor, labels: torch.Tensor, hi
         raise ValueError("hist must be a contiguous [2,M] int64 tensor")
     ign = [int(v) for v in ignore]
     h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
-    rc = _lib.lib().slu_score_hist(_lib.ptr(score), _lib.ptr(pred), _lib.ptr(labels), score.numel(), hist.size(1),
-                                   h_ign, len(ign), _lib.ptr(hist), _lib.stream_ptr())
+    if hybrid:
+        if hist.size(1) != HYBRID_BINS:
+            raise ValueError(f"the hybrid scheme needs hist [2,{HYBRID_BINS}]")
+        rc = _lib.lib().slu_score_hist_hybrid(_lib.ptr(score), _lib.ptr(pred), _lib.ptr(labels), score.numel(),
+                                              h_ign, len(ign), _lib.ptr(hist), _lib.stream_ptr())
+    else:
+        rc = _lib.lib().slu_score_hist(_lib.ptr(score), _lib.ptr(pred), _lib.ptr(labels), score.numel(), hist.size(1),
+                                       h_ign, len(ign), _lib.ptr(hist), _lib.stream_ptr())
     _lib.check(rc, "slu_score_hist")
 
 

@@ -198,7 +198,10 @@ def test_packed_evidential_kernel_agrees_with_one_pixel_kernel(cuda, C, from_out
         res.append((r, cm, bins))
     _switch("slu_debug_no_packed_evidential", 0)
     (a, cma, ba), (b, cmb, bb) = res
-    assert torch.equal(a["alpha"], b["alpha"]) and torch.equal(a["pred"], b["pred"]) and torch.equal(a["conf"], b["conf"])
+    # same formulas, but ptxas schedules / contracts the two kernels differently: concentrations agree to an ulp or two,
+    # the integer results exactly
+    assert ((a["alpha"] - b["alpha"]).abs() <= 6e-7 * b["alpha"].abs()).all()
+    assert torch.equal(a["pred"], b["pred"]) and (a["conf"] - b["conf"]).abs().max().item() < 1e-7
     assert torch.equal(cma, cmb) and torch.equal(ba[:2], bb[:2])
     for k in ("H", "AU", "EU", "MI"):
         assert (a[k] - b[k]).abs().max().item() < 2e-6, k
@@ -241,7 +244,7 @@ def test_loss_step_api_self_cleaning_state_and_graph(cuda):
         assert float(l4[1]) == pytest.approx(float(ref["sums"][0]) / n, rel=1e-6)
         assert float(l4[2]) == pytest.approx(float(ref["sums"][1]) / n, rel=1e-6)
         assert float(l4[0]) == pytest.approx((float(ref["sums"][0]) + 0.05 * float(ref["sums"][1])) / n, rel=1e-6)
-    count, state = crit._buffers(x.device)
+    count, state = crit._work_buffers(x.device)
     assert float(count) == 0.0 and bool((state == 0).all())
     # autograd path: same values, gradient = kernel gradient times the upstream gradient
     xo = x.clone().requires_grad_(True)

@@ -16,6 +16,10 @@ from semanticlidarunc_b200 import ops, synth  # noqa: E402
 from semanticlidarunc_b200.dataset.definitions import build_id_lut  # noqa: E402
 
 dev = torch.device("cuda", 0)
+if os.environ.get("SLU_NO_PACKED", "0") == "1":          # A/B: the one-pixel-per-thread kernels instead of the packed f32x2 ones
+    from semanticlidarunc_b200 import _lib
+    _lib.lib().slu_debug_no_packed_loss(1)
+    _lib.lib().slu_debug_no_packed_evidential(1)
 PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 only = set(sys.argv[1:])
