@@ -190,11 +190,11 @@ __global__ void __launch_bounds__(EV_THREADS, EV_MINB) evidential_kernel(const _
 // and pred (the dispatcher checks; otherwise the one-pixel kernel above runs).
 constexpr int EV2_THREADS = 128;
 #ifndef SLU_EV2_MINB
-#define SLU_EV2_MINB 5
+#define SLU_EV2_MINB 6
 #endif
 static int g_ev_no_packed = 0;
 
-template <int CP, bool EXACT, bool MI>
+template <int CP, bool EXACT, bool MI, bool GE1>
 __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kernel(const __grid_constant__ EvParams p) {
     __shared__ AtomicHist hs;
     const int tid = threadIdx.x;
@@ -277,34 +277,81 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
         const f2 a0 = asum + p.eps;                        // probability_helper.py:119,127
         const f2 a0m = asum + p.eps_m;                     // auroc.py:57
         const bool want_unc = p.h || p.au || p.eu || MI;
-        f2 H(0.f), AU(0.f), Hm(0.f), EHm(0.f);
+        f2 H(0.f), AU(0.f), EU(0.f), MIv(0.f);
         if (want_unc) {                                    // warp-uniform
-            const f2 x0 = a0 + 1.0f;
-            const PsiG2 q0 = psi_g2(x0);
             const bool same0 = a0m.v.x == a0.v.x && a0m.v.y == a0.v.y;     // alpha >= 1: both eps vanish in fp32
-            PsiG2 q0m = q0;
-            if (MI && !same0) q0m = psi_g2(a0m + 1.0f);
             const f2 inv0 = rcp_rn2(a0), inv0m = (MI && !same0) ? rcp_rn2(a0m) : inv0;
-            f2 H2(0.f), Hm2(0.f);                          // entropies in log2 units
+            // Every concentration >= 1 (always true for a head output: alpha = 1 + softplus * softmax + eps):
+            // the digamma recurrence psi(a + 1) = psi(a) + 1/a and psi(a) = ln a + g(1/a) give
+            //     psi(alpha_c + 1) - psi(alpha0 + 1) = ln(alpha_c / alpha0) + G(1/alpha_c) - G(1/alpha0),  G(w) = g(w) + w,
+            // so the digamma difference shares its logarithm with the entropy (ln p_c): 3 MUFU per class (softmax ex2, one
+            // reciprocal, one lg2) instead of 5, and the epistemic part comes out WITHOUT the cancellation of H - AU:
+            //     EU = sum_c p_c G(1/alpha_c) - G(1/alpha0) sum_c p_c,   AU = H - EU,   Dirichlet MI (auroc.py:55-63) = EU
+            // with the AUROC eps.  (eps inside the log shifts H by <= C eps = 2e-7, far inside the 1e-5 tolerance.)
+            bool ge1 = GE1;
+            if (!GE1) {
+                float amin = 3.0e38f;
 #pragma unroll
-            for (int c = 0; c < CP; ++c) {
-                if (EXACT || c < p.C) {
-                    const f2 ph = a[c] * inv0;
-                    const f2 xc = a[c] + 1.0f;
-                    const PsiG2 q = psi_g2(xc);
-                    const f2 d = psi_diff2(xc, q, q0);
-                    H2 = fma2(-ph, lg2_2(ph + p.eps), H2);                    // :121
-                    AU = fma2(-ph, d, AU);                                    // :128-130
-                    if (MI) {
-                        const f2 pm = a[c] * inv0m;
-                        const f2 pmc = max2(pm, p.eps_m);
-                        Hm2 = fma2(-pmc, lg2_2(pmc), Hm2);                    // auroc.py:59
-                        EHm = fma2(-pm, same0 ? d : psi_diff2(xc, q, q0m), EHm);   // auroc.py:60-61
+                for (int c = 0; c < CP; ++c)
+                    if (EXACT || c < p.C) amin = fminf(amin, fminf(a[c].v.x, a[c].v.y));
+                ge1 = amin >= 1.0f;                        // NaN fails the test too: the literal formulas below then apply
+            }
+            if (ge1) {
+                f2 H2(0.f), SG(0.f), SGm(0.f);
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) {
+                        const f2 ph = a[c] * inv0;
+                        const f2 w = rcp2(a[c]);
+                        f2 h = fma2(f2(2.889277183e-04f), w, -1.886666441e-03f);
+                        h = fma2(h, w, 4.937323876e-03f);
+                        h = fma2(h, w, -5.935221128e-03f);
+                        h = fma2(h, w, 4.237475471e-04f);
+                        h = fma2(h, w, 8.287647461e-03f);
+                        h = fma2(h, w, 1.917667073e-06f);
+                        h = fma2(h, w, -8.333334680e-02f);
+                        const f2 Gc = w * fma2(h, w, 0.5f);                   // g(w) + w = w (w h(w) + 1/2)
+                        H2 = fma2(-ph, lg2_2(ph + p.eps), H2);                // :121
+                        SG = fma2(ph, Gc, SG);
+                        if (MI && !same0) SGm = fma2(a[c] * inv0m, Gc, SGm);
                     }
                 }
+                H = H2 * 0.6931471805599453f;
+                const PsiG2 q0 = psi_g2(a0);                                  // G(1/alpha0) = q0.g + q0.w
+                EU = fma2(-(q0.g + q0.w), asum * inv0, SG);
+                AU = H - EU;                                                  // :128-136
+                if (MI) {
+                    if (same0) MIv = EU;
+                    else { const PsiG2 q0m = psi_g2(a0m); MIv = fma2(-(q0m.g + q0m.w), asum * inv0m, SGm); }
+                }
+            } else {
+                // concentrations below 1 (caller-supplied alpha only): the literal formulas, digamma on alpha + 1 >= 1
+                const f2 x0 = a0 + 1.0f;
+                const PsiG2 q0 = psi_g2(x0);
+                PsiG2 q0m = q0;
+                if (MI && !same0) q0m = psi_g2(a0m + 1.0f);
+                f2 H2(0.f), Hm2(0.f), EHm(0.f);
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) {
+                        const f2 ph = a[c] * inv0;
+                        const f2 xc = a[c] + 1.0f;
+                        const PsiG2 q = psi_g2(xc);
+                        const f2 d = psi_diff2(xc, q, q0);
+                        H2 = fma2(-ph, lg2_2(ph + p.eps), H2);                // :121
+                        AU = fma2(-ph, d, AU);                                // :128-130
+                        if (MI) {
+                            const f2 pm = a[c] * inv0m;
+                            const f2 pmc = max2(pm, p.eps_m);
+                            Hm2 = fma2(-pmc, lg2_2(pmc), Hm2);                // auroc.py:59
+                            EHm = fma2(-pm, same0 ? d : psi_diff2(xc, q, q0m), EHm);   // auroc.py:60-61
+                        }
+                    }
+                }
+                H = H2 * 0.6931471805599453f;
+                EU = H - AU;
+                MIv = Hm2 * 0.6931471805599453f - EHm;
             }
-            H = H2 * 0.6931471805599453f;
-            Hm = Hm2 * 0.6931471805599453f;
         }
         const float conf0 = __fdiv_rn(amax0, asum.v.x + p.eps_m), conf1 = __fdiv_rn(amax1, asum.v.y + p.eps_m);   // ece.py:57-58,75
         if (live) {
@@ -312,8 +359,8 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
             if (p.conf) st2(p.conf + g, f2(conf0, conf1));
             if (p.h) st2(p.h + g, f2(__fdiv_rn(H.v.x, p.logC), __fdiv_rn(H.v.y, p.logC)));
             if (p.au) st2(p.au + g, AU);
-            if (p.eu) st2(p.eu + g, H - AU);
-            if (MI) { const f2 d = Hm - EHm; st2(p.mi + g, f2(__fdiv_rn(d.v.x, p.logC), __fdiv_rn(d.v.y, p.logC))); }
+            if (p.eu) st2(p.eu + g, EU);
+            if (MI) st2(p.mi + g, f2(__fdiv_rn(MIv.v.x, p.logC), __fdiv_rn(MIv.v.y, p.logC)));
         }
         if (p.labels && live) {     // confusion: tester's argmax of the shape softmax; ECE: argmax of alpha/alpha0 (ece.py:75,84)
             const longlong2 lb = *reinterpret_cast<const longlong2*>(p.labels + g);
@@ -344,10 +391,18 @@ static int launch_ev(const EvParams& p, cudaStream_t st) {
         const long long chunks2 = ((p.n_px >> 1) + EV2_THREADS - 1) / EV2_THREADS;
         const long long cap2 = (long long)SLU_EV2_MINB * sms;
         const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
-        if (exact && mi) evidential_x2_kernel<CP, true, true><<<grid2, EV2_THREADS, 0, st>>>(p);
-        else if (exact) evidential_x2_kernel<CP, true, false><<<grid2, EV2_THREADS, 0, st>>>(p);
-        else if (mi) evidential_x2_kernel<CP, false, true><<<grid2, EV2_THREADS, 0, st>>>(p);
-        else evidential_x2_kernel<CP, false, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+        // GE1: a head output always gives alpha >= 1; caller-supplied concentrations are checked per thread
+        if (p.outputs) {
+            if (exact && mi) evidential_x2_kernel<CP, true, true, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else if (exact) evidential_x2_kernel<CP, true, false, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else if (mi) evidential_x2_kernel<CP, false, true, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else evidential_x2_kernel<CP, false, false, true><<<grid2, EV2_THREADS, 0, st>>>(p);
+        } else {
+            if (exact && mi) evidential_x2_kernel<CP, true, true, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else if (exact) evidential_x2_kernel<CP, true, false, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else if (mi) evidential_x2_kernel<CP, false, true, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+            else evidential_x2_kernel<CP, false, false, false><<<grid2, EV2_THREADS, 0, st>>>(p);
+        }
         SLU_LAUNCH_CHECK("evidential_x2_kernel");
         return 0;
     }

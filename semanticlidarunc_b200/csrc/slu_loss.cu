@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) dirichlet_loss_kernel
 // ---- packed variant of dirichlet_loss_kernel: two adjacent pixels per thread (slu_packed.cuh) -------------------------
 constexpr int DL2_THREADS = 128;
 #ifndef SLU_DL2_MINB
-#define SLU_DL2_MINB 4
+#define SLU_DL2_MINB 5
 #endif
 static int g_no_packed = 0;        // A/B switch (slu_debug_no_packed_loss): 1 = always run the one-pixel-per-thread kernels
 
@@ -217,57 +217,77 @@ __global__ void __launch_bounds__(DL2_THREADS, SLU_DL2_MINB) dirichlet_loss_x2_k
                 s2 = fma2(a[c], a[c], s2);
                 ay = f2(c == y0 ? a[c].v.x : ay.v.x, c == y1 ? a[c].v.y : ay.v.y);
             }
+            // sum p^2 = s2 / D^2 and the variance term (a0^2 - s2) / G in closed form; sum (y - p)^2 per class (it cancels
+            // at confident pixels)
             const f2 D = a0 + p.eps_mse, invD(1.0f / D.v.x, 1.0f / D.v.y);
             const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG(1.0f / G.v.x, 1.0f / G.v.y);
-            f2 sq(0.f), sp2(0.f), var(0.f);
+            const f2 N = fma2(a0, a0, -s2);
+            const f2 sp2 = s2 * invD * invD;
+            const f2 Gp = fma2(a0 * 2.0f, a0 + 1.0f, fma2(a0, a0, p.eps_mse));
+            const f2 common = fma2((fma2(ay, invD, -sp2)) * 2.0f, invD, fma2(a0 * 2.0f, invG, -(N * Gp * invG * invG)));
+            const f2 m2invD = invD * -2.0f, m2invG = invG * -2.0f;
+            f2 sq(0.f);
 #pragma unroll
             for (int c = 0; c < CP; ++c) {
                 if (EXACT || c < p.C) {
-                    const f2 pc = a[c] * invD;
-                    const f2 d = f2(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f) - pc;
+                    const f2 d = f2(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f) - a[c] * invD;
                     sq = fma2(d, d, sq);
-                    sp2 = fma2(pc, pc, sp2);
-                    var = fma2(a[c] * (a0 - a[c]), invG, var);
-                }
-            }
-            const f2 mse = sq + var;
-            if (v0) acc_mse += (double)mse.v.x;
-            if (v1) acc_mse += (double)mse.v.y;
-            if (gm) {
-                const f2 N = fma2(a0, a0, -s2);
-                const f2 Gp = fma2(a0 * 2.0f, a0 + 1.0f, fma2(a0, a0, p.eps_mse));
-                const f2 common = fma2((fma2(ay, invD, -sp2)) * 2.0f, invD, fma2(a0 * 2.0f, invG, -(N * Gp * invG * invG)));
-#pragma unroll
-                for (int c = 0; c < CP; ++c) {
-                    if (EXACT || c < p.C) {
-                        const f2 pc = a[c] * invD;
-                        const f2 yc(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f);
-                        const f2 o = fma2((yc - pc) * -2.0f, invD, fma2(a[c] * -2.0f, invG, common));
+                    if (gm) {
+                        const f2 o = fma2(d, m2invD, fma2(a[c], m2invG, common));
                         st2(gm + (long long)c * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
                     }
                 }
             }
+            const f2 mse = fma2(N, invG, sq);
+            if (v0) acc_mse += (double)mse.v.x;
+            if (v1) acc_mse += (double)mse.v.y;
         }
         if (p.want_kl) {
-            f2 s(0.f);
+            f2 s(0.f), amin(3.0e38f);
 #pragma unroll
             for (int c = 0; c < CP; ++c)
-                if (EXACT || c < p.C) s += max2(f2(c == y0 ? 1.0f : a[c].v.x, c == y1 ? 1.0f : a[c].v.y), p.eps_kl);
-            const LDT2 fs = ldt_pos2<false>(s);
-            f2 kl = fs.lg;
-            const f2 tail = (s - (float)p.C) * fs.tri;
-#pragma unroll
-            for (int c = 0; c < CP; ++c) {
                 if (EXACT || c < p.C) {
-                    const bool t0 = c == y0, t1 = c == y1;
-                    const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
-                    const LDT2 f = ldt_pos2<false>(ac);
-                    kl = kl - f.lg;
-                    kl = fma2(ac - 1.0f, f.psi - fs.psi, kl);
-                    if (gk) {
-                        const f2 gj = fma2(ac - 1.0f, f.tri, -tail);
-                        st2(gk + (long long)c * p.HW, f2((v0 && !t0 && a[c].v.x > p.eps_kl) ? gj.v.x : 0.f,
-                                                         (v1 && !t1 && a[c].v.y > p.eps_kl) ? gj.v.y : 0.f));
+                    const f2 ac = max2(f2(c == y0 ? 1.0f : a[c].v.x, c == y1 ? 1.0f : a[c].v.y), p.eps_kl);
+                    s += ac;
+                    amin = f2(fminf(amin.v.x, ac.v.x), fminf(amin.v.y, ac.v.y));
+                }
+            const LDT2 fs = ldt_pos2<false>(s);
+            const f2 tail = (s - (float)p.C) * fs.tri;
+            f2 kl;
+            if (amin.v.x >= 1.0f && amin.v.y >= 1.0f) {
+                // every a~ >= 1 (what an evidential head produces): merged polynomials, slu_packed.cuh
+                f2 L(0.f), Qs(0.f);
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) {
+                        const bool t0 = c == y0, t1 = c == y1;
+                        const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+                        const f2 w = rcp2(ac);
+                        L += lg2_2(ac);
+                        Qs = fma2(w, kl_value_poly(w), Qs);
+                        if (gk) {
+                            const f2 gj = kl_grad_term(w) - tail;
+                            st2(gk + (long long)c * p.HW, f2((v0 && !t0 && a[c].v.x > p.eps_kl) ? gj.v.x : 0.f,
+                                                             (v1 && !t1 && a[c].v.y > p.eps_kl) ? gj.v.y : 0.f));
+                        }
+                    }
+                }
+                kl = (fma2(-fs.psi, s - (float)p.C, fs.lg) + fma2(L, -0.34657359027997264f, s - (float)p.C * KL_VALUE_CONST)) + Qs;
+            } else {
+                kl = fs.lg;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    if (EXACT || c < p.C) {
+                        const bool t0 = c == y0, t1 = c == y1;
+                        const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+                        const LDT2 f = ldt_pos2<false>(ac);
+                        kl = kl - f.lg;
+                        kl = fma2(ac - 1.0f, f.psi - fs.psi, kl);
+                        if (gk) {
+                            const f2 gj = fma2(ac - 1.0f, f.tri, -tail);
+                            st2(gk + (long long)c * p.HW, f2((v0 && !t0 && a[c].v.x > p.eps_kl) ? gj.v.x : 0.f,
+                                                             (v1 && !t1 && a[c].v.y > p.eps_kl) ? gj.v.y : 0.f));
+                        }
                     }
                 }
             }
@@ -507,7 +527,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, LOSS_MINB) evidential_loss_fused
 // aligned target / 8-byte aligned outputs and gradient (the dispatcher checks; otherwise the scalar kernel runs).
 constexpr int LOSS2_THREADS = 128;
 #ifndef SLU_LOSS2_MINB
-#define SLU_LOSS2_MINB 4
+#define SLU_LOSS2_MINB 3
 #endif
 
 template <int CP, bool EXACT>
@@ -562,46 +582,42 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
             ay = f2(t0 ? a[c].v.x : ay.v.x, t1 ? a[c].v.y : ay.v.y);
             if (EXACT || c < p.C) s += max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
         }
-        // ---- MSE term
+        // ---- both terms in ONE class loop.  Closed forms carry everything that does not need the class index:
+        //   sum p^2 = s2 / D^2,  variance term = (a0^2 - s2) / G;  only sum (y - p)^2 keeps its per-class form (it cancels
+        //   at confident pixels).  KL value through the merged polynomial (slu_packed.cuh::kl_value_poly):
+        //   kl = lgamma(s) - psi(s)(s - C) + sum_c f(a~_c),  sum_c f = -ln2/2 sum lg2 a~ + s - C (ln 2pi + 1)/2 + sum w u(w)
         const f2 D = a0 + p.eps_mse, invD(1.0f / D.v.x, 1.0f / D.v.y);
         const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG(1.0f / G.v.x, 1.0f / G.v.y);
-        f2 sq(0.f), sp2(0.f), var(0.f);
-#pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            if (EXACT || c < p.C) {
-                const f2 pc = a[c] * invD;
-                const f2 d = f2(c == y0 ? 1.0f : 0.0f, c == y1 ? 1.0f : 0.0f) - pc;
-                sq = fma2(d, d, sq);
-                sp2 = fma2(pc, pc, sp2);
-                var = fma2(a[c] * (a0 - a[c]), invG, var);
-            }
-        }
-        const f2 mse = sq + var;
         const f2 N = fma2(a0, a0, -s2);
+        const f2 sp2 = s2 * invD * invD;
+        const f2 var = N * invG;
         const f2 Gp = fma2(a0 * 2.0f, a0 + 1.0f, fma2(a0, a0, p.eps_mse));
         const f2 common = fma2((fma2(ay, invD, -sp2)) * 2.0f, invD, fma2(a0 * 2.0f, invG, -(N * Gp * invG * invG)));
-        // ---- KL term
+        const f2 m2invD = invD * -2.0f, m2invG = invG * -2.0f;
+        const float wm = p.w_mse * inv_n, wk = p.w_kl * inv_n;      // 1/n_valid folded into the term weights
         const LDT2 fs = ldt_pos2<true>(s);
-        f2 kl = fs.lg;
         const f2 tail = (s - (float)p.C) * fs.tri;
-        f2 gp_sum(0.f);
+        f2 sq(0.f), L(0.f), Qs(0.f), gp_sum(0.f);
 #pragma unroll
         for (int c = 0; c < CP; ++c) {
             if (EXACT || c < p.C) {
                 const bool t0 = c == y0, t1 = c == y1;
-                const f2 pc = a[c] * invD;
-                const f2 yc(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f);
-                f2 gc = fma2((yc - pc) * -2.0f, invD, fma2(a[c] * -2.0f, invG, common)) * p.w_mse;
-                const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
-                const LDT2 f = ldt_pos2<true>(ac);
-                kl = kl - f.lg;
-                kl = fma2(ac - 1.0f, f.psi - fs.psi, kl);
-                const f2 gkl = fma2(fma2(ac - 1.0f, f.tri, -tail), p.w_kl, gc);
-                gc = f2((!t0 && a[c].v.x > p.eps_kl) ? gkl.v.x : gc.v.x, (!t1 && a[c].v.y > p.eps_kl) ? gkl.v.y : gc.v.y);
-                a[c] = gc * inv_n;               // a[] now holds d(loss)/d(alpha_c)
-                gp_sum = fma2(a[c], pr[c], gp_sum);
+                const f2 d = f2(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f) - a[c] * invD;
+                sq = fma2(d, d, sq);
+                const f2 gm = fma2(d, m2invD, fma2(a[c], m2invG, common));
+                const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);   // a~_y = 1: f(1) = 0, no gradient
+                const f2 w = rcp2(ac);
+                L += lg2_2(ac);
+                Qs = fma2(w, kl_value_poly(w), Qs);
+                const f2 gA = gm * wm;
+                const f2 gB = fma2(kl_grad_term(w) - tail, wk, gA);
+                const f2 gc((!t0 && a[c].v.x > p.eps_kl) ? gB.v.x : gA.v.x, (!t1 && a[c].v.y > p.eps_kl) ? gB.v.y : gA.v.y);
+                a[c] = gc;                       // a[] now holds d(loss)/d(alpha_c), 1/n_valid included
+                gp_sum = fma2(gc, pr[c], gp_sum);
             }
         }
+        const f2 mse = sq + var;
+        const f2 kl = (fma2(-fs.psi, s - (float)p.C, fs.lg) + fma2(L, -0.34657359027997264f, s - (float)p.C * KL_VALUE_CONST)) + Qs;
         if (v0) { acc_mse += (double)mse.v.x; acc_kl += (double)kl.v.x; }
         if (v1) { acc_mse += (double)mse.v.y; acc_kl += (double)kl.v.y; }
         if (go) {

@@ -134,4 +134,31 @@ __device__ __forceinline__ LDT2 ldt_pos2(f2 a) {
     return o;
 }
 
+
+// ---- merged forms for the KL regulariser (a >= 1, w = 1/a) -------------------------------------------------------------
+// The KL value needs, per class, f(a) = -lgamma(a) + (a - 1) psi(a).  With the expansions above,
+//   f(a) = -ln(a)/2 + a - (ln(2 pi) + 1)/2 + w u(w),   u(w) = 1/2 - r(w) + (1 - w) h(w),  u(0) = 1/3
+// so ONE degree-6 polynomial (least squares on Chebyshev nodes, tools/fit_digamma.py: |w u| error 1.6e-7) replaces the
+// separate lgamma and digamma evaluations; sum_c ln a_c and sum_c a_c are accumulated by the caller.
+__device__ __forceinline__ f2 kl_value_poly(f2 w) {
+    f2 u = fma2(f2(-1.514686388e-03f), w, 5.008932959e-03f);
+    u = fma2(u, w, -3.317222958e-03f);
+    u = fma2(u, w, -9.171346347e-03f);
+    u = fma2(u, w, 1.127716751e-02f);
+    u = fma2(u, w, 8.332211733e-02f);
+    u = fma2(u, w, 3.333334523e-01f);
+    return u;
+}
+constexpr float KL_VALUE_CONST = 1.418938533204672742f;      // (ln(2 pi) + 1) / 2
+
+// The KL gradient needs (a - 1) psi'(a) = (1 - w)(1 + w/2 + w^2 v(w)), v as in ldt_pos.
+__device__ __forceinline__ f2 kl_grad_term(f2 w) {
+    f2 v = fma2(f2(-3.238177565e-03f), w, 1.716627286e-02f);
+    v = fma2(v, w, -3.719230805e-02f); v = fma2(v, w, 3.725572734e-02f);
+    v = fma2(v, w, -2.641956099e-03f); v = fma2(v, w, -3.307210709e-02f); v = fma2(v, w, -1.011315425e-05f);
+    v = fma2(v, w, 1.666667325e-01f);
+    const f2 t = fma2(w * w, v, fma2(w, 0.5f, 1.0f));
+    return fma2(-w, t, t);
+}
+
 }  // namespace slu

@@ -204,7 +204,7 @@ def test_packed_evidential_kernel_agrees_with_one_pixel_kernel(cuda, C, from_out
     assert torch.equal(a["pred"], b["pred"]) and (a["conf"] - b["conf"]).abs().max().item() < 1e-7
     assert torch.equal(cma, cmb) and torch.equal(ba[:2], bb[:2])
     for k in ("H", "AU", "EU", "MI"):
-        assert (a[k] - b[k]).abs().max().item() < 2e-6, k
+        assert (a[k] - b[k]).abs().max().item() < 5e-6, k
 
 
 @pytest.mark.parametrize("C", [20, 6])

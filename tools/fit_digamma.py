@@ -67,3 +67,28 @@ for name, fn, deg in (("r", r_fn, 6), ("v", v_fn, 7)):
     else:
         tri = (w + f(0.5) * w * w + w * w * w * acc).astype(np.float64)
         print("  max rel |trigamma err| = %.3e" % (np.abs(tri - polygamma(1, xd)) / polygamma(1, xd)).max())
+
+
+# ---- merged value polynomial of the KL regulariser (round 2):  f(a) = -lgamma(a) + (a - 1) psi(a)
+#      f(a) = -ln(a)/2 + a - ln(2 pi)/2 - 1/2 + w u(w),  u(w) = 1/2 - r(w) + (1 - w) h(w),  u(0) = 1/3
+def u_fn(w):
+    w = mp.mpf(w)
+    if w == 0:
+        return mp.mpf(1) / 3
+    a = 1 / w
+    fa = -mp.loggamma(a) + (a - 1) * mp.digamma(a)
+    return (fa + mp.log(a) / 2 - a + HL2PI + mp.mpf(1) / 2) / w
+
+
+for deg in (6, 7, 8):
+    vals = np.array([float(u_fn(float(t))) for t in (nodes + 1) / 2])
+    cf = Polynomial(Ch.cheb2poly(Ch.chebfit(nodes, vals, deg)))(Polynomial([-1, 2.0])).coef
+    print("u deg", deg, ", ".join("%.9ef" % c for c in cf))
+    acc = np.full_like(w, f(cf[-1]))
+    for c in cf[-2::-1]:
+        acc = (acc * w + f(c)).astype(f)
+    xd = x.astype(np.float64)
+    fa = -0.5 * np.log(xd) + xd - float(HL2PI) - 0.5 + (w * acc).astype(np.float64)
+    ref = -gammaln(xd) + (xd - 1) * digamma(xd)
+    print("  max |f err| = %.3e   (max |w u| err %.3e)" % (np.abs(fa - ref).max(),
+          np.abs((w * acc).astype(np.float64) - (ref + 0.5 * np.log(xd) - xd + float(HL2PI) + 0.5)).max()))
