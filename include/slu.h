@@ -107,6 +107,9 @@ int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_labels,
 /* A/B switch (tests, profiles): 1 = single-sample inputs (T == 1) also take the multi-sample staged kernel instead
  * of the dedicated one-thread-per-pixel kernel slu_reduce_metrics picks for them. */
 int slu_debug_reduce_no_single(int on);
+/* A/B switch (tests, profiles): 1 = single-sample LOGITS take the general single-sample kernel (shared-atomic histograms)
+ * instead of the specialised one with thread-private reliability cells. */
+int slu_debug_reduce_no_private(int on);
 
 
 /* ---------------------------------------------------------------------------------------------

@@ -32,6 +32,7 @@ SIGNATURES = {
     "slu_reduce_metrics_direct": (_i, [_p, _p, _i, _i, _i, _i64, _i, _i, _f, _i, _i, _i64, _i, _p,
                                        _p, _p, _p, _p, _p, _p, _p, _p]),
     "slu_debug_reduce_no_single": (_i, [_i]),
+    "slu_debug_reduce_no_private": (_i, [_i]),
     "slu_evidential_reduce": (_i, [_p, _p, _p, _i, _i, _i64, _f, _f, _f, _i, _i, _i64, _i, _p,
                                    _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "slu_dirichlet_loss": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p]),

@@ -36,6 +36,10 @@
 namespace slu {
 
 constexpr int PT_THREADS = 256;
+#ifndef SLU_PT_BATCH
+#define SLU_PT_BATCH 4
+#endif
+constexpr int PT_BATCH = SLU_PT_BATCH;     // points (pixels) a thread handles per loop iteration in the gather / scatter kernels
 constexpr int MAX_SCANS = 256;
 constexpr double HALF_PI = 1.5707963267948966;   // np.pi / 2
 constexpr double PI = 3.141592653589793;         // np.pi
@@ -109,6 +113,7 @@ struct ProjParams {
     int use_range;
     double theta_lo, theta_hi;
     int farthest;
+    int key_sq;                    // depth keys hold the bits of r^2 (fast path: no DSQRT per point) instead of r
     // workspace
     double* theta;                 // [n_total]
     unsigned long long* rkey;      // [n_total]
@@ -332,8 +337,11 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         const Pt q = load_pt(p, b, v4);
         const double x = q.x, y = q.y, z = q.z;
         const float4 v = make_float4((float)x, (float)y, (float)z, 0.f);     // fp32 view for the prefilter
-        const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-        const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
+        // depth key: the bits of r^2 = x^2 + y^2 + z^2 in numpy's operation order (utils.py:299 before its sqrt).  sqrt is
+        // monotone, so ordering by r^2 is ordering by r except where two different r^2 round to the same r; the tie pass
+        // treats those as the ties they are in the reference (proj_ties_kernel)
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r2) & 0x7fffffffffffffffull;
         p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
         const float phi32 = atan2f(v.y, v.x);
         const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
@@ -460,26 +468,42 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         missing = __reduce_add_sync(0xffffffffu, missing);
         if ((threadIdx.x & 31) == 0 && missing) atomicAdd(&p.diag[2 * b], missing);
     }
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        // all three per-point loads are issued before the first use: one memory wait per point instead of three
-        const float t32 = p.theta32[n];
-        const int col = p.col[n];
-        const unsigned long long rk = p.rkey[n];
-        int cnt_h = fast_count_le(fh, t32);
-        if (cnt_h < 0) {
-            const int slot = atomicAdd(&s_qn, 1);
-            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
-            bool near;
-            const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
-            cnt_h = count_le(eh, th, near);
-            if (near && !p.use_range) near = !(th == lo || th == hi);
-            if (near) ++near_cnt;
+    // PT_BATCH points per thread and iteration: all their loads are issued before the first use, so a thread has
+    // 3 * PT_BATCH memory requests in flight instead of paying one L2 round trip per point
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long* key = p.key + (long long)b * p.HW;
+    for (long long nb = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; nb < n1; nb += stride * PT_BATCH) {
+        float t32[PT_BATCH];
+        int col[PT_BATCH];
+        unsigned long long rk[PT_BATCH];
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const long long n = nb + k * stride;
+            const bool in = n < n1;
+            t32[k] = in ? p.theta32[n] : 0.f;
+            col[k] = in ? p.col[n] : 0;
+            rk[k] = in ? p.rkey[n] : 0ull;
         }
-        int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
-        if (r < 0) r += p.H;
-        const int px = r * p.W + col;
-        p.pix[n] = px;
-        atomicMin(&p.key[(long long)b * p.HW + px], rk);
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const long long n = nb + k * stride;
+            if (n >= n1) continue;
+            int cnt_h = fast_count_le(fh, t32[k]);
+            if (cnt_h < 0) {
+                const int slot = atomicAdd(&s_qn, 1);
+                if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
+                bool near;
+                const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
+                cnt_h = count_le(eh, th, near);
+                if (near && !p.use_range) near = !(th == lo || th == hi);
+                if (near) ++near_cnt;
+            }
+            int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
+            if (r < 0) r += p.H;
+            const int px = r * p.W + col[k];
+            p.pix[n] = px;
+            atomicMin(&key[px], rk[k]);
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
@@ -525,8 +549,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         const Pt q = load_pt(p, b, v4);
         const double x = q.x, y = q.y, z = q.z;
         const float4 v = make_float4((float)x, (float)y, (float)z, 0.f);
-        const double r = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-        const unsigned long long rb = (unsigned long long)__double_as_longlong(r) & 0x7fffffffffffffffull;
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));     // r^2 key, see proj_fast_angles_kernel
+        const unsigned long long rb = (unsigned long long)__double_as_longlong(r2) & 0x7fffffffffffffffull;
         const unsigned long long rk = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
         p.rkey[n] = rk;                                            // the tie pass compares against it
         const float phi32 = atan2f(v.y, v.x);
@@ -575,14 +599,40 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
     }
 }
 
+// A point is a winner candidate of its pixel when its range equals the pixel's best range.  With r^2 keys (key_sq) two
+// DIFFERENT keys can stand for the same float64 range (sqrt rounds at most a few neighbouring r^2 values together); the
+// reference, which sorts by r, sees a tie there, so keys within 8 ulp of the best are compared after the square root.
+__device__ __forceinline__ bool same_range(const ProjParams& p, unsigned long long rk, unsigned long long best) {
+    if (rk == best) return true;
+    if (!p.key_sq || rk - best > 8ull) return false;           // best is the minimum: rk >= best
+    const unsigned long long a = p.farthest ? 0x7fffffffffffffffull - rk : rk;
+    const unsigned long long c = p.farthest ? 0x7fffffffffffffffull - best : best;
+    return __dsqrt_rn(__longlong_as_double((long long)a)) == __dsqrt_rn(__longlong_as_double((long long)c));
+}
+
 __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const int px = p.pix[n];
-        const unsigned long long rk = p.rkey[n];
-        const long long cell = (long long)b * p.HW + px;
-        if (rk == p.key[cell]) atomicMin(&p.winner[cell], (int)(n - n0));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned long long* key = p.key + (long long)b * p.HW;
+    int* winner = p.winner + (long long)b * p.HW;
+    for (long long nb = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; nb < n1; nb += stride * PT_BATCH) {
+        int px[PT_BATCH];
+        unsigned long long rk[PT_BATCH], best[PT_BATCH];
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const long long n = nb + k * stride;
+            const bool in = n < n1;
+            px[k] = in ? p.pix[n] : 0;
+            rk[k] = in ? p.rkey[n] : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) best[k] = (nb + k * stride < n1) ? key[px[k]] : ~0ull;
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const long long n = nb + k * stride;
+            if (n < n1 && same_range(p, rk[k], best[k])) atomicMin(&winner[px[k]], (int)(n - n0));
+        }
     }
 }
 
@@ -591,30 +641,48 @@ __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_cons
 __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b];
-    for (long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x; px < p.HW; px += (long long)gridDim.x * blockDim.x) {
-        const long long cell = (long long)b * p.HW + px;
-        int w = p.winner[cell];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        float lab = 0.f, rng = 0.f;
-        if (w == 0x7fffffff) {
-            w = -1;
-        } else {
-            v = __ldg(p.xyzi + n0 + w);
-            if (p.yaw) {                                   // the image carries float32(rotated float64 coordinate)
-                const Pt q = load_pt(p, b, v);
-                v.x = (float)q.x; v.y = (float)q.y;
-            }
-            if (p.raw_label) {
-                const unsigned raw = __ldg(p.raw_label + n0 + w) & 0xffffu;
-                lab = (float)(p.lut ? __ldg(p.lut + raw) : (int)raw);
-            }
-            rng = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int* winner = p.winner + (long long)b * p.HW;
+    // the gather is a chain of dependent loads (winner -> point -> raw label -> LUT): PT_BATCH pixels per thread go
+    // through it together, one L2 round trip per link for the whole batch
+    for (long long pb = (long long)blockIdx.x * blockDim.x + threadIdx.x; pb < p.HW; pb += stride * PT_BATCH) {
+        int w[PT_BATCH];
+        float4 v[PT_BATCH];
+        unsigned raw[PT_BATCH];
+        float lab[PT_BATCH];
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) w[k] = (pb + k * stride < p.HW) ? winner[pb + k * stride] : 0x7fffffff;
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const bool has = w[k] != 0x7fffffff;
+            v[k] = has ? __ldg(p.xyzi + n0 + w[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            raw[k] = (has && p.raw_label) ? (__ldg(p.raw_label + n0 + w[k]) & 0xffffu) : 0u;
         }
-        p.winner[cell] = w;
-        if (p.label_img) p.label_img[cell] = (long long)lab;
-        if (p.img) {
-            float* o = p.img + (long long)b * 6 * p.HW + px;
-            o[0] = v.x; o[p.HW] = v.y; o[2 * p.HW] = v.z; o[3 * p.HW] = rng; o[4 * p.HW] = v.w; o[5 * p.HW] = lab;
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const bool has = w[k] != 0x7fffffff && p.raw_label;
+            lab[k] = has ? (float)(p.lut ? __ldg(p.lut + raw[k]) : (int)raw[k]) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) {
+            const long long px = pb + k * stride;
+            if (px >= p.HW) continue;
+            float rng = 0.f;
+            float4 q = v[k];
+            if (w[k] != 0x7fffffff) {
+                if (p.yaw) {                               // the image carries float32(rotated float64 coordinate)
+                    const Pt t = load_pt(p, b, q);
+                    q.x = (float)t.x; q.y = (float)t.y;
+                }
+                rng = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)));
+            }
+            const long long cell = (long long)b * p.HW + px;
+            winner[px] = w[k] == 0x7fffffff ? -1 : w[k];
+            if (p.label_img) p.label_img[cell] = (long long)lab[k];
+            if (p.img) {
+                float* o = p.img + (long long)b * 6 * p.HW + px;
+                o[0] = q.x; o[p.HW] = q.y; o[2 * p.HW] = q.z; o[3 * p.HW] = rng; o[4 * p.HW] = q.w; o[5 * p.HW] = lab[k];
+            }
         }
     }
 }
@@ -640,8 +708,19 @@ __global__ void __launch_bounds__(PT_THREADS) backproject_kernel(const long long
                                                                  long long* __restrict__ out) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x)
-        out[n] = __ldg(label_img + (long long)b * p.HW + __ldg(pix + n));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long* img = label_img + (long long)b * p.HW;
+    for (long long nb = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; nb < n1; nb += stride * PT_BATCH) {
+        int px[PT_BATCH];
+        long long v[PT_BATCH];
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) px[k] = (nb + k * stride < n1) ? __ldg(pix + nb + k * stride) : 0;
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k) v[k] = (nb + k * stride < n1) ? __ldg(img + px[k]) : 0ll;
+#pragma unroll
+        for (int k = 0; k < PT_BATCH; ++k)
+            if (nb + k * stride < n1) out[nb + k * stride] = v[k];
+    }
 }
 
 // ---- host ------------------------------------------------------------------------------------------
@@ -711,6 +790,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
     p.gx = (int)gp.x;
     if (!generic && !exact_only()) {
+        p.key_sq = 1;
         if (p.use_range && !g_no_fused) {
             // fixed elevation range: init -> one fused pass (angles + rows + depth test) -> ties
             const long long cells = (long long)p.B * p.HW;

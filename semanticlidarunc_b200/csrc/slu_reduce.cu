@@ -519,10 +519,208 @@ __global__ void __launch_bounds__(SINGLE_THREADS, 8) reduce_single_kernel(const 
     atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, SINGLE_THREADS);
 }
 
+// ---- single-sample LOGITS with plain (not renormalised) confidence: config 1 of BASELINE.json ------------------------
+// (the single-pass branch src/models/trainer.py:1170-1225 and ECEAggregator / IoUEvaluator updates in 'logits' mode).
+// Against reduce_single_kernel above, two things change:
+//   * less arithmetic per class: the arg-max is taken over the logits while the running maximum is formed (softmax is
+//     monotone; first maximal index on ties, as torch.argmax of the probabilities gives), the confidence is
+//     e_max / S (no normalised copy of the distribution unless p_bar is asked for), NaN / infinite inputs are detected
+//     from S and A and sent to an out-of-line literal routine -- about 10 instructions per class instead of 17;
+//   * the reliability bins are PRIVATE to a thread: cells laid out [bin][thread] in shared memory (bank = lane, plain
+//     conflict-free read-modify-write, no atomics), packed n << 16 | n_correct plus a u64 fixed-point confidence sum, and
+//     the confusion matrix has one copy per warp.  The shared-atomic epilogue of the kernel above costs it a quarter of
+//     its bandwidth on 15 hot bins (0.74 -> 0.60 of the HBM peak, profiles/reduce_single_r01_ncu_summary.txt).
+// Needs bins that pass one_step_bin_search_ok() and (n_bins + 1) * 128 * 12 B of shared memory; other cases take
+// reduce_single_kernel.
+constexpr int S2_THREADS = 128;
+constexpr int S2_WARPS = S2_THREADS / 32;
+constexpr int S2_MAX_BINS = 20;                       // 21 * 128 * 12 B = 32 KB of private cells
+constexpr long long S2_MAX_PX_PER_THREAD = 32768;     // packed u16 counts cannot overflow below 65536 pixels
+
+struct S2Odd { int arg; float conf; float hb2; };
+
+// literal evaluation of one pixel (NaN / infinite logits, overflowing sums): the formulas of reduce_single_kernel
+template <int CP>
+__device__ __noinline__ S2Odd single_pixel_literal(const ReduceParams& p, const float* src) {
+    float x[CP];
+    for (int c = 0; c < CP; ++c) x[c] = c < p.C ? src[(long long)c * p.HW] : -1.0e30f;
+    float m = x[0];
+    for (int c = 1; c < CP; ++c) m = fmaxf(m, x[c]);
+    const float m2 = m * LOG2E;
+    float S = 0.f;
+    for (int c = 0; c < CP; ++c) { x[c] = ex2_approx(fmaf(x[c], LOG2E, -m2)); S += x[c]; }
+    const float inv = __frcp_rn(S);
+    for (int c = 0; c < CP; ++c) x[c] *= inv;
+    S2Odd o;
+    o.hb2 = 0.f;
+    for (int c = 0; c < p.C; ++c) { const float pc = fmaxf(x[c], p.eps); o.hb2 = fmaf(-pc, lg2_approx(pc), o.hb2); }
+    float pmax = x[0];
+    o.arg = 0;
+    for (int c = 1; c < p.C; ++c) {
+        const bool gt = (x[c] > pmax) | ((x[c] != x[c]) & (pmax == pmax));      // torch.argmax: first maximum, NaN maximal
+        pmax = gt ? x[c] : pmax;
+        o.arg = gt ? c : o.arg;
+    }
+    o.conf = pmax;
+    return o;
+}
+
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(S2_THREADS, 7) reduce_single_logits_kernel(const __grid_constant__ ReduceParams p) {
+    extern __shared__ __align__(16) unsigned char s2_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cells = p.C * p.C;
+    const int nb1 = p.n_bins + 1;                                     // + one spare row for pixels that do not count
+    unsigned long long* bsum = reinterpret_cast<unsigned long long*>(s2_smem);
+    unsigned* bnc = reinterpret_cast<unsigned*>(s2_smem + (p.bins ? nb1 * S2_THREADS * 8 : 0));
+    unsigned* cm = reinterpret_cast<unsigned*>(s2_smem + (p.bins ? nb1 * S2_THREADS * 12 : 0));
+    float* edges = reinterpret_cast<float*>(cm + (p.confmat ? cells * S2_WARPS : 0));
+    if (p.bins)
+        for (int i = tid; i < nb1 * S2_THREADS; i += S2_THREADS) { bnc[i] = 0; bsum[i] = 0ull; }
+    if (p.confmat)
+        for (int i = tid; i < cells * S2_WARPS; i += S2_THREADS) cm[i] = 0;
+    for (int i = tid; i <= p.n_bins; i += S2_THREADS) edges[i] = p.edges[i];
+    __syncthreads();
+    unsigned* my_cm = cm + warp * cells;
+    const float nb_f = (float)p.n_bins;
+    const long long tiles_per_scan = (p.HW + S2_THREADS - 1) / S2_THREADS;
+    const long long n_tiles = tiles_per_scan * p.B;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_scan);
+        const long long px = (tile - (long long)b * tiles_per_scan) * S2_THREADS + tid;
+        const bool live = px < p.HW;
+        const float* src = p.in + ((long long)b * p.C) * p.HW + (live ? px : p.HW - 1);
+        const long long o = (long long)b * p.HW + px;
+        const bool has_lab = p.labels && live;
+        const long long lab = has_lab ? p.labels[o] : 0;
+        float x[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) x[c] = (EXACT || c < p.C) ? ldg_stream(src + (long long)c * p.HW) : -1.0e30f;
+        float m = x[0];
+        int arg = 0;
+#pragma unroll
+        for (int c = 1; c < CP; ++c) {
+            const bool gt = x[c] > m;
+            m = gt ? x[c] : m;
+            arg = gt ? c : arg;
+        }
+        const float m2 = m * LOG2E;
+        float S = 0.f, A = 0.f;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            const float a = fmaf(x[c], LOG2E, -m2);
+            const float e = ex2_approx(a);
+            x[c] = e;
+            S += e;
+            A = fmaf(e, a, A);
+        }
+        const float inv = __frcp_rn(S);
+        float conf = ex2_approx(fmaf(m, LOG2E, -m2)) * inv;             // p at the arg-max, the product reduce_single_kernel forms
+        float Hb2 = fmaf(-A, inv, lg2_approx(S));                        // H[p] = ln S - ln2 A/S in log2 units
+        if (!(fabsf(Hb2) <= 3.0e38f) || !(S <= 3.0e38f)) {               // NaN / infinite logits: literal routine, out of line
+            const S2Odd odd = single_pixel_literal<CP>(p, src);
+            arg = odd.arg; conf = odd.conf; Hb2 = odd.hb2;
+        }
+        if (live) {
+            if (p.pbar) {                                                // CTA-uniform
+                float* dst = p.pbar + (long long)b * p.C * p.HW + px;
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+                    if (EXACT || c < p.C) dst[(long long)c * p.HW] = x[c] * inv;
+            }
+            if (p.pred) p.pred[o] = arg;
+            if (p.conf) p.conf[o] = conf;
+            if (p.hnorm) p.hnorm[o] = __fdiv_rn(Hb2 * LN2, p.logC);
+            if (p.minorm) p.minorm[o] = 0.f;                             // H[p_bar] and H[p_1] are the same number
+        }
+        if (p.labels) {
+            if (p.confmat && has_lab && (unsigned long long)lab < (unsigned long long)p.C) atomicAdd(&my_cm[(int)lab * p.C + arg], 1u);   // evaluator.py:49
+            if (p.bins) {
+                const float c = __saturatef(conf);                        // ece.py:83 clamp_(0,1); NaN -> 0, dropped below
+                int k = (int)(c * nb_f);
+                k = k > p.n_bins - 1 ? p.n_bins - 1 : k;
+                const float lo = edges[k], hi = edges[k + 1];
+                k += (c >= hi && k < p.n_bins - 1) ? 1 : 0;             // the host has checked one_step_bin_search_ok()
+                k -= (c < lo && k > 0) ? 1 : 0;
+                const bool ok = has_lab && conf == conf && c >= edges[0] && c <= edges[p.n_bins] &&
+                                !(p.has_ignore && lab == p.ignore);
+                const int cell = (ok ? k : p.n_bins) * S2_THREADS + tid;
+                bnc[cell] += 0x10000u + ((long long)arg == lab ? 1u : 0u);
+                bsum[cell] += __float2ull_rn(c * 4294967296.0f);
+            }
+        }
+    }
+    __syncthreads();
+    if (p.confmat)
+        for (int i = tid; i < cells; i += S2_THREADS) {
+            unsigned v = 0;
+#pragma unroll
+            for (int k = 0; k < S2_WARPS; ++k) v += cm[k * cells + i];
+            if (v) atomicAdd(&p.confmat[i], (unsigned long long)v);
+        }
+    if (p.bins)
+        for (int bn = warp; bn < p.n_bins; bn += S2_WARPS) {
+            unsigned n = 0, c = 0;
+            unsigned long long sfx = 0ull;
+#pragma unroll
+            for (int k = 0; k < S2_THREADS / 32; ++k) {
+                const unsigned v = bnc[bn * S2_THREADS + k * 32 + lane];
+                n += v >> 16; c += v & 0xffffu;
+                sfx += bsum[bn * S2_THREADS + k * 32 + lane];
+            }
+            n = __reduce_add_sync(0xffffffffu, n);
+            c = __reduce_add_sync(0xffffffffu, c);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sfx += __shfl_xor_sync(0xffffffffu, sfx, off);
+            if (lane == 0 && n) {
+                atomicAdd(&p.bins[bn], (unsigned long long)n);
+                if (c) atomicAdd(&p.bins[p.n_bins + bn], (unsigned long long)c);
+                atomicAdd(&p.bins[2 * p.n_bins + bn], sfx);
+            }
+        }
+}
+
+static int g_single_no_private = 0;       // A/B switch (slu_debug_reduce_no_private): 1 = reduce_single_kernel for every T == 1 call
+
+template <int CP>
+static int launch_single_logits(const ReduceParams& p, cudaStream_t stream, bool& taken) {
+    taken = false;
+    const long long n_tiles = ((p.HW + S2_THREADS - 1) / S2_THREADS) * p.B;
+    const int sms = sm_count_current_device();
+    if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    if (g_single_no_private || p.conf_mode != SLU_CONF_RAW || p.literal_clamp || p.n_bins > S2_MAX_BINS ||
+        (p.bins && !p.bins_one_step))
+        return 0;
+    const long long max_ctas = 7LL * sms;
+    const long long grid = n_tiles < max_ctas ? n_tiles : max_ctas;
+    if ((n_tiles + grid - 1) / grid > S2_MAX_PX_PER_THREAD) return 0;     // packed counts could overflow: the other kernel flushes
+    const int smem = (p.bins ? (p.n_bins + 1) * S2_THREADS * 12 : 0) + (p.confmat ? p.C * p.C * S2_WARPS * 4 : 0) +
+                     (SLU_MAX_BINS + 1) * 4 + 16;
+    static bool attr_set[64][2] = {};
+    int dev = 0;
+    SLU_CUDA(cudaGetDevice(&dev));
+    const bool exact = p.C == CP;
+    if (dev < 64 && !attr_set[dev][exact ? 1 : 0]) {
+        if (exact) SLU_CUDA(cudaFuncSetAttribute(reduce_single_logits_kernel<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        else SLU_CUDA(cudaFuncSetAttribute(reduce_single_logits_kernel<CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set[dev][exact ? 1 : 0] = true;
+    }
+    if (exact) reduce_single_logits_kernel<CP, true><<<(unsigned)grid, S2_THREADS, smem, stream>>>(p);
+    else reduce_single_logits_kernel<CP, false><<<(unsigned)grid, S2_THREADS, smem, stream>>>(p);
+    SLU_LAUNCH_CHECK("reduce_single_logits_kernel");
+    taken = true;
+    return 0;
+}
+
 template <int CP, int KIND>
 static int launch_single(const ReduceParams& p, cudaStream_t stream) {
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
+    if (KIND == SLU_IN_LOGITS) {
+        bool taken = false;
+        const int rc = launch_single_logits<CP>(p, stream, taken);
+        if (rc || taken) return rc;
+    }
     const long long n_tiles = ((p.HW + SINGLE_THREADS - 1) / SINGLE_THREADS) * p.B;
     const long long max_ctas = 8LL * sms;
     const int grid = (int)(n_tiles < max_ctas ? n_tiles : max_ctas);
@@ -654,6 +852,13 @@ extern "C" int slu_reduce_metrics_direct(const float* d_in, const int64_t* d_lab
 }
 
 /* A/B switch for tests and profiles: 1 = T == 1 inputs also go through the multi-sample (staged) kernel. */
+/* A/B switch (tests, profiles): 1 = T == 1 logits take reduce_single_kernel (shared-atomic histograms) instead of the
+ * private-cell kernel. */
+extern "C" int slu_debug_reduce_no_private(int on) {
+    slu::g_single_no_private = on ? 1 : 0;
+    return 0;
+}
+
 extern "C" int slu_debug_reduce_no_single(int on) {
     slu::g_reduce_no_single = on ? 1 : 0;
     return 0;

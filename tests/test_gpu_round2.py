@@ -291,3 +291,34 @@ def test_drop_in_projection_settles_points_on_bin_edges_like_numpy(cuda):
     # ... and a scan without them is not touched by the host at all
     img0, *_ = spherical_projection(pc, H, W)
     assert spherical_projection.last_near_edge == 0 and np.array_equal(img0, oproj.spherical_projection(pc, H, W)[0])
+
+
+# ---------------------------------------------------------------------------------------------- single-sample logits kernel
+@pytest.mark.parametrize("shape", [(16, 20, 64, 2048), (3, 7, 5, 37), (1, 20, 9, 130)])
+def test_single_sample_logits_kernel_agrees_with_general_single_kernel(cuda, shape):
+    """reduce_single_logits_kernel (arg-max on the logits, e_max / S confidence, thread-private reliability cells) against
+    reduce_single_kernel (arg-max on the probabilities, shared-atomic histograms): identical confidence / entropy maps,
+    identical counters up to pixels whose two best probabilities round to the same float."""
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(B * 31 + C)
+    x = (torch.randn((B, C, H, W), generator=g) * 3.0).to(cuda)
+    lab = torch.randint(-1, C + 1, (B, H, W), generator=g).to(cuda)
+    x[0, :, 0, 0] = float("nan"); x[0, 1, 0, 1] = float("inf"); x[0, :, 0, 2] = -float("inf")
+    out = []
+    for off in (0, 1):
+        _lib.lib().slu_debug_reduce_no_private(off)
+        cm, bins = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+        r = ops.reduce_metrics(x, lab, kind="logits", ignore_index=0, confmat=cm, ece_bins=bins, want=("p_bar", "pred", "conf", "H_norm", "MI_norm"))
+        out.append((r, cm, bins))
+    _lib.lib().slu_debug_reduce_no_private(0)
+    (a, cma, ba), (b, cmb, bb) = out
+    same = a["pred"] == b["pred"]
+    assert int((~same).sum()) <= max(3, same.numel() // 20000)
+    for k in ("conf", "H_norm", "MI_norm"):
+        assert torch.equal(torch.nan_to_num(a[k][same], nan=-7.0), torch.nan_to_num(b[k][same], nan=-7.0)), k
+    assert torch.equal(torch.nan_to_num(a["p_bar"], nan=-7.0), torch.nan_to_num(b["p_bar"], nan=-7.0))
+    assert int(cma.sum()) == int(cmb.sum()) and int((cma - cmb).abs().sum()) <= 2 * int((~same).sum())
+    assert torch.equal(ba[0], bb[0]) and torch.equal(ba[2], bb[2]) and int((ba[1] - bb[1]).abs().sum()) <= int((~same).sum())
+    ref = ou.mc_reduce(x[None].cpu())
+    ok = torch.isfinite(ref["H_norm"])
+    assert (a["H_norm"].cpu()[ok] - ref["H_norm"][ok]).abs().max() < 1e-5
