@@ -328,6 +328,9 @@ int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW);
  * of the fp32-prefiltered ones (bit-identical results, ~2x slower); on=0 restores the default; on<0 only
  * queries.  Returns the previous setting.  Process-wide host state, not for concurrent use. */
 int slu_debug_project_exact(int on);
+/* diagnostic: out[i] = the projection prefilter's fp32 arctangent of (y[i], x[i]); NaN for zero / denormal / huge / non-finite
+ * inputs (those points always take the fp64 path).  Tests bound its error against float64 atan2. */
+int slu_diag_fast_atan2(const float* d_y, const float* d_x, int64_t n, float* d_out, slu_stream_t stream);
 int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_label, const int32_t* d_lut,
                       const int64_t* h_offsets, int64_t n_total, int B, int H, int W,
                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,

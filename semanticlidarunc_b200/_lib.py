@@ -53,6 +53,7 @@ SIGNATURES = {
     "slu_class_score_hist": (_i, [_p, _p, _i64, _i, _i, _p, _p, _p]),
     "slu_project_workspace_bytes": (_i64, [_i64, _i, _i64]),
     "slu_debug_project_exact": (_i, [_i]),
+    "slu_diag_fast_atan2": (_i, [_p, _p, _i64, _p, _p]),
     "slu_project_batch": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p,
                                _p, _p, _p, _p, _p, _p, _p]),
     "slu_project_points": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p]),

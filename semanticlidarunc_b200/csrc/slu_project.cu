@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
 // ====================================================================================================
 // Fast path of the batched entry point.  Two double atan2 per point made the exact kernels FP64-bound
 // (46 us for 1.9 M points).  Here every point is first classified with fp32 angles; their error is
-// bounded (atan2f <= 3 ulp of pi = 7.2e-7 rad, plus 1.2e-7 for sqrtf and the pi/2 subtraction), so a
+// bounded (fast_atan2 <= 5.9e-7 rad, plus 2.4e-7 for sqrtf and the pi/2 subtraction), so a
 // point whose fp32 angle lies more than ANGLE_MARGIN from every bin edge is in the same bin as its fp64
 // angle and never needs the fp64 evaluation; the others (~0.5 % of columns, ~0.2 % of rows) take the
 // exact path unchanged.  The scan's theta min/max are found the same way: fp32 min/max first, then only
@@ -273,6 +273,29 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
 // ====================================================================================================
 constexpr double ANGLE_MARGIN = 8.0e-6;     // rad; >= 7x the fp32 angle error bound
 constexpr int DEFER_CAP = 1024;             // per-block queue of near-edge points (overflow is handled inline)
+
+// fp32 arctangent of the prefilter: atan(t) = t P(t^2) on [0,1] (degree-6 P, tools/fit_atan.py) plus octant folding,
+// ~20 instructions against ~100 for atan2f with its special-case handling.  Certified maximum error 5.9e-7 rad over
+// +-pi including a 2-ulp error of the approximate division (tools/fit_atan.py; tests/test_gpu_round2.py measures it on
+// the device), i.e. 13x below ANGLE_MARGIN.  Zero, denormal, huge, infinite or NaN inputs return NaN, which no bin test
+// accepts: such points always take the exact fp64 path.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    if (!(mx > 1.0e-30f && mx < 1.0e30f)) return __int_as_float(0x7fc00000);
+    const float q = __fdividef(mn, mx);
+    const float t = q * q;
+    float a = fmaf(6.811646790e-03f, t, -3.360372957e-02f);
+    a = fmaf(a, t, 7.962303474e-02f);
+    a = fmaf(a, t, -1.323330193e-01f);
+    a = fmaf(a, t, 1.980780307e-01f);
+    a = fmaf(a, t, -3.331736634e-01f);
+    a = fmaf(a, t, 9.999961108e-01f);
+    float r = a * q;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return y < 0.f ? -r : r;
+}
 
 __device__ __forceinline__ double exact_phi(const Pt q) { return atan2(q.y, q.x); }
 __device__ __forceinline__ double exact_theta(const Pt q) {
@@ -343,8 +366,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
         const unsigned long long rb = (unsigned long long)__double_as_longlong(r2) & 0x7fffffffffffffffull;
         p.rkey[n] = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
-        const float phi32 = atan2f(v.y, v.x);
-        const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
+        const float phi32 = fast_atan2(v.y, v.x);
+        const float th32 = 1.57079632679489662f - fast_atan2(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
         p.theta32[n] = th32;
         pend_lut = check_ids ? __ldg(p.lut + raw) : 0;          // tested at the top of the next iteration
         if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
@@ -553,8 +576,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         const unsigned long long rb = (unsigned long long)__double_as_longlong(r2) & 0x7fffffffffffffffull;
         const unsigned long long rk = p.farthest ? (0x7fffffffffffffffull - rb) : rb;
         p.rkey[n] = rk;                                            // the tie pass compares against it
-        const float phi32 = atan2f(v.y, v.x);
-        const float th32 = 1.57079632679489662f - atan2f(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
+        const float phi32 = fast_atan2(v.y, v.x);
+        const float th32 = 1.57079632679489662f - fast_atan2(sqrtf(fmaf(v.x, v.x, v.y * v.y)), v.z);
         pend_lut = check_ids ? __ldg(p.lut + raw) : 0;
         int cnt_w = fast_count_le(fw, phi32);
         int cnt_h = fast_count_le(fh, th32);
@@ -751,11 +774,15 @@ static Workspace carve(int64_t n_total, int B, int64_t HW) {
     return w;
 }
 
+// CTAs per SM the point kernels are sized for (8 = one resident wave of 256-thread CTAs; more = several waves of shorter
+// CTAs).  SLU_PT_CTAS_PER_SM overrides it for experiments.
+static int g_pt_ctas_per_sm = [] { const char* e = getenv("SLU_PT_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+
 static int point_grid_x(const long long* offsets, int B, int sms) {
     long long max_n = 1;
     for (int b = 0; b < B; ++b) max_n = offsets[b + 1] - offsets[b] > max_n ? offsets[b + 1] - offsets[b] : max_n;
     long long gx = (max_n + PT_THREADS - 1) / PT_THREADS;
-    const long long cap = (8LL * sms + B - 1) / B;           // ~8 resident CTAs per SM over the batch
+    const long long cap = ((long long)g_pt_ctas_per_sm * sms + B - 1) / B;   // CTAs per SM over the batch
     if (gx > cap) gx = cap;
     if (gx > MAX_GX) gx = MAX_GX;
     return (int)(gx < 1 ? 1 : gx);
@@ -878,7 +905,7 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     if (rc) return rc;
     const int sms = sm_count_current_device();
     long long gx = (p.HW + PT_THREADS - 1) / PT_THREADS;
-    const long long cap = (8LL * sms + B - 1) / B;
+    const long long cap = ((long long)g_pt_ctas_per_sm * sms + B - 1) / B;
     if (gx > cap) gx = cap;
     proj_resolve_planes_kernel<<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("proj_resolve_planes_kernel");
@@ -938,5 +965,20 @@ extern "C" int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix,
     backproject_kernel<<<g, PT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const long long*>(d_label_img), d_pix, p, reinterpret_cast<long long*>(d_out));
     SLU_LAUNCH_CHECK("backproject_kernel");
+    return 0;
+}
+
+/* diagnostic: the prefilter's fp32 arctangent on arrays (tests measure its error against float64 atan2) */
+namespace slu {
+__global__ void fast_atan2_kernel(const float* __restrict__ y, const float* __restrict__ x, long long n, float* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fast_atan2(y[i], x[i]);
+}
+}  // namespace slu
+extern "C" int slu_diag_fast_atan2(const float* d_y, const float* d_x, int64_t n, float* d_out, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_y || !d_x || !d_out || n < 1) return fail(SLU_E_ARG, "slu_diag_fast_atan2: bad arguments");
+    fast_atan2_kernel<<<1024, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_y, d_x, n, d_out);
+    SLU_LAUNCH_CHECK("fast_atan2_kernel");
     return 0;
 }

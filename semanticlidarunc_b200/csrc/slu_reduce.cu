@@ -31,6 +31,7 @@
 // divides; <= 1 ulp apart) and ln(p_bar) uses lg2.approx (relative error <= 2^-22): both far inside
 // the 1e-5 relative tolerance BASELINE.json states.
 #include <math.h>
+#include <stdlib.h>
 #include "slu_common.cuh"
 
 namespace slu {
@@ -680,6 +681,165 @@ __global__ void __launch_bounds__(S2_THREADS, 7) reduce_single_logits_kernel(con
         }
 }
 
+// ---- the same kernel with FOUR consecutive pixels per thread: 16-byte loads and stores ---------------------------------
+// One-pixel threads issue 4-byte requests (a warp touches 128 B per class plane); at 108 B/pixel that tops out near
+// 0.74 of the HBM peak even without histograms.  Here a thread owns 4 adjacent pixels: one LDG.128 per class, float4 /
+// longlong2 stores, 320 B in flight per thread, 256-thread CTAs that live for many tiles (the private reliability cells
+// are zeroed and reduced once per CTA).  Used when HW % 4 == 0, the buffers are 16-byte aligned and the launch has
+// enough pixels to fill the machine; smaller or ragged inputs take the kernels above.
+constexpr int S4_THREADS = 256;
+constexpr int S4_WARPS = S4_THREADS / 32;
+constexpr int S4_PX = 4;
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(S4_THREADS, 2) reduce_single_logits4_kernel(const __grid_constant__ ReduceParams p) {
+    extern __shared__ __align__(16) unsigned char s2_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cells = p.C * p.C;
+    const int nb1 = p.n_bins + 1;
+    unsigned long long* bsum = reinterpret_cast<unsigned long long*>(s2_smem);
+    unsigned* bnc = reinterpret_cast<unsigned*>(s2_smem + (p.bins ? nb1 * S4_THREADS * 8 : 0));
+    unsigned* cm = reinterpret_cast<unsigned*>(s2_smem + (p.bins ? nb1 * S4_THREADS * 12 : 0));
+    float* edges = reinterpret_cast<float*>(cm + (p.confmat ? cells * S4_WARPS : 0));
+    if (p.bins)
+        for (int i = tid; i < nb1 * S4_THREADS; i += S4_THREADS) { bnc[i] = 0; bsum[i] = 0ull; }
+    if (p.confmat)
+        for (int i = tid; i < cells * S4_WARPS; i += S4_THREADS) cm[i] = 0;
+    for (int i = tid; i <= p.n_bins; i += S4_THREADS) edges[i] = p.edges[i];
+    __syncthreads();
+    unsigned* my_cm = cm + warp * cells;
+    const float nb_f = (float)p.n_bins;
+    constexpr int TILE_PX = S4_THREADS * S4_PX;
+    const long long tiles_per_scan = (p.HW + TILE_PX - 1) / TILE_PX;
+    const long long n_tiles = tiles_per_scan * p.B;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = (int)(tile / tiles_per_scan);
+        const long long px = (tile - (long long)b * tiles_per_scan) * TILE_PX + (long long)tid * S4_PX;
+        const bool live = px < p.HW;                                   // HW % 4 == 0: a thread's 4 pixels are all in or all out
+        const float* src = p.in + ((long long)b * p.C) * p.HW + (live ? px : p.HW - S4_PX);
+        const long long o = (long long)b * p.HW + px;
+        const bool has_lab = p.labels && live;
+        long long lab[S4_PX] = {0, 0, 0, 0};
+        if (has_lab) {
+            const longlong2 l0 = *reinterpret_cast<const longlong2*>(p.labels + o), l1 = *reinterpret_cast<const longlong2*>(p.labels + o + 2);
+            lab[0] = l0.x; lab[1] = l0.y; lab[2] = l1.x; lab[3] = l1.y;
+        }
+        float x[CP][S4_PX];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            if (EXACT || c < p.C) {
+                const float4 v = ldg_stream4(src + (long long)c * p.HW);
+                x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
+            } else {
+                x[c][0] = x[c][1] = x[c][2] = x[c][3] = -1.0e30f;
+            }
+        }
+        int arg[S4_PX];
+        float conf[S4_PX], hn[S4_PX], inv[S4_PX];
+#pragma unroll
+        for (int k = 0; k < S4_PX; ++k) {
+            float m = x[0][k];
+            int a = 0;
+#pragma unroll
+            for (int c = 1; c < CP; ++c) {
+                const bool gt = x[c][k] > m;
+                m = gt ? x[c][k] : m;
+                a = gt ? c : a;
+            }
+            const float m2 = m * LOG2E;
+            float S = 0.f, A = 0.f;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const float t = fmaf(x[c][k], LOG2E, -m2);
+                const float e = ex2_approx(t);
+                x[c][k] = e;
+                S += e;
+                A = fmaf(e, t, A);
+            }
+            inv[k] = __frcp_rn(S);
+            conf[k] = ex2_approx(fmaf(m, LOG2E, -m2)) * inv[k];
+            float Hb2 = fmaf(-A, inv[k], lg2_approx(S));
+            if (!(fabsf(Hb2) <= 3.0e38f) || !(S <= 3.0e38f)) {           // NaN / infinite logits: literal routine, out of line
+                const S2Odd odd = single_pixel_literal<CP>(p, src + k);
+                a = odd.arg; conf[k] = odd.conf; Hb2 = odd.hb2;
+            }
+            arg[k] = a;
+            hn[k] = __fdiv_rn(Hb2 * LN2, p.logC);
+        }
+        if (live) {
+            if (p.pbar) {                                                // CTA-uniform
+                float* dst = p.pbar + (long long)b * p.C * p.HW + px;
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+                    if (EXACT || c < p.C)
+                        *reinterpret_cast<float4*>(dst + (long long)c * p.HW) =
+                            make_float4(x[c][0] * inv[0], x[c][1] * inv[1], x[c][2] * inv[2], x[c][3] * inv[3]);
+            }
+            if (p.pred) {
+                *reinterpret_cast<longlong2*>(p.pred + o) = make_longlong2(arg[0], arg[1]);
+                *reinterpret_cast<longlong2*>(p.pred + o + 2) = make_longlong2(arg[2], arg[3]);
+            }
+            if (p.conf) *reinterpret_cast<float4*>(p.conf + o) = make_float4(conf[0], conf[1], conf[2], conf[3]);
+            if (p.hnorm) *reinterpret_cast<float4*>(p.hnorm + o) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            if (p.minorm) *reinterpret_cast<float4*>(p.minorm + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.labels) {
+#pragma unroll
+            for (int k = 0; k < S4_PX; ++k) {
+                if (p.confmat && has_lab && (unsigned long long)lab[k] < (unsigned long long)p.C) atomicAdd(&my_cm[(int)lab[k] * p.C + arg[k]], 1u);
+                if (p.bins) {
+                    const float c = __saturatef(conf[k]);
+                    int kk = (int)(c * nb_f);
+                    kk = kk > p.n_bins - 1 ? p.n_bins - 1 : kk;
+                    const float lo = edges[kk], hi = edges[kk + 1];
+                    kk += (c >= hi && kk < p.n_bins - 1) ? 1 : 0;
+                    kk -= (c < lo && kk > 0) ? 1 : 0;
+                    const bool ok = has_lab && conf[k] == conf[k] && c >= edges[0] && c <= edges[p.n_bins] &&
+                                    !(p.has_ignore && lab[k] == p.ignore);
+                    const int cell = (ok ? kk : p.n_bins) * S4_THREADS + tid;
+                    bnc[cell] += 0x10000u + ((long long)arg[k] == lab[k] ? 1u : 0u);
+                    bsum[cell] += __float2ull_rn(c * 4294967296.0f);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (p.confmat)
+        for (int i = tid; i < cells; i += S4_THREADS) {
+            unsigned v = 0;
+#pragma unroll
+            for (int k = 0; k < S4_WARPS; ++k) v += cm[k * cells + i];
+            if (v) atomicAdd(&p.confmat[i], (unsigned long long)v);
+        }
+    if (p.bins)
+        for (int bn = warp; bn < p.n_bins; bn += S4_WARPS) {
+            unsigned n = 0, c = 0;
+            unsigned long long sfx = 0ull;
+#pragma unroll
+            for (int k = 0; k < S4_THREADS / 32; ++k) {
+                const unsigned v = bnc[bn * S4_THREADS + k * 32 + lane];
+                n += v >> 16; c += v & 0xffffu;
+                sfx += bsum[bn * S4_THREADS + k * 32 + lane];
+            }
+            n = __reduce_add_sync(0xffffffffu, n);
+            c = __reduce_add_sync(0xffffffffu, c);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sfx += __shfl_xor_sync(0xffffffffu, sfx, off);
+            if (lane == 0 && n) {
+                atomicAdd(&p.bins[bn], (unsigned long long)n);
+                if (c) atomicAdd(&p.bins[p.n_bins + bn], (unsigned long long)c);
+                atomicAdd(&p.bins[2 * p.n_bins + bn], sfx);
+            }
+        }
+}
+
+static int g_single_no_px4 = [] { const char* e = getenv("SLU_SINGLE_NO_PX4"); return (e && e[0] == '1') ? 1 : 0; }();   // A/B: one pixel per thread
 static int g_single_no_private = 0;       // A/B switch (slu_debug_reduce_no_private): 1 = reduce_single_kernel for every T == 1 call
 
 template <int CP>
@@ -691,6 +851,32 @@ static int launch_single_logits(const ReduceParams& p, cudaStream_t stream, bool
     if (g_single_no_private || p.conf_mode != SLU_CONF_RAW || p.literal_clamp || p.n_bins > S2_MAX_BINS ||
         (p.bins && !p.bins_one_step))
         return 0;
+    // four pixels per thread when the launch is large enough to keep 2 CTAs of 256 threads per SM busy for several tiles
+    const uintptr_t al = reinterpret_cast<uintptr_t>(p.in) | reinterpret_cast<uintptr_t>(p.labels) | reinterpret_cast<uintptr_t>(p.pbar) |
+                         reinterpret_cast<uintptr_t>(p.pred) | reinterpret_cast<uintptr_t>(p.conf) | reinterpret_cast<uintptr_t>(p.hnorm) |
+                         reinterpret_cast<uintptr_t>(p.minorm);
+    const long long tiles4 = ((p.HW + S4_THREADS * S4_PX - 1) / (S4_THREADS * S4_PX)) * p.B;
+    if (!g_single_no_px4 && (p.HW & 3) == 0 && (al & 15) == 0 && tiles4 >= 8LL * sms) {
+        const long long grid4 = 2LL * sms;
+        if ((tiles4 + grid4 - 1) / grid4 * S4_PX <= S2_MAX_PX_PER_THREAD) {
+            const int smem4 = (p.bins ? (p.n_bins + 1) * S4_THREADS * 12 : 0) + (p.confmat ? p.C * p.C * S4_WARPS * 4 : 0) +
+                              (SLU_MAX_BINS + 1) * 4 + 16;
+            static bool attr4[64][2] = {};
+            int dev4 = 0;
+            SLU_CUDA(cudaGetDevice(&dev4));
+            const bool ex4 = p.C == CP;
+            if (dev4 < 64 && !attr4[dev4][ex4 ? 1 : 0]) {
+                if (ex4) SLU_CUDA(cudaFuncSetAttribute(reduce_single_logits4_kernel<CP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                else SLU_CUDA(cudaFuncSetAttribute(reduce_single_logits4_kernel<CP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr4[dev4][ex4 ? 1 : 0] = true;
+            }
+            if (ex4) reduce_single_logits4_kernel<CP, true><<<(unsigned)grid4, S4_THREADS, smem4, stream>>>(p);
+            else reduce_single_logits4_kernel<CP, false><<<(unsigned)grid4, S4_THREADS, smem4, stream>>>(p);
+            SLU_LAUNCH_CHECK("reduce_single_logits4_kernel");
+            taken = true;
+            return 0;
+        }
+    }
     const long long max_ctas = 7LL * sms;
     const long long grid = n_tiles < max_ctas ? n_tiles : max_ctas;
     if ((n_tiles + grid - 1) / grid > S2_MAX_PX_PER_THREAD) return 0;     // packed counts could overflow: the other kernel flushes

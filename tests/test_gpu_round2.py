@@ -322,3 +322,23 @@ def test_single_sample_logits_kernel_agrees_with_general_single_kernel(cuda, sha
     ref = ou.mc_reduce(x[None].cpu())
     ok = torch.isfinite(ref["H_norm"])
     assert (a["H_norm"].cpu()[ok] - ref["H_norm"][ok]).abs().max() < 1e-5
+
+
+def test_prefilter_arctangent_error_bound(cuda):
+    """The fp32 arctangent that decides which points may skip the fp64 angles: its error must stay far below the
+    prefilter's margin (8e-6 rad), and degenerate inputs must come out as NaN (-> exact path)."""
+    g = torch.Generator().manual_seed(0)
+    n = 4_000_000
+    ang = torch.rand(n, generator=g, dtype=torch.float64) * (2 * np.pi) - np.pi
+    rad = 10 ** (torch.rand(n, generator=g, dtype=torch.float64) * 4.5 - 2)
+    x, y = (rad * torch.cos(ang)).float(), (rad * torch.sin(ang)).float()
+    x[:4] = torch.tensor([0.0, float("inf"), float("nan"), 1e38]); y[:4] = torch.tensor([0.0, 1.0, 1.0, 1.0])
+    out = torch.empty(n, dtype=torch.float32, device=cuda)
+    xd, yd = x.to(cuda), y.to(cuda)
+    _lib.check(_lib.lib().slu_diag_fast_atan2(_lib.ptr(yd), _lib.ptr(xd), n, _lib.ptr(out), _lib.stream_ptr()), "slu_diag_fast_atan2")
+    out = out.cpu()
+    assert bool(torch.isnan(out[:4]).all())
+    ref = torch.atan2(y[4:].double(), x[4:].double())
+    err = (out[4:].double() - ref).abs()
+    err = torch.minimum(err, 2 * np.pi - err)
+    assert float(err.max()) < 1.0e-6, float(err.max())
