@@ -345,6 +345,15 @@ int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
                        void* d_work,
                        float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
                        slu_stream_t stream);
+/* slu_project_points with caller-supplied ROW edges (the reference's bins_h argument, src/dataset/utils.py:330-338:
+ * idx_h = np.digitize(theta, bins_h) - 1).  d_row_edges_ascending [H] float64 holds the edges in ASCENDING order;
+ * edges_were_increasing says how the caller's array ran (the reference builds a DEcreasing one: idx = H - 1 - #{e <= theta};
+ * for an increasing array idx = #{e <= theta} - 1; -1 wraps to H - 1 either way).  NULL edges = slu_project_points. */
+int slu_project_points_bins(const double* d_pc, int64_t N, int Cin, int H, int W,
+                            int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                            const double* d_row_edges_ascending, int edges_were_increasing, void* d_work,
+                            float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                            slu_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Loader glue behind the projection.

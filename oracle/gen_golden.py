@@ -471,6 +471,26 @@ def gen_aurc():
     np.savez_compressed(os.path.join(GOLD, "aurc.npz"), **out)
 
 
+def gen_per_class():
+    """UncertaintyPerClassAggregator (src/models/evaluator.py:191-281): per-class sample counts, means and quartiles of
+    the reference's per-pixel arrays, and the class order plot_iou_sorted_by_uncertainty derives from them (:559-566)."""
+    from models.evaluator import UncertaintyPerClassAggregator
+    g = torch.Generator().manual_seed(808)
+    C = 20
+    labels = torch.randint(-1, C + 1, (4, 16, 256), generator=g)              # includes ids outside [0, C)
+    base = torch.rand((4, 16, 256), generator=g)
+    unc = (base ** (1.0 + 0.15 * labels.clamp(0, C - 1).float())).float()    # class-dependent distributions
+    agg = UncertaintyPerClassAggregator(C)
+    agg.update(labels[:1], unc[:1])
+    agg.update(labels[1:], unc[1:])
+    vals = [agg._values[c].double().numpy() for c in range(C)]
+    stats = np.array([[v.size, v.mean(), np.quantile(v, 0.25), np.median(v), np.quantile(v, 0.75)] for v in vals])
+    df = agg.as_dataframe([str(i) for i in range(C)], ignore_ids=(0,))
+    order = df.groupby("class_id")["uncertainty"].mean().sort_values().index.to_numpy()
+    np.savez_compressed(os.path.join(GOLD, "per_class.npz"), labels=labels.numpy(), unc=unc.numpy(), stats=stats,
+                        seen=np.array(agg._seen_counts), order_by_mean=order, df_rows=np.array(len(df)))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(1)
@@ -493,6 +513,7 @@ def main():
     gen_losses()
     gen_loss_terms()
     gen_aurc()
+    gen_per_class()
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     for fn in sorted(os.listdir(GOLD)):

@@ -57,6 +57,7 @@ SIGNATURES = {
     "slu_project_batch": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p,
                                _p, _p, _p, _p, _p, _p, _p]),
     "slu_project_points": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "slu_project_points_bins": (_i, [_p, _i64, _i, _i, _i, _i, _d, _d, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p]),
     "slu_frame_normals": (_i, [_p, _i, _i, _i, _i64, _f, _p, _p]),
     "slu_organized_planes": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "slu_frame_tensors": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _i, _p]),

@@ -114,6 +114,8 @@ struct ProjParams {
     double theta_lo, theta_hi;
     int farthest;
     int key_sq;                    // depth keys hold the bits of r^2 (fast path: no DSQRT per point) instead of r
+    const double* row_edges;       // caller-supplied row edges (bins_h of the reference), ASCENDING, [H], or NULL
+    int row_edges_increasing;      // the caller's array was increasing: idx = cnt - 1 instead of H - 1 - cnt
     // workspace
     double* theta;                 // [n_total]
     unsigned long long* rkey;      // [n_total]
@@ -246,11 +248,27 @@ __global__ void __launch_bounds__(PT_THREADS) proj_rows_kernel(const __grid_cons
     int near_cnt = 0;
     for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
         bool near;
-        const int cnt_h = count_le(eh, p.theta[n], near);
-        // the scan's own extreme points sit exactly ON the first/last edge by construction
-        if (near && !p.use_range) near = !(p.theta[n] == lo || p.theta[n] == hi);
+        int cnt_h, r;
+        if (p.row_edges) {
+            // np.digitize(theta, bins_h) - 1 with the caller's edges (utils.py:330-338): cnt = #{edges <= theta} by bisection
+            const double th = p.theta[n];
+            int lo_i = 0, hi_i = p.H;                       // first index with edge > th (NaN: beyond every edge)
+            if (th != th) lo_i = p.H;
+            while (lo_i < hi_i) {
+                const int mid = (lo_i + hi_i) >> 1;
+                if (p.row_edges[mid] <= th) lo_i = mid + 1; else hi_i = mid;
+            }
+            cnt_h = lo_i;
+            const double tol = 8.9e-16 * fmax(fabs(th), 2.3e-308);
+            near = (cnt_h > 0 && fabs(th - p.row_edges[cnt_h - 1]) <= tol) || (cnt_h < p.H && fabs(p.row_edges[cnt_h] - th) <= tol);
+            r = p.row_edges_increasing ? cnt_h - 1 : p.H - 1 - cnt_h;
+        } else {
+            cnt_h = count_le(eh, p.theta[n], near);
+            // the scan's own extreme points sit exactly ON the first/last edge by construction
+            if (near && !p.use_range) near = !(p.theta[n] == lo || p.theta[n] == hi);
+            r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
+        }
         if (near) ++near_cnt;
-        int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
         if (r < 0) r += p.H;
         const int px = r * p.W + p.col[n];
         p.pix[n] = px;
@@ -282,7 +300,8 @@ constexpr int DEFER_CAP = 1024;             // per-block queue of near-edge poin
 __device__ __forceinline__ float fast_atan2(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    if (!(mx > 1.0e-30f && mx < 1.0e30f)) return __int_as_float(0x7fc00000);
+    // fmaxf / fminf drop a NaN operand: both magnitudes are tested on their own (a comparison with NaN is false)
+    if (!(ax < 1.0e30f) || !(ay < 1.0e30f) || !(mx > 1.0e-30f)) return __int_as_float(0x7fc00000);
     const float q = __fdividef(mn, mx);
     const float t = q * q;
     float a = fmaf(6.811646790e-03f, t, -3.360372957e-02f);
@@ -912,11 +931,26 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     return 0;
 }
 
+extern "C" int slu_project_points_bins(const double* d_pc, int64_t N, int Cin, int H, int W,
+                                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                                       const double* d_row_edges_ascending, int edges_were_increasing, void* d_work,
+                                       float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                                       slu_stream_t stream);
+
 extern "C" int slu_project_points(const double* d_pc, int64_t N, int Cin, int H, int W,
                                   int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
                                   void* d_work,
                                   float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
                                   slu_stream_t stream) {
+    return slu_project_points_bins(d_pc, N, Cin, H, W, use_theta_range, theta_lo, theta_hi, farthest_wins, nullptr, 0, d_work,
+                                   d_img_hwc, d_pix, d_winner, d_theta, d_diag, stream);
+}
+
+extern "C" int slu_project_points_bins(const double* d_pc, int64_t N, int Cin, int H, int W,
+                                       int use_theta_range, double theta_lo, double theta_hi, int farthest_wins,
+                                       const double* d_row_edges_ascending, int edges_were_increasing, void* d_work,
+                                       float* d_img_hwc, int32_t* d_pix, int32_t* d_winner, double* d_theta, int32_t* d_diag,
+                                       slu_stream_t stream) {
     using namespace slu;
     if (N < 0 || N > 0x7ffffff0LL) return fail(SLU_E_RANGE, "N=%lld unsupported", (long long)N);
     if (Cin < 3) return fail(SLU_E_ARG, "Cin=%d < 3", Cin);
@@ -930,6 +964,7 @@ extern "C" int slu_project_points(const double* d_pc, int64_t N, int Cin, int H,
     p.B = 1; p.H = H; p.W = W; p.HW = (long long)H * W;
     p.use_range = use_theta_range; p.theta_lo = theta_lo; p.theta_hi = theta_hi;
     p.farthest = farthest_wins;
+    p.row_edges = d_row_edges_ascending; p.row_edges_increasing = edges_were_increasing;
     p.img = d_img_hwc; p.theta_out = d_theta;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = project_common(p, N, d_work, d_pix, d_winner, d_diag, true, st);

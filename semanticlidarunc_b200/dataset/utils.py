@@ -43,16 +43,16 @@ _WS = {}          # device -> projection workspace, reused across calls (the dro
 _PIN = {}         # (H, W, Cin) -> pinned host image buffer + pinned meta buffer
 
 
-def project_device(pc: torch.Tensor, height=64, width=2048, theta_range=None, sort_largest_first=False):
+def project_device(pc: torch.Tensor, height=64, width=2048, theta_range=None, sort_largest_first=False, bins_h=None):
     """pc [N,Cin] CUDA tensor -> dict(img [H,W,Cin] f32, pix [N] i32, winner [H,W] i32, theta [1,2] f64, diag)."""
     dev = pc.device
     res = ops.project_points(pc.to(torch.float64), height, width, theta_range=theta_range,
-                             farthest_wins=sort_largest_first, workspace=_WS.get(dev))
+                             farthest_wins=sort_largest_first, workspace=_WS.get(dev), bins_h=bins_h)
     _WS[dev] = res["workspace"]
     return res
 
 
-def _host_bins(pc64: np.ndarray, height: int, width: int, theta_range):
+def _host_bins(pc64: np.ndarray, height: int, width: int, theta_range, bins_h=None):
     """Per-point pixel index in numpy, the reference's own arithmetic (src/dataset/utils.py:313-339: arctan2, linspace,
     digitize - 1 with the negative index wrapping round).  Only used to settle points the device flags as sitting within
     a few ulps of a bin edge."""
@@ -60,17 +60,17 @@ def _host_bins(pc64: np.ndarray, height: int, width: int, theta_range):
     phi = np.arctan2(y, x)
     theta = -np.arctan2(np.sqrt(x ** 2 + y ** 2), z) + np.pi / 2
     tmin, tmax = (theta.min(), theta.max()) if theta_range is None else theta_range
-    row = (np.digitize(theta, np.linspace(tmin, tmax, height)[::-1]) - 1) % height
+    row = (np.digitize(theta, np.linspace(tmin, tmax, height)[::-1] if bins_h is None else np.asarray(bins_h)) - 1) % height
     col = (np.digitize(phi, np.linspace(-np.pi, np.pi, width)[::-1]) - 1) % width
     return row * width + col, (float(tmin), float(tmax))
 
 
-def _settle_edge_points(pc64: np.ndarray, img: np.ndarray, pix: np.ndarray, height, width, theta_range, farthest_wins):
+def _settle_edge_points(pc64: np.ndarray, img: np.ndarray, pix: np.ndarray, height, width, theta_range, farthest_wins, bins_h=None):
     """Bit-exactness by construction: CUDA's and numpy's atan2 are both good to ~2 ulp, so a point within 4 ulp of a bin
     edge (the kernel counts them; ~1e-14 of all points) could land on either side.  When a scan has such points, every
     point's bin is recomputed with numpy and the pixels whose membership changed are re-resolved on the host.
     Returns (number of points that changed pixel, numpy's (theta_min, theta_max))."""
-    host, trange = _host_bins(pc64, height, width, theta_range)
+    host, trange = _host_bins(pc64, height, width, theta_range, bins_h)
     changed = np.nonzero(host != pix)[0]
     if changed.size == 0:
         return 0, trange
@@ -95,18 +95,17 @@ def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, so
     pc: array [N,Cin] (x,y,z first).  The reference computes in pc's dtype, float64 in every loader
     (np.concatenate of float32 xyzi with int64 labels); this path always computes in float64.
     `th` and `max_range` are dead parameters in the reference and are ignored here too.
-    `bins_h` (caller-supplied row edges) is not supported on the device path.
+    `bins_h`: caller-supplied row edges (H monotone values), used exactly as the reference uses them
+    (np.digitize(theta, bins_h) - 1); the device bisects the same float64 array.
     `alpha` [H,W] float64 depends only on the bin edges and every reference caller discards it: pass
     return_alpha=False to skip building it (None is returned in its place).
     One H2D copy of the cloud, one D2H copy of the image into a reused pinned buffer, one synchronisation.  Points the
     kernel flags as within 4 ulp of a bin edge are settled with numpy's own arithmetic (`_settle_edge_points`); the
     count of the last call is left in `spherical_projection.last_near_edge` / `.last_settled`."""
-    if bins_h is not None:
-        raise NotImplementedError("caller-supplied bins_h is not supported by the CUDA projection")
     dev = _lib.require_cuda()
     pc64 = np.ascontiguousarray(pc, dtype=np.float64)
     pc_t = torch.from_numpy(pc64).to(dev, non_blocking=True)
-    res = project_device(pc_t, height, width, theta_range, sort_largest_first)
+    res = project_device(pc_t, height, width, theta_range, sort_largest_first, bins_h)
     key = (height, width, pc64.shape[1])
     if key not in _PIN:
         _PIN[key] = (torch.empty((height, width, pc64.shape[1]), dtype=torch.float32, pin_memory=True),
@@ -122,12 +121,12 @@ def spherical_projection(pc, height=64, width=2048, theta_range=None, th=1.0, so
     if near_edge > 0:
         pix = res["pix"].cpu().numpy()
         spherical_projection.last_settled, (tmin, tmax) = _settle_edge_points(pc64, pj_img, pix, height, width, theta_range,
-                                                                              sort_largest_first)
+                                                                              sort_largest_first, bins_h)
     if theta_range is not None:
         tmin, tmax = theta_range
     alpha = None
     if return_alpha:
-        bh = np.linspace(tmin, tmax, height)[::-1]
+        bh = np.linspace(tmin, tmax, height)[::-1] if bins_h is None else np.asarray(bins_h, dtype=np.float64)
         bw = np.linspace(-np.pi, np.pi, width)[::-1]
         alpha = np.sqrt(np.square(bh)[:, None] + np.square(bw)[None, :])
     return pj_img, alpha, (tmin, tmax), (-np.pi, np.pi)

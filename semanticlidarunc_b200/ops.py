@@ -520,7 +520,7 @@ def project_batch(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], offsets
 
 @_lib.device_guard
 def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthest_wins: bool = False,
-                   want_img: bool = True, workspace: Optional[torch.Tensor] = None) -> dict:
+                   want_img: bool = True, workspace: Optional[torch.Tensor] = None, bins_h=None) -> dict:
     """Generic stage 1 (slu_project_points): pc [N,Cin] float64 CUDA -> img [H,W,Cin] float32.
     `workspace`: a uint8 CUDA tensor from an earlier call (returned under "workspace") is reused when large enough."""
     _lib.require_cuda()
@@ -539,9 +539,22 @@ def project_points(pc: torch.Tensor, H: int, W: int, *, theta_range=None, farthe
     diag = torch.empty((1, 2), dtype=torch.int32, device=dev)
     use_range = theta_range is not None
     lo, hi = (float(theta_range[0]), float(theta_range[1])) if use_range else (0.0, 0.0)
-    rc = _lib.lib().slu_project_points(_lib.ptr(pc), N, Cin, H, W, int(use_range), lo, hi, int(farthest_wins),
-                                       _lib.ptr(workspace), _lib.ptr(img), _lib.ptr(pix), _lib.ptr(winner),
-                                       _lib.ptr(theta), _lib.ptr(diag), _lib.stream_ptr())
+    edges, increasing = None, 0
+    if bins_h is not None:                        # the reference's bins_h: H monotone row edges (np.digitize's requirement)
+        e = np.asarray(bins_h, dtype=np.float64).reshape(-1)
+        if e.shape[0] != H:
+            raise ValueError(f"bins_h must have height={H} entries")
+        d = np.diff(e)
+        if np.all(d >= 0):
+            increasing = 1
+        elif np.all(d <= 0):
+            e = e[::-1]
+        else:
+            raise ValueError("bins must be monotonically increasing or decreasing")
+        edges = torch.from_numpy(np.ascontiguousarray(e)).to(dev)
+    rc = _lib.lib().slu_project_points_bins(_lib.ptr(pc), N, Cin, H, W, int(use_range), lo, hi, int(farthest_wins),
+                                            _lib.ptr(edges), increasing, _lib.ptr(workspace), _lib.ptr(img), _lib.ptr(pix),
+                                            _lib.ptr(winner), _lib.ptr(theta), _lib.ptr(diag), _lib.stream_ptr())
     _lib.check(rc, "slu_project_points")
     return {"img": img, "pix": pix, "winner": winner, "theta": theta, "diag": diag, "workspace": workspace}
 

@@ -276,3 +276,27 @@ def test_streaming_and_generic_histogram_kernels_agree(cuda, C, n, n_bins, offse
     cm2 = torch.zeros((C, C), dtype=torch.int64, device=cuda)
     ops.confusion_ece(pd, ld, None, num_classes=C, confmat=cm2)
     assert torch.equal(2 * b2.cpu(), out[0][1]) and torch.equal(2 * cm2.cpu(), out[0][0])
+
+
+def test_uncertainty_per_class_aggregator_vs_reference_golden(cuda, golden):
+    """Against the reference's own UncertaintyPerClassAggregator (golden from oracle/gen_golden.py::gen_per_class): sample
+    counts and per-class means exact (fixed-point sums), quartiles to one histogram bin, and the same class order by mean
+    uncertainty that plot_iou_sorted_by_uncertainty uses."""
+    from semanticlidarunc_b200.models.evaluator import UncertaintyPerClassAggregator, plot_iou_sorted_by_uncertainty
+    g = golden("per_class.npz")
+    labels, unc = torch.from_numpy(g["labels"]), torch.from_numpy(g["unc"])
+    C = 20
+    agg = UncertaintyPerClassAggregator(C)
+    agg.update(labels[:1].to(cuda), unc[:1].to(cuda))
+    agg.update(labels[1:].to(cuda), unc[1:].to(cuda))
+    assert agg._seen_counts == [int(v) for v in g["seen"]]
+    st = agg.class_stats().set_index("class_id")
+    for c in range(C):
+        n, mean, q25, med, q75 = g["stats"][c]
+        assert int(st.loc[c, "n"]) == int(n)
+        assert abs(st.loc[c, "mean"] - mean) < 2e-7
+        for ours, ref in ((st.loc[c, "q25"], q25), (st.loc[c, "median"], med), (st.loc[c, "q75"], q75)):
+            assert abs(ours - ref) < 0.01
+    names = [str(i) for i in range(C)]
+    order = plot_iou_sorted_by_uncertainty(agg, {n: 0.5 for n in names}, names, {i: [0, 0, 0] for i in range(C)}, ignore_ids=(0,))
+    assert [int(v) for v in order["class_id"]] == [int(v) for v in g["order_by_mean"]]

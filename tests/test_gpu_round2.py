@@ -342,3 +342,21 @@ def test_prefilter_arctangent_error_bound(cuda):
     err = (out[4:].double() - ref).abs()
     err = torch.minimum(err, 2 * np.pi - err)
     assert float(err.max()) < 1.0e-6, float(err.max())
+
+
+@pytest.mark.parametrize("increasing", [False, True])
+def test_drop_in_projection_with_caller_supplied_row_edges(cuda, increasing):
+    """bins_h (src/dataset/utils.py:330-338): non-uniform row edges, in either direction, against the numpy oracle."""
+    from semanticlidarunc_b200.dataset.utils import spherical_projection
+    H, W = 16, 256
+    xyzi, raw = synth.synth_scan(33, "tiny")
+    pc = np.concatenate([xyzi.astype(np.float64), np.arange(xyzi.shape[0], dtype=np.float64)[:, None] + 1.0], axis=1)
+    rng = np.random.default_rng(5)
+    edges = np.sort(rng.uniform(-0.40, 0.20, H))                       # non-uniform, strictly increasing
+    bins = edges if increasing else edges[::-1]
+    img, alpha, tr, _ = spherical_projection(pc, H, W, bins_h=bins)
+    ref, alpha_ref, tr_ref, _ = oproj.spherical_projection(pc, H, W, bins_h=bins)
+    assert np.array_equal(img, ref) and tr == tr_ref
+    assert np.array_equal(alpha, alpha_ref)
+    with pytest.raises(ValueError):
+        spherical_projection(pc, H, W, bins_h=np.array([0.0, 1.0, 0.5] + [2.0] * (H - 3)))
