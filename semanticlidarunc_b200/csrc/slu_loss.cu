@@ -19,6 +19,7 @@
 // the caller (one scalar), so the kernel needs no second pass.
 // Bound: instruction-bound (lgamma + digamma + trigamma per class), 88 B/px read, 84 B/px written per term.
 #include <math.h>
+#include <stdlib.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
 #include "slu_packed.cuh"
@@ -650,6 +651,143 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
     }
 }
 
+// ---- packed over CLASS pairs: one pixel per thread, the two halves of every f32x2 operation are classes 2k and 2k+1 ----
+// The pixel-pair kernel above needs 80 registers for its two per-class arrays of two pixels (168 in all: 3 CTAs of 128
+// threads per SM, 12 warps) and is bound by the latency of its dependent FFMA2 chains, not by issue (ncu: issue slots 51 %
+// busy, 0.79 eligible warps per cycle; profiles/packed_kernels_r02_ncu_summary.txt).  Packing class pairs of ONE pixel
+// keeps the packed instruction count per pixel and halves the per-thread arrays, so twice as many pixels are in flight per
+// register; loads and stores stay 4-byte per thread (a warp covers 128 contiguous bytes of a class plane), which also
+// lifts the even-HW / alignment conditions.  Horizontal sums over the two halves close each reduction.
+constexpr int LOSSC_THREADS = 256;
+#ifndef SLU_LOSSC_MINB
+#define SLU_LOSSC_MINB 3
+#endif
+
+template <int CP, bool EXACT>
+__global__ void __launch_bounds__(LOSSC_THREADS, SLU_LOSSC_MINB) evidential_loss_fused_cp_kernel(const __grid_constant__ FusedParams p) {
+    static_assert(CP % 2 == 0, "class pairs");
+    constexpr int C2 = CP / 2;
+    const int tid = threadIdx.x;
+    const double n_valid = p.count ? *p.count : p.sums[2];
+    const float inv_n = (float)(1.0 / fmax(n_valid, 1.0));
+    const float wm = p.w_mse * inv_n, wk = p.w_kl * inv_n;
+    double acc_mse = 0.0, acc_kl = 0.0;
+    const long long chunks = (p.n_px + LOSSC_THREADS - 1) / LOSSC_THREADS;
+    for (long long ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const long long g = ch * LOSSC_THREADS + tid;
+        if (g >= p.n_px) continue;
+        const int b = (int)(g / p.HW);
+        const long long px = g - (long long)b * p.HW;
+        const long long tgt = p.target[g];
+        const float* base = p.outputs + ((long long)b * (p.C + 1)) * p.HW + px;
+        float* go = p.grad ? p.grad + ((long long)b * (p.C + 1)) * p.HW + px : nullptr;
+        if (!px_valid(p, g, tgt)) {
+            if (go) for (int c = 0; c <= p.C; ++c) go[(long long)c * p.HW] = 0.f;
+            continue;
+        }
+        const int y = (int)tgt;
+        f2 pr[C2], a[C2];
+#pragma unroll
+        for (int k = 0; k < C2; ++k)
+            pr[k] = f2((EXACT || 2 * k < p.C) ? ldg_stream(base + (long long)(2 * k) * p.HW) : -1.0e30f,
+                       (EXACT || 2 * k + 1 < p.C) ? ldg_stream(base + (long long)(2 * k + 1) * p.HW) : -1.0e30f);
+        const float sl = ldg_stream(base + (long long)p.C * p.HW) * p.inv_temp;
+        const float scale = sl > 20.f ? sl : log1pf(expf(sl));
+        const float dscale = sl > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl));       // d softplus
+        f2 mm = pr[0];
+#pragma unroll
+        for (int k = 1; k < C2; ++k) mm = max2(mm, pr[k]);
+        const float m2 = fmaxf(mm.v.x, mm.v.y) * 1.4426950408889634f;
+        f2 S2(0.f);
+#pragma unroll
+        for (int k = 0; k < C2; ++k) { pr[k] = ex2_2(fma2(pr[k], 1.4426950408889634f, f2(-m2))); S2 += pr[k]; }
+        const float invS = __frcp_rn(S2.v.x + S2.v.y);
+        f2 a0v(0.f), s2v(0.f), sv(0.f);
+        float ay = 0.f;
+#pragma unroll
+        for (int k = 0; k < C2; ++k) {
+            pr[k] = pr[k] * invS;
+            const bool in0 = EXACT || 2 * k < p.C, in1 = EXACT || 2 * k + 1 < p.C;
+            const f2 al = alpha_from_probs2(f2(scale), pr[k], p.eps_alpha);
+            a[k] = f2(in0 ? al.v.x : 0.f, in1 ? al.v.y : 0.f);
+            a0v += a[k];
+            s2v = fma2(a[k], a[k], s2v);
+            const bool t0 = 2 * k == y, t1 = 2 * k + 1 == y;
+            ay = t0 ? a[k].v.x : (t1 ? a[k].v.y : ay);
+            const f2 ac = max2(f2(t0 ? 1.0f : a[k].v.x, t1 ? 1.0f : a[k].v.y), p.eps_kl);
+            sv += f2(in0 ? ac.v.x : 0.f, in1 ? ac.v.y : 0.f);
+        }
+        const float a0 = a0v.v.x + a0v.v.y, s2 = s2v.v.x + s2v.v.y, s = sv.v.x + sv.v.y;
+        // per-pixel scalars (formulas: evidential_loss_fused_x2_kernel)
+        const float D = a0 + p.eps_mse, invD = 1.0f / D;
+        const float G = fmaf(a0, a0, p.eps_mse) * (a0 + 1.0f), invG = 1.0f / G;
+        const float N = fmaf(a0, a0, -s2);
+        const float sp2 = s2 * invD * invD;
+        const float var = N * invG;
+        const float Gp = fmaf(2.0f * a0, a0 + 1.0f, fmaf(a0, a0, p.eps_mse));
+        const float common = fmaf(2.0f * fmaf(ay, invD, -sp2), invD, fmaf(2.0f * a0, invG, -(N * Gp * invG * invG)));
+        const float m2invD = -2.0f * invD, m2invG = -2.0f * invG;
+        const LDT fs = ldt_pos(s);
+        const float sC = s - (float)p.C;
+        const float tail = sC * fs.tri;
+        f2 sqv(0.f), Lv(0.f), Qv(0.f), gpv(0.f);
+#pragma unroll
+        for (int k = 0; k < C2; ++k) {
+            const bool in0 = EXACT || 2 * k < p.C, in1 = EXACT || 2 * k + 1 < p.C;
+            const bool t0 = 2 * k == y, t1 = 2 * k + 1 == y;
+            const f2 d = f2(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f) - a[k] * invD;
+            const f2 gm = fma2(d, m2invD, fma2(a[k], m2invG, common));
+            const f2 ac = max2(f2((t0 || !in0) ? 1.0f : a[k].v.x, (t1 || !in1) ? 1.0f : a[k].v.y), p.eps_kl);   // padded classes: a~ = 1 (f = 0)
+            const f2 w = rcp2(ac);
+            const f2 gA = gm * wm;
+            const f2 gB = fma2(kl_grad_term(w) - tail, wk, gA);
+            const f2 gc((in0 && !t0 && a[k].v.x > p.eps_kl) ? gB.v.x : (in0 ? gA.v.x : 0.f),
+                        (in1 && !t1 && a[k].v.y > p.eps_kl) ? gB.v.y : (in1 ? gA.v.y : 0.f));
+            const f2 dm(in0 ? d.v.x : 0.f, in1 ? d.v.y : 0.f);
+            sqv = fma2(dm, dm, sqv);
+            Lv += lg2_2(ac);
+            Qv = fma2(w, kl_value_poly(w), Qv);
+            a[k] = gc;                           // a[] now holds d(loss)/d(alpha_c), 1/n_valid included
+            gpv = fma2(gc, pr[k], gpv);
+        }
+        // padded classes entered Qv with w = 1 (a~ = 1): f(1) = 0 = -0 + 1 - KL_VALUE_CONST + u(1), i.e. their w u(w) term is
+        // exactly what the constant part below subtracts for them when it runs over CP instead of C classes
+        const float n_cls = EXACT ? (float)p.C : (float)CP;
+        const float sq = sqv.v.x + sqv.v.y, L = Lv.v.x + Lv.v.y, Qs = Qv.v.x + Qv.v.y, gp_sum = gpv.v.x + gpv.v.y;
+        const float s_all = EXACT ? s : s + (float)(CP - p.C);                    // padded a~ = 1 each
+        const float mse = sq + var;
+        const float kl = (fmaf(-fs.psi, sC, fs.lg) + fmaf(L, -0.34657359027997264f, s_all - n_cls * KL_VALUE_CONST)) + Qs;
+        acc_mse += (double)mse;
+        acc_kl += (double)kl;
+        if (go) {
+#pragma unroll
+            for (int k = 0; k < C2; ++k) {
+                const f2 o = pr[k] * scale * (a[k] - gp_sum);
+                if (EXACT || 2 * k < p.C) go[(long long)(2 * k) * p.HW] = o.v.x;
+                if (EXACT || 2 * k + 1 < p.C) go[(long long)(2 * k + 1) * p.HW] = o.v.y;
+            }
+            go[(long long)p.C * p.HW] = gp_sum * dscale * p.inv_temp;
+        }
+    }
+    __shared__ double s_m[LOSSC_THREADS / 32], s_k[LOSSC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_mse += __shfl_xor_sync(0xffffffffu, acc_mse, o);
+        acc_kl += __shfl_xor_sync(0xffffffffu, acc_kl, o);
+    }
+    if ((tid & 31) == 0) { s_m[tid >> 5] = acc_mse; s_k[tid >> 5] = acc_kl; }
+    __syncthreads();
+    if (tid == 0) {
+        double mm2 = 0.0, kk = 0.0;
+        for (int i = 0; i < LOSSC_THREADS / 32; ++i) { mm2 += s_m[i]; kk += s_k[i]; }
+        atomicAdd(&p.sums[0], mm2);
+        atomicAdd(&p.sums[1], kk);
+        if (p.loss4) fused_step_epilogue(p, n_valid);
+    }
+}
+
+static int g_loss_variant = [] { const char* e = getenv("SLU_LOSS_VARIANT"); return e ? atoi(e) : 0; }();   // 0 = automatic (pixel pairs, class pairs for odd / unaligned shapes), 1 = class pairs, 2 = one pixel per thread
+
 template <int CP>
 static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) {
     const int sms = sm_count_current_device();
@@ -661,8 +799,20 @@ static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) 
         count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p, p.count ? const_cast<double*>(p.count) : p.sums + 2);
         SLU_LAUNCH_CHECK("count_valid_kernel");
     }
-    const bool packed = !g_no_packed && (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
-                        (reinterpret_cast<uintptr_t>(p.outputs) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.grad) & 7) == 0;
+    const bool pair_ok = (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.outputs) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.grad) & 7) == 0;
+    // class-pair kernel: shapes the pixel-pair kernel cannot take (odd HW, unaligned views), or SLU_LOSS_VARIANT=1.  On
+    // aligned even shapes the two measure the same (0.135 / 0.140 ms per 16 scans), the pixel-pair one is kept there.
+    if (!g_no_packed && (g_loss_variant == 1 || (g_loss_variant == 0 && !pair_ok))) {
+        const long long capc = (long long)SLU_LOSSC_MINB * sms;
+        const long long chunksc = (p.n_px + LOSSC_THREADS - 1) / LOSSC_THREADS;
+        const unsigned gridc = (unsigned)(chunksc < capc ? chunksc : capc);
+        if (p.C == CP) evidential_loss_fused_cp_kernel<CP, true><<<gridc, LOSSC_THREADS, 0, st>>>(p);
+        else evidential_loss_fused_cp_kernel<CP, false><<<gridc, LOSSC_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("evidential_loss_fused_cp_kernel");
+        return 0;
+    }
+    const bool packed = !g_no_packed && g_loss_variant != 2 && pair_ok;
     if (packed) {
         const long long chunks2 = ((p.n_px >> 1) + LOSS2_THREADS - 1) / LOSS2_THREADS;
         const long long cap2 = (long long)SLU_LOSS2_MINB * sms;

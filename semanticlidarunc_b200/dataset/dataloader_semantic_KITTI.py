@@ -53,9 +53,15 @@ class SemanticKitti(Dataset):
         label = np.fromfile(label_path, dtype=np.uint32).reshape(-1)
         return xyzi, label
 
-    def device_batch(self, scans, yaw_deg=None, flip=None):
+    def device_batch(self, scans, yaw_deg=None, flip=None, settle_edges: bool = False):
         """scans: list of (xyzi, raw_label) numpy pairs -> dict of stacked device tensors
-        (range, reflectivity, xyz, normals, semantics) plus pix / offsets for back-projection."""
+        (range, reflectivity, xyz, normals, semantics) plus pix / offsets for back-projection.
+
+        settle_edges: read the kernels' near-edge counters (one synchronisation) and, for a scan that has points
+        within 4 ulp of a bin edge, settle those points with numpy's own arithmetic before the image is framed
+        (`_settle_scan`; ~1e-14 of all points are affected, so this is almost always just the counter read).
+        `__getitem__` turns it on -- it synchronises anyway; batched callers that must not synchronise leave it off
+        and can inspect out["near_edge"] later."""
         dev = self._dev()
         offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])]).astype(np.int64)
         xyzi = torch.from_numpy(np.ascontiguousarray(np.concatenate([s[0] for s in scans]))).to(dev, non_blocking=True)
@@ -63,9 +69,51 @@ class SemanticKitti(Dataset):
         proj = ops.project_batch(xyzi, raw, offs, self.projection[0], self.projection[1], lut=self._lut, yaw_deg=yaw_deg,
                                  theta_range=self.THETA_RANGE, want_label=False)
         missing = proj["diag"][:, 0]
+        settled = 0
+        if settle_edges:
+            diag = proj["diag"].cpu()
+            for b in np.nonzero(diag[:, 1].numpy())[0]:
+                settled += self._settle_scan(proj, int(b), scans[int(b)], offs, None if yaw_deg is None else yaw_deg[int(b)])
         out = self._frame(proj["img"], flip)
         out["pix"], out["offsets"], out["missing_label_ids"] = proj["pix"], offs, missing
+        out["near_edge"], out["settled_points"] = proj["diag"][:, 1], settled
         return self._finish(out)
+
+    def _settle_scan(self, proj, b, scan, offs, yaw):
+        """Bit-exactness by construction for scan b of a projected batch: recompute every point's bin with numpy (the
+        reference's arithmetic, dataset/utils.py::_host_bins), and re-resolve on the host the few pixels whose membership
+        differs from the device's; the device image planes, label plane and pix are patched in place."""
+        from .utils import _host_bins
+        xyzi, raw = scan
+        H, W = self.projection
+        xyz = xyzi[:, :3].astype(np.float64)
+        if yaw is not None:                                     # rotate_z, src/dataset/utils.py:4-18
+            a = np.radians(float(yaw))
+            c, s_ = np.cos(a), np.sin(a)
+            xyz = xyz @ np.array([[c, -s_, 0.0], [s_, c, 0.0], [0.0, 0.0, 1.0]])
+        host, _ = _host_bins(xyz, H, W, self.THETA_RANGE)
+        n0, n1 = int(offs[b]), int(offs[b + 1])
+        pix = proj["pix"][n0:n1].cpu().numpy().astype(np.int64)
+        changed = np.nonzero(host != pix)[0]
+        if changed.size == 0:
+            return 0
+        r = np.sqrt(xyz[:, 0] ** 2 + xyz[:, 1] ** 2 + xyz[:, 2] ** 2)
+        sem = self._lut_host[(raw & 0xFFFF).astype(np.int64)]
+        img = proj["img"][b].reshape(6, H * W)
+        for q in np.unique(np.concatenate([host[changed], pix[changed]])):
+            members = np.nonzero(host == q)[0]
+            vals = np.zeros(6, dtype=np.float32)
+            if members.size:
+                rr = r[members]
+                w = int(members[rr == rr.min()].min())          # nearest wins, lowest index among exact ties
+                x32 = xyz[w].astype(np.float32)
+                vals[:3] = x32
+                vals[3] = np.sqrt(np.float32(x32[0] * x32[0]) + np.float32(x32[1] * x32[1]) + np.float32(x32[2] * x32[2]), dtype=np.float32)
+                vals[4] = xyzi[w, 3]
+                vals[5] = np.float32(sem[w])
+            img[:, int(q)] = torch.from_numpy(vals).to(img.device)
+        proj["pix"][n0:n1][torch.from_numpy(changed).to(proj["pix"].device)] = torch.from_numpy(host[changed].astype(np.int32)).to(proj["pix"].device)
+        return int(changed.size)
 
     def staged_batches(self, indices, batch_size: int = 16, n_slots: int = 32, n_io_threads: int = 4, max_points: int = 300_000):
         """Yield `device_batch`-style dicts for `indices` in chunks of `batch_size`, the files read by libslu's native
@@ -114,7 +162,7 @@ class SemanticKitti(Dataset):
         frame_path, label_path = self.data_path[idx]
         xyzi, label = self.read_scan(frame_path, label_path)
         yaw, do_flip = self._draw_augmentation()
-        out = self.device_batch([(xyzi, label)], yaw_deg=None if yaw is None else [yaw], flip=[do_flip])
+        out = self.device_batch([(xyzi, label)], yaw_deg=None if yaw is None else [yaw], flip=[do_flip], settle_edges=True)
         if int(out["missing_label_ids"][0]) != 0:
             raise KeyError("scan %s contains semantic ids that are not in the label map" % (label_path,))   # id_map[l] at :47
         items = tuple(out[k][0] for k in ("range", "reflectivity", "xyz", "normals", "semantics"))

@@ -360,3 +360,59 @@ def test_drop_in_projection_with_caller_supplied_row_edges(cuda, increasing):
     assert np.array_equal(alpha, alpha_ref)
     with pytest.raises(ValueError):
         spherical_projection(pc, H, W, bins_h=np.array([0.0, 1.0, 0.5] + [2.0] * (H - 3)))
+
+
+def test_kitti_loader_settles_edge_points(cuda, tmp_path):
+    """SemanticKitti.__getitem__ on a scan with points planted on / 1-2 ulp around column edges: the five tensors must
+    equal the reference's (oracle kitti_item), whatever side the device's angles fall on."""
+    from semanticlidarunc_b200.dataset.dataloader_semantic_KITTI import SemanticKitti
+    H, W = 16, 256
+    xyzi, raw = synth.synth_scan(41, "tiny")
+    edges_w = np.linspace(-np.pi, np.pi, W)
+    rng = np.random.default_rng(2)
+    extra = []
+    for e in edges_w[9:240:11]:
+        for ulps in (-1, 0, 1):
+            phi = e
+            for _ in range(abs(ulps)):
+                phi = np.nextafter(phi, np.inf if ulps > 0 else -np.inf)
+            r, el = rng.uniform(5, 60), rng.uniform(-0.3, 0.1)
+            extra.append([r * np.cos(el) * np.cos(phi), r * np.cos(el) * np.sin(phi), r * np.sin(el), 0.25])
+    xyzi2 = np.concatenate([xyzi, np.asarray(extra, dtype=np.float32)]).astype(np.float32)
+    raw2 = np.concatenate([raw, np.full(len(extra), raw[0], dtype=np.uint32)])
+    b, l = tmp_path / "000000.bin", tmp_path / "000000.label"
+    xyzi2.tofile(b); raw2.tofile(l)
+    ds = SemanticKitti([(str(b), str(l))], projection=(H, W), resize=False)
+    got = ds[0]
+    ref = oproj.kitti_item(xyzi2, raw2, build_id_lut(), projection=(H, W), resize=False)
+    for k, (a, r_) in enumerate(zip(got, ref)):
+        if k == 3:
+            continue                                     # normals: tolerance-checked elsewhere
+        assert np.array_equal(a.numpy(), r_), k
+
+
+def test_class_pair_loss_kernel_on_odd_shapes(cuda):
+    """Odd HW cannot take the pixel-pair kernel: the class-pair packed kernel runs instead and must agree with the
+    one-pixel-per-thread kernel (same formulas as the pixel-pair kernel, horizontal sums in another order)."""
+    B, C, H, W = 2, 20, 7, 37
+    x, lab = synth.synth_evidential_logits(11, B, C, H, W)
+    x, lab = x.to(cuda), lab.to(cuda)
+    n0 = _lib.launch_count()
+    a = ops.evidential_loss_fused(x, lab, ignore=(0,))
+    assert _lib.launch_count() - n0 == 2
+    _switch("slu_debug_no_packed_loss", 1)
+    b = ops.evidential_loss_fused(x, lab, ignore=(0,))
+    _switch("slu_debug_no_packed_loss", 0)
+    assert a["sums"][2] == b["sums"][2]
+    np.testing.assert_allclose(a["sums"].cpu().numpy(), b["sums"].cpu().numpy(), rtol=3e-6)
+    assert (a["grad"] - b["grad"]).abs().max().item() <= 1e-5 * b["grad"].abs().max().item()
+    assert torch.equal(a["grad"] == 0, b["grad"] == 0)
+    for Cc in (5, 6):                                     # padded class pairs
+        x2, lab2 = synth.synth_evidential_logits(12, 1, Cc, 5, 9)
+        x2, lab2 = x2.to(cuda), lab2.to(cuda)
+        a = ops.evidential_loss_fused(x2, lab2, ignore=(0,))
+        _switch("slu_debug_no_packed_loss", 1)
+        b = ops.evidential_loss_fused(x2, lab2, ignore=(0,))
+        _switch("slu_debug_no_packed_loss", 0)
+        np.testing.assert_allclose(a["sums"].cpu().numpy(), b["sums"].cpu().numpy(), rtol=3e-6)
+        assert (a["grad"] - b["grad"]).abs().max().item() <= 1e-5 * b["grad"].abs().max().item()
