@@ -144,6 +144,74 @@ __global__ void __launch_bounds__(FR_THREADS) frame_normals_kernel(const __grid_
     }
 }
 
+// Four consecutive pixels of a row per thread: per plane three 16-byte row loads plus the two neighbours left and right
+// of the strip (9 load instructions instead of 36 for four pixels), float4 stores.  Same arithmetic, operation for
+// operation, as frame_normals_kernel (the results are bit-identical); used when W % 4 == 0, the planes are 16-byte
+// aligned and no rows were dropped.
+__global__ void __launch_bounds__(FR_THREADS) frame_normals4_kernel(const __grid_constant__ FrameParams p) {
+    const int b = blockIdx.y;
+    const long long HW = (long long)p.Hd * p.Wd;
+    const float* base = p.xyz + (long long)b * p.xyz_bstride;
+    float* out = p.normals + (long long)b * 3 * HW;
+    const int W4 = p.Wd >> 2;
+    const long long n4 = (long long)p.Hd * W4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W4), x0 = (int)(i - (long long)y * W4) << 2;
+        const int ym = reflect101(y - 1, p.Hd), yp = reflect101(y + 1, p.Hd);
+        const int xm = reflect101(x0 - 1, p.Wd), xp = reflect101(x0 + 4, p.Wd);
+        float gx[3][4], gy[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* P = base + (long long)c * HW;
+            float r[3][6];                                   // rows ym, y, yp; columns x0-1 .. x0+4
+            const int ys[3] = {ym, y, yp};
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float* row = P + (long long)ys[j] * p.Wd;
+                const float4 m = *reinterpret_cast<const float4*>(row + x0);
+                r[j][0] = row[xm]; r[j][1] = m.x; r[j][2] = m.y; r[j][3] = m.z; r[j][4] = m.w; r[j][5] = row[xp];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a00 = r[0][k], a01 = r[0][k + 1], a02 = r[0][k + 2];
+                const float a10 = r[1][k], a12 = r[1][k + 2];
+                const float a20 = r[2][k], a21 = r[2][k + 1], a22 = r[2][k + 2];
+                const float d0 = __fsub_rn(a02, a00), d1 = __fsub_rn(a12, a10), d2 = __fsub_rn(a22, a20);
+                gx[c][k] = __fadd_rn(__fmul_rn(p.tap_c, d1), __fmul_rn(p.tap_s, __fadd_rn(d0, d2)));
+                const float r0 = __fadd_rn(__fmul_rn(p.tap_c, a01), __fmul_rn(p.tap_s, __fadd_rn(a00, a02)));
+                const float r2 = __fadd_rn(__fmul_rn(p.tap_c, a21), __fmul_rn(p.tap_s, __fadd_rn(a20, a22)));
+                gy[c][k] = __fsub_rn(r2, r0);
+            }
+        }
+        float o[3][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float Sxx = gx[0][k], Sxy = gy[0][k], Syx = gx[1][k], Syy = gy[1][k], Szx = gx[2][k], Szy = gy[2][k];
+            const float nx = -__fsub_rn(__fmul_rn(Syx, Szy), __fmul_rn(Szx, Syy));
+            const float ny = -__fsub_rn(__fmul_rn(Szx, Sxy), __fmul_rn(Szy, Sxx));
+            const float nz = -__fsub_rn(__fmul_rn(Sxx, Syy), __fmul_rn(Syx, Sxy));
+            const float n = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz))), 1e-10f);
+            o[0][k] = __fdiv_rn(nx, n); o[1][k] = __fdiv_rn(ny, n); o[2][k] = __fdiv_rn(nz, n);
+        }
+        const long long off = (long long)y * p.Wd + x0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<float4*>(out + (long long)c * HW + off) = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+    }
+}
+
+static void launch_normals(const FrameParams& p, int B, int sms, cudaStream_t st) {
+    const long long HWd = (long long)p.Hd * p.Wd;
+    const bool vec = (p.Wd & 3) == 0 && p.Wd >= 8 && !(p.rowmap && p.keep_native_h) && (p.xyz_bstride & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(p.xyz) | reinterpret_cast<uintptr_t>(p.normals)) & 15) == 0;
+    const long long work = vec ? HWd / 4 : HWd;
+    long long gx = (work + FR_THREADS - 1) / FR_THREADS;
+    const long long cap = (8LL * sms + B - 1) / B;
+    if (gx > cap) gx = cap;
+    if (vec) frame_normals4_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+    else frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+}
+
 // ---- organised clouds (Ouster / SemanticTHAB): the sensor already delivers H x W points, pixel = point -----------
 // Replaces src/dataset/dataloader_semantic_THAB.py:35-66: label remap, reshape to (H,W,.), optional flip
 // (columns reversed, y negated), optional yaw as an image roll (rotate_equirectangular_image,
@@ -261,7 +329,7 @@ extern "C" int slu_frame_tensors(const float* d_img, int B, int Hs, int Ws, int 
     frame_resample_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("frame_resample_kernel");
     if (d_normals) {
-        frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
+        launch_normals(p, B, sms, st);
         SLU_LAUNCH_CHECK("frame_normals_kernel");
     }
     return 0;
@@ -285,11 +353,7 @@ extern "C" int slu_frame_normals(const float* d_xyz, int B, int H, int W, int64_
     p.normals = d_normals;
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
-    const long long HW = (long long)H * W;
-    long long gx = (HW + FR_THREADS - 1) / FR_THREADS;
-    const long long cap = (8LL * sms + B - 1) / B;
-    if (gx > cap) gx = cap;
-    frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    launch_normals(p, B, sms, reinterpret_cast<cudaStream_t>(stream));
     SLU_LAUNCH_CHECK("frame_normals_kernel");
     return 0;
 }

@@ -416,3 +416,17 @@ def test_class_pair_loss_kernel_on_odd_shapes(cuda):
         _switch("slu_debug_no_packed_loss", 0)
         np.testing.assert_allclose(a["sums"].cpu().numpy(), b["sums"].cpu().numpy(), rtol=3e-6)
         assert (a["grad"] - b["grad"]).abs().max().item() <= 1e-5 * b["grad"].abs().max().item()
+
+
+def test_vectorised_normals_kernel_is_bit_identical_to_scalar(cuda):
+    """frame_normals4_kernel (four pixels per thread, 16-byte accesses) against frame_normals_kernel, which an unaligned view
+    of the same planes falls back to."""
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 16, 256
+    xyz = torch.randn((B, 3, H, W), generator=g).to(cuda)
+    a = ops.frame_normals(xyz)                                             # aligned: vectorised kernel
+    pad = torch.empty(B * 3 * H * W + 1, dtype=torch.float32, device=cuda)
+    view = pad[1:].view(B, 3, H, W)                                        # 4-byte offset: scalar kernel
+    view.copy_(xyz)
+    b = ops.frame_normals(view)
+    assert torch.equal(a, b)
