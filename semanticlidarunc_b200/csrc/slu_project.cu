@@ -797,6 +797,38 @@ static Workspace carve(int64_t n_total, int B, int64_t HW) {
 // CTAs).  SLU_PT_CTAS_PER_SM overrides it for experiments.
 static int g_pt_ctas_per_sm = [] { const char* e = getenv("SLU_PT_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
 
+// The point / pixel kernels are latency-bound chains of dependent loads, atomics and barriers; they run best as EXACTLY
+// one resident wave (measured: 4 or 8 CTAs/SM = 1 or 2 full waves of the angle kernel 0.080 / 0.084 ms, 3, 5 or 6 = a
+// partial last wave 0.090-0.094 ms per 16 HDL-64 scans).  Each kernel's grid is therefore sized from ITS occupancy.
+template <typename K>
+static int resident_ctas_per_sm(K kernel) {
+    static int cached = 0;                       // one instantiation per kernel type: the value depends on the kernel only
+    if (cached == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, PT_THREADS, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+        cached = n;
+    }
+    const char* e = getenv("SLU_PT_CTAS_PER_SM");
+    const int forced = e ? atoi(e) : 0;
+    return forced > 0 ? forced : cached;
+}
+
+template <typename K>
+static int wave_grid_x(K kernel, long long items_max, int B, int sms) {
+    long long gx = (items_max + PT_THREADS - 1) / PT_THREADS;
+    long long cap = ((long long)resident_ctas_per_sm(kernel) * sms) / B;      // floor: never more than one wave
+    if (cap < 1) cap = 1;
+    if (gx > cap) gx = cap;
+    if (gx > MAX_GX) gx = MAX_GX;
+    return (int)(gx < 1 ? 1 : gx);
+}
+
+static long long max_points(const long long* offsets, int B) {
+    long long m = 1;
+    for (int b = 0; b < B; ++b) m = offsets[b + 1] - offsets[b] > m ? offsets[b + 1] - offsets[b] : m;
+    return m;
+}
+
 static int point_grid_x(const long long* offsets, int B, int sms) {
     long long max_n = 1;
     for (int b = 0; b < B; ++b) max_n = offsets[b + 1] - offsets[b] > max_n ? offsets[b + 1] - offsets[b] : max_n;
@@ -843,17 +875,19 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
             const long long gi = (cells + PT_THREADS - 1) / PT_THREADS;
             proj_init_kernel<<<(unsigned)(gi < 8LL * sms ? (gi < 1 ? 1 : gi) : 8LL * sms), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_init_kernel");
-            proj_fast_fused_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            proj_fast_fused_kernel<<<dim3(wave_grid_x(proj_fast_fused_kernel, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_fused_kernel");
         } else {
             // fp32-prefiltered path: angles (+ init, + exact theta extremes per block) -> rows -> ties
-            proj_fast_angles_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            const long long nmax = max_points(p.offsets, p.B);
+            p.gx = wave_grid_x(proj_fast_angles_kernel, nmax, p.B, sms);      // the row kernel reads gx per-block partials
+            proj_fast_angles_kernel<<<dim3(p.gx, p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
-            proj_fast_rows_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            proj_fast_rows_kernel<<<dim3(wave_grid_x(proj_fast_rows_kernel, nmax, p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
         }
         if (n_total > 0) {
-            proj_ties_kernel<<<gp, PT_THREADS, 0, st>>>(p);
+            proj_ties_kernel<<<dim3(wave_grid_x(proj_ties_kernel, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_ties_kernel");
         }
         return 0;
@@ -923,9 +957,7 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     int rc = project_common(p, n_total, d_work, d_pix, d_winner, d_diag, false, st);
     if (rc) return rc;
     const int sms = sm_count_current_device();
-    long long gx = (p.HW + PT_THREADS - 1) / PT_THREADS;
-    const long long cap = ((long long)g_pt_ctas_per_sm * sms + B - 1) / B;
-    if (gx > cap) gx = cap;
+    const int gx = wave_grid_x(proj_resolve_planes_kernel, p.HW, B, sms);
     proj_resolve_planes_kernel<<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
     SLU_LAUNCH_CHECK("proj_resolve_planes_kernel");
     return 0;
@@ -996,7 +1028,7 @@ extern "C" int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix,
     p.B = B; p.HW = HW;
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
-    const dim3 g(point_grid_x(p.offsets, B, sms), B);
+    const dim3 g(wave_grid_x(backproject_kernel, max_points(p.offsets, B), B, sms), B);
     backproject_kernel<<<g, PT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const long long*>(d_label_img), d_pix, p, reinterpret_cast<long long*>(d_out));
     SLU_LAUNCH_CHECK("backproject_kernel");
