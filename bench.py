@@ -643,7 +643,7 @@ def run_reference(args):
     from oracle import ref_arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    steps, warm = args.steps, max(1, min(args.warmup, 2))
+    steps, warm = args.steps, max(1, args.warmup)
     per_step = args.cpu_scans_per_step
     if ref_arm.available():
         scans, logits = reference_inputs(per_step, min(per_step, 4))
