@@ -690,6 +690,9 @@ __global__ void __launch_bounds__(S2_THREADS, 7) reduce_single_logits_kernel(con
 constexpr int S4_THREADS = 256;
 constexpr int S4_WARPS = S4_THREADS / 32;
 constexpr int S4_PX = 4;
+#ifndef SLU_S4_MINB
+#define SLU_S4_MINB 2
+#endif
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 v;
@@ -698,7 +701,7 @@ __device__ __forceinline__ float4 ldg_stream4(const float* p) {
 }
 
 template <int CP, bool EXACT>
-__global__ void __launch_bounds__(S4_THREADS, 2) reduce_single_logits4_kernel(const __grid_constant__ ReduceParams p) {
+__global__ void __launch_bounds__(S4_THREADS, SLU_S4_MINB) reduce_single_logits4_kernel(const __grid_constant__ ReduceParams p) {
     extern __shared__ __align__(16) unsigned char s2_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cells = p.C * p.C;
@@ -857,7 +860,7 @@ static int launch_single_logits(const ReduceParams& p, cudaStream_t stream, bool
                          reinterpret_cast<uintptr_t>(p.minorm);
     const long long tiles4 = ((p.HW + S4_THREADS * S4_PX - 1) / (S4_THREADS * S4_PX)) * p.B;
     if (!g_single_no_px4 && (p.HW & 3) == 0 && (al & 15) == 0 && tiles4 >= 8LL * sms) {
-        const long long grid4 = 2LL * sms;
+        const long long grid4 = (long long)SLU_S4_MINB * sms;
         if ((tiles4 + grid4 - 1) / grid4 * S4_PX <= S2_MAX_PX_PER_THREAD) {
             const int smem4 = (p.bins ? (p.n_bins + 1) * S4_THREADS * 12 : 0) + (p.confmat ? p.C * p.C * S4_WARPS * 4 : 0) +
                               (SLU_MAX_BINS + 1) * 4 + 16;
