@@ -430,3 +430,67 @@ def test_vectorised_normals_kernel_is_bit_identical_to_scalar(cuda):
     view.copy_(xyz)
     b = ops.frame_normals(view)
     assert torch.equal(a, b)
+
+
+def test_near_edge_queue_overflow_falls_back_inline(cuda):
+    """The per-block queue of near-edge points holds 1024 entries (DEFER_CAP); with one CTA per SM over a 16-scan batch a
+    block sees ~2 200 points, ALL planted within the prefilter's margin of a column edge here, so most of them overflow the
+    queue and take the inline fp64 path.  Result must equal the all-fp64 kernels bit for bit (and the oracle)."""
+    import os
+    H, W = 16, 2048
+    edges = np.linspace(-np.pi, np.pi, W)
+    rng = np.random.default_rng(3)
+    scans = []
+    for b in range(16):
+        n = 20_000
+        ang = edges[rng.integers(2, W - 2, n)] + rng.choice([0.0, 1e-7, -1e-7, 2e-6, -2e-6], n)
+        el = rng.uniform(-0.4, 0.05, n)
+        r = rng.uniform(3, 70, n)
+        xyzi = np.stack([r * np.cos(el) * np.cos(ang), r * np.cos(el) * np.sin(ang), r * np.sin(el), rng.uniform(0, 1, n)], 1).astype(np.float32)
+        scans.append((xyzi, synth.synth_scan(b, "tiny")[1][:1].repeat(n)))
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])]).astype(np.int64)
+    dx = torch.from_numpy(np.concatenate([s[0] for s in scans])).to(cuda)
+    dr = torch.from_numpy(np.concatenate([s[1] for s in scans]).view(np.int32)).to(cuda)
+    dl = torch.from_numpy(build_id_lut()).to(cuda)
+    old = os.environ.get("SLU_PT_CTAS_PER_SM")
+    os.environ["SLU_PT_CTAS_PER_SM"] = "1"
+    try:
+        fast = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+        prev = _lib.lib().slu_debug_project_exact(1)
+        try:
+            exact = ops.project_batch(dx, dr, offs, H, W, lut=dl)
+        finally:
+            _lib.lib().slu_debug_project_exact(prev)
+    finally:
+        if old is None:
+            del os.environ["SLU_PT_CTAS_PER_SM"]
+        else:
+            os.environ["SLU_PT_CTAS_PER_SM"] = old
+    for k in ("pix", "winner", "img", "label", "theta", "diag"):
+        assert torch.equal(fast[k], exact[k]), k
+    o = oproj.kitti_frame(scans[3][0], scans[3][1], H, W, build_id_lut())
+    assert np.array_equal(fast["pix"][offs[3]:offs[4]].cpu().numpy().astype(np.int64), o["pix"])
+
+
+def test_config1_full_size_single_scan_vs_oracle(cuda):
+    """BASELINE.json configs[0] at its real size: one 64x2048 scan, single-pass logits (T=1, C=20) -> entropy map within 1e-5 of
+    the oracle, confusion counts and reliability-bin counts exact on margin-enforced inputs, ECE within 1e-5 relative."""
+    from tests.helpers import enforce_margins
+    C, H, W = 20, 64, 2048
+    x, lab = synth.synth_mc_logits(17, 1, 1, C, H, W)
+    x, lab = enforce_margins(x, lab, conf_renorm=False)
+    cm, bins = ops.new_confmat(C, cuda), ops.new_ece_bins(15, cuda)
+    out = ops.reduce_metrics(x[0].to(cuda), lab.to(cuda), kind="logits", conf_mode=ops.CONF_RAW, ignore_index=0, confmat=cm, ece_bins=bins,
+                             want=("p_bar", "pred", "conf", "H_norm"))
+    ref = ou.mc_reduce(x)
+    assert torch.equal(out["pred"].cpu(), ref["pred"])
+    assert (out["H_norm"].cpu() - ref["H_norm"]).abs().max().item() < 1e-5
+    assert torch.equal(cm.cpu(), om.confusion_counts(ref["pred"], lab, C))
+    p = torch.softmax(x[0], dim=1)
+    cf, pr = p.max(1)
+    valid = lab != 0
+    n_ref, c_ref, s_ref = om.ece_bin_counts(cf[valid].numpy(), (pr == lab)[valid].numpy(), 15)
+    assert np.array_equal(bins[0].cpu().numpy(), n_ref) and np.array_equal(bins[1].cpu().numpy(), c_ref)
+    ece = ops.ece_from_bins(bins)[0]
+    ece_ref = om.ece_from_counts(n_ref, c_ref, s_ref)[0]
+    assert abs(ece - ece_ref) <= 1e-5 * abs(ece_ref)
