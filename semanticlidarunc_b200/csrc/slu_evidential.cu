@@ -42,7 +42,7 @@ struct EvParams {
     int B, C;
     long long HW;
     float inv_temp, eps, eps_m;
-    float logC;
+    float logC, inv_logC;
     int has_ignore;
     long long ignore;
     int n_bins;
@@ -227,8 +227,9 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
 #pragma unroll
             for (int c = 0; c < CP; ++c) z[c] = (EXACT || c < p.C) ? ldg_stream2(base + (long long)c * p.HW) : f2(-1.0e30f);
             const f2 sl = ldg_stream2(base + (long long)p.C * p.HW) * p.inv_temp;
-            // softplus (ATen: x > 20 ? x : log1p(exp(x)))
-            const f2 scale(sl.v.x > 20.f ? sl.v.x : log1pf(expf(sl.v.x)), sl.v.y > 20.f ? sl.v.y : log1pf(expf(sl.v.y)));
+            // softplus (ATen: x > 20 ? x : log1p(exp(x))), slu_packed.cuh::softplus_fast
+            float ds_unused;
+            const f2 scale(softplus_fast(sl.v.x, ds_unused), softplus_fast(sl.v.y, ds_unused));
             f2 m = z[0];
 #pragma unroll
             for (int c = 1; c < CP; ++c) m = max2(m, z[c]);
@@ -256,15 +257,46 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
         f2 asum(0.f);
         float amax0 = 0.f, amax1 = 0.f;
         int aarg0 = 0, aarg1 = 0;
+        if (GE1 && p.outputs) {
+            // alpha = fl(fl(1 + fl(s p)) + eps) is a monotone function of p, so its maximum sits at the arg-max of the softmax
+            // (pred) and only its FIRST occurrence can differ: an earlier class whose smaller p rounds to the same alpha.
+            // Count the classes that equal the maximum; the exact scan runs only if there is more than one (or NaN).
+            int neq0 = 0, neq1 = 0;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            if (EXACT || c < p.C) {
-                asum += a[c];
-                const float u = a[c].v.x, w = a[c].v.y;
-                const bool g0 = (c == 0) | (u > amax0) | ((u != u) & (amax0 == amax0));   // torch.argmax: first maximum, NaN maximal
-                const bool g1 = (c == 0) | (w > amax1) | ((w != w) & (amax1 == amax1));
-                amax0 = g0 ? u : amax0; aarg0 = g0 ? c : aarg0;
-                amax1 = g1 ? w : amax1; aarg1 = g1 ? c : aarg1;
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) {
+                    asum += a[c];
+                    amax0 = fmaxf(amax0, a[c].v.x); amax1 = fmaxf(amax1, a[c].v.y);
+                }
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+                if (EXACT || c < p.C) { neq0 += a[c].v.x == amax0 ? 1 : 0; neq1 += a[c].v.y == amax1 ? 1 : 0; }
+            aarg0 = pred0; aarg1 = pred1;
+            if (neq0 != 1 || neq1 != 1 || asum.v.x != asum.v.x || asum.v.y != asum.v.y) {
+                amax0 = 0.f; amax1 = 0.f; aarg0 = 0; aarg1 = 0;
+#pragma unroll 1
+                for (int c = 0; c < p.C; ++c) {
+                    float u = 0.f, w = 0.f;
+#pragma unroll
+                    for (int k = 0; k < CP; ++k)
+                        if (k == c) { u = a[k].v.x; w = a[k].v.y; }
+                    const bool g0 = (c == 0) | (u > amax0) | ((u != u) & (amax0 == amax0));
+                    const bool g1 = (c == 0) | (w > amax1) | ((w != w) & (amax1 == amax1));
+                    amax0 = g0 ? u : amax0; aarg0 = g0 ? c : aarg0;
+                    amax1 = g1 ? w : amax1; aarg1 = g1 ? c : aarg1;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                if (EXACT || c < p.C) {
+                    asum += a[c];
+                    const float u = a[c].v.x, w = a[c].v.y;
+                    const bool g0 = (c == 0) | (u > amax0) | ((u != u) & (amax0 == amax0));   // torch.argmax: first maximum, NaN maximal
+                    const bool g1 = (c == 0) | (w > amax1) | ((w != w) & (amax1 == amax1));
+                    amax0 = g0 ? u : amax0; aarg0 = g0 ? c : aarg0;
+                    amax1 = g1 ? w : amax1; aarg1 = g1 ? c : aarg1;
+                }
             }
         }
         if (p.alpha_out && live) {
@@ -357,10 +389,10 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
         if (live) {
             if (p.pred) *reinterpret_cast<longlong2*>(p.pred + g) = make_longlong2(pred0, pred1);
             if (p.conf) st2(p.conf + g, f2(conf0, conf1));
-            if (p.h) st2(p.h + g, f2(__fdiv_rn(H.v.x, p.logC), __fdiv_rn(H.v.y, p.logC)));
+            if (p.h) st2(p.h + g, H * p.inv_logC);
             if (p.au) st2(p.au + g, AU);
             if (p.eu) st2(p.eu + g, EU);
-            if (MI) st2(p.mi + g, f2(__fdiv_rn(MIv.v.x, p.logC), __fdiv_rn(MIv.v.y, p.logC)));
+            if (MI) st2(p.mi + g, MIv * p.inv_logC);
         }
         if (p.labels && live) {     // confusion: tester's argmax of the shape softmax; ECE: argmax of alpha/alpha0 (ece.py:75,84)
             const longlong2 lb = *reinterpret_cast<const longlong2*>(p.labels + g);
@@ -440,6 +472,7 @@ extern "C" int slu_evidential_reduce(const float* d_outputs, const float* d_alph
     p.B = B; p.C = C; p.HW = HW; p.n_px = (long long)B * HW;
     p.inv_temp = 1.0f / temperature; p.eps = eps; p.eps_m = eps_metrics;
     p.logC = normalize ? (float)log((double)C) : 1.0f;
+    p.inv_logC = normalize ? (float)(1.0 / log((double)C)) : 1.0f;
     p.has_ignore = has_ignore; p.ignore = ignore;
     p.n_bins = d_ece_bins ? n_bins : 0;
     for (int i = 0; i <= p.n_bins && d_ece_bins; ++i) p.edges[i] = h_edges[i];

@@ -561,8 +561,9 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
         f2 scale, dscale;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            scale[h] = sl[h] > 20.f ? sl[h] : log1pf(expf(sl[h]));
-            dscale[h] = sl[h] > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl[h]));       // d softplus
+            float ds;
+            scale[h] = softplus_fast(sl[h], ds);                                        // softplus and its derivative
+            dscale[h] = ds;
         }
         f2 m = pr[0];
 #pragma unroll
@@ -581,14 +582,15 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
             s2 = fma2(a[c], a[c], s2);
             const bool t0 = c == y0, t1 = c == y1;
             ay = f2(t0 ? a[c].v.x : ay.v.x, t1 ? a[c].v.y : ay.v.y);
-            if (EXACT || c < p.C) s += max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);
+            // a~ = max(y + (1 - y) alpha, eps_kl); alpha >= 1 here and the launcher requires eps_kl <= 1, so the clamp is the identity
+            if (EXACT || c < p.C) s += f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y);
         }
         // ---- both terms in ONE class loop.  Closed forms carry everything that does not need the class index:
         //   sum p^2 = s2 / D^2,  variance term = (a0^2 - s2) / G;  only sum (y - p)^2 keeps its per-class form (it cancels
         //   at confident pixels).  KL value through the merged polynomial (slu_packed.cuh::kl_value_poly):
         //   kl = lgamma(s) - psi(s)(s - C) + sum_c f(a~_c),  sum_c f = -ln2/2 sum lg2 a~ + s - C (ln 2pi + 1)/2 + sum w u(w)
-        const f2 D = a0 + p.eps_mse, invD(1.0f / D.v.x, 1.0f / D.v.y);
-        const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG(1.0f / G.v.x, 1.0f / G.v.y);
+        const f2 D = a0 + p.eps_mse, invD = rcp2(D);                  // reciprocals to 2^-23 relative: inside the loss tolerance
+        const f2 G = fma2(a0, a0, p.eps_mse) * (a0 + 1.0f), invG = rcp2(G);
         const f2 N = fma2(a0, a0, -s2);
         const f2 sp2 = s2 * invD * invD;
         const f2 var = N * invG;
@@ -606,13 +608,13 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
                 const f2 d = f2(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f) - a[c] * invD;
                 sq = fma2(d, d, sq);
                 const f2 gm = fma2(d, m2invD, fma2(a[c], m2invG, common));
-                const f2 ac = max2(f2(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y), p.eps_kl);   // a~_y = 1: f(1) = 0, no gradient
+                const f2 ac(t0 ? 1.0f : a[c].v.x, t1 ? 1.0f : a[c].v.y);              // a~_y = 1: f(1) = 0, no gradient
                 const f2 w = rcp2(ac);
                 L += lg2_2(ac);
                 Qs = fma2(w, kl_value_poly(w), Qs);
                 const f2 gA = gm * wm;
                 const f2 gB = fma2(kl_grad_term(w) - tail, wk, gA);
-                const f2 gc((!t0 && a[c].v.x > p.eps_kl) ? gB.v.x : gA.v.x, (!t1 && a[c].v.y > p.eps_kl) ? gB.v.y : gA.v.y);
+                const f2 gc(t0 ? gA.v.x : gB.v.x, t1 ? gA.v.y : gB.v.y);
                 a[c] = gc;                       // a[] now holds d(loss)/d(alpha_c), 1/n_valid included
                 gp_sum = fma2(gc, pr[c], gp_sum);
             }
@@ -622,16 +624,21 @@ __global__ void __launch_bounds__(LOSS2_THREADS, SLU_LOSS2_MINB) evidential_loss
         if (v0) { acc_mse += (double)mse.v.x; acc_kl += (double)kl.v.x; }
         if (v1) { acc_mse += (double)mse.v.y; acc_kl += (double)kl.v.y; }
         if (go) {
-            const f2 keep(v0 ? 1.0f : 0.0f, v1 ? 1.0f : 0.0f);
+            if (v0 && v1) {                                  // the common case: no masking of the stores
 #pragma unroll
-            for (int c = 0; c < CP; ++c)
-                if (EXACT || c < p.C) {
-                    const f2 o = scale * pr[c] * (a[c] - gp_sum);
-                    st2(go + (long long)c * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
-                }
-            const f2 o = gp_sum * dscale * p.inv_temp;
-            st2(go + (long long)p.C * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
-            (void)keep;
+                for (int c = 0; c < CP; ++c)
+                    if (EXACT || c < p.C) st2(go + (long long)c * p.HW, scale * pr[c] * (a[c] - gp_sum));
+                st2(go + (long long)p.C * p.HW, gp_sum * dscale * p.inv_temp);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+                    if (EXACT || c < p.C) {
+                        const f2 o = scale * pr[c] * (a[c] - gp_sum);
+                        st2(go + (long long)c * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
+                    }
+                const f2 o = gp_sum * dscale * p.inv_temp;
+                st2(go + (long long)p.C * p.HW, f2(v0 ? o.v.x : 0.f, v1 ? o.v.y : 0.f));
+            }
         }
     }
     __shared__ double s_m[LOSS2_THREADS / 32], s_k[LOSS2_THREADS / 32];
@@ -692,8 +699,8 @@ __global__ void __launch_bounds__(LOSSC_THREADS, SLU_LOSSC_MINB) evidential_loss
             pr[k] = f2((EXACT || 2 * k < p.C) ? ldg_stream(base + (long long)(2 * k) * p.HW) : -1.0e30f,
                        (EXACT || 2 * k + 1 < p.C) ? ldg_stream(base + (long long)(2 * k + 1) * p.HW) : -1.0e30f);
         const float sl = ldg_stream(base + (long long)p.C * p.HW) * p.inv_temp;
-        const float scale = sl > 20.f ? sl : log1pf(expf(sl));
-        const float dscale = sl > 20.f ? 1.f : __fdividef(1.f, 1.f + expf(-sl));       // d softplus
+        float dscale;
+        const float scale = softplus_fast(sl, dscale);
         f2 mm = pr[0];
 #pragma unroll
         for (int k = 1; k < C2; ++k) mm = max2(mm, pr[k]);
@@ -714,13 +721,13 @@ __global__ void __launch_bounds__(LOSSC_THREADS, SLU_LOSSC_MINB) evidential_loss
             s2v = fma2(a[k], a[k], s2v);
             const bool t0 = 2 * k == y, t1 = 2 * k + 1 == y;
             ay = t0 ? a[k].v.x : (t1 ? a[k].v.y : ay);
-            const f2 ac = max2(f2(t0 ? 1.0f : a[k].v.x, t1 ? 1.0f : a[k].v.y), p.eps_kl);
+            const f2 ac(t0 ? 1.0f : a[k].v.x, t1 ? 1.0f : a[k].v.y);                // alpha >= 1 >= eps_kl: no clamp
             sv += f2(in0 ? ac.v.x : 0.f, in1 ? ac.v.y : 0.f);
         }
         const float a0 = a0v.v.x + a0v.v.y, s2 = s2v.v.x + s2v.v.y, s = sv.v.x + sv.v.y;
         // per-pixel scalars (formulas: evidential_loss_fused_x2_kernel)
-        const float D = a0 + p.eps_mse, invD = 1.0f / D;
-        const float G = fmaf(a0, a0, p.eps_mse) * (a0 + 1.0f), invG = 1.0f / G;
+        const float D = a0 + p.eps_mse, invD = rcp_fast(D);
+        const float G = fmaf(a0, a0, p.eps_mse) * (a0 + 1.0f), invG = rcp_fast(G);
         const float N = fmaf(a0, a0, -s2);
         const float sp2 = s2 * invD * invD;
         const float var = N * invG;
@@ -737,12 +744,11 @@ __global__ void __launch_bounds__(LOSSC_THREADS, SLU_LOSSC_MINB) evidential_loss
             const bool t0 = 2 * k == y, t1 = 2 * k + 1 == y;
             const f2 d = f2(t0 ? 1.0f : 0.0f, t1 ? 1.0f : 0.0f) - a[k] * invD;
             const f2 gm = fma2(d, m2invD, fma2(a[k], m2invG, common));
-            const f2 ac = max2(f2((t0 || !in0) ? 1.0f : a[k].v.x, (t1 || !in1) ? 1.0f : a[k].v.y), p.eps_kl);   // padded classes: a~ = 1 (f = 0)
+            const f2 ac((t0 || !in0) ? 1.0f : a[k].v.x, (t1 || !in1) ? 1.0f : a[k].v.y);   // padded classes: a~ = 1 (f = 0)
             const f2 w = rcp2(ac);
             const f2 gA = gm * wm;
             const f2 gB = fma2(kl_grad_term(w) - tail, wk, gA);
-            const f2 gc((in0 && !t0 && a[k].v.x > p.eps_kl) ? gB.v.x : (in0 ? gA.v.x : 0.f),
-                        (in1 && !t1 && a[k].v.y > p.eps_kl) ? gB.v.y : (in1 ? gA.v.y : 0.f));
+            const f2 gc((in0 && !t0) ? gB.v.x : (in0 ? gA.v.x : 0.f), (in1 && !t1) ? gB.v.y : (in1 ? gA.v.y : 0.f));
             const f2 dm(in0 ? d.v.x : 0.f, in1 ? d.v.y : 0.f);
             sqv = fma2(dm, dm, sqv);
             Lv += lg2_2(ac);
@@ -799,11 +805,13 @@ static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) 
         count_valid_kernel<<<grid, LOSS_THREADS, 0, st>>>(p, p.count ? const_cast<double*>(p.count) : p.sums + 2);
         SLU_LAUNCH_CHECK("count_valid_kernel");
     }
-    const bool pair_ok = (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
+    // the packed kernels drop the a~ >= eps_kl clamp (alpha = 1 + softplus * softmax + eps >= 1): valid while eps_kl <= 1, eps_alpha >= 0
+    const bool packed_math_ok = p.eps_kl <= 1.0f && p.eps_alpha >= 0.0f;
+    const bool pair_ok = packed_math_ok && (p.HW & 1) == 0 && (reinterpret_cast<uintptr_t>(p.target) & 15) == 0 &&
                          (reinterpret_cast<uintptr_t>(p.outputs) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.grad) & 7) == 0;
     // class-pair kernel: shapes the pixel-pair kernel cannot take (odd HW, unaligned views), or SLU_LOSS_VARIANT=1.  On
     // aligned even shapes the two measure the same (0.135 / 0.140 ms per 16 scans), the pixel-pair one is kept there.
-    if (!g_no_packed && (g_loss_variant == 1 || (g_loss_variant == 0 && !pair_ok))) {
+    if (!g_no_packed && packed_math_ok && (g_loss_variant == 1 || (g_loss_variant == 0 && !pair_ok))) {
         const long long capc = (long long)SLU_LOSSC_MINB * sms;
         const long long chunksc = (p.n_px + LOSSC_THREADS - 1) / LOSSC_THREADS;
         const unsigned gridc = (unsigned)(chunksc < capc ? chunksc : capc);
