@@ -324,9 +324,12 @@ int slu_class_score_hist(const float* d_score, const int64_t* d_labels, int64_t 
  *                                 #points within 4 ulp of a bin edge (index could differ from numpy's)]
  */
 int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW);
-/* Test / profiling switch: on=1 makes slu_project_batch run the exact fp64 kernels for every point instead
- * of the fp32-prefiltered ones (bit-identical results, ~2x slower); on=0 restores the default; on<0 only
- * queries.  Returns the previous setting.  Process-wide host state, not for concurrent use. */
+/* Test / profiling switch of slu_project_batch: on=1 runs the exact fp64 kernels for every point instead of the
+ * fp32-prefiltered ones (bit-identical results, ~2x slower); on=2 runs the three-launch "cell" pipeline (one fused point
+ * pass whose depth test is a 128-bit compare-and-swap on a (range, index) cell per pixel; bit-identical results, same
+ * speed with an automatic range, slower with a fixed one; needs the larger workspace slu_project_workspace_bytes
+ * already reports); on=0 restores the default; on<0 only queries.  Returns the previous setting.  Process-wide host
+ * state, not for concurrent use. */
 int slu_debug_project_exact(int on);
 /* diagnostic: out[i] = the projection prefilter's fp32 arctangent of (y[i], x[i]); NaN for zero / denormal / huge / non-finite
  * inputs (those points always take the fp64 path).  Tests bound its error against float64 atan2. */

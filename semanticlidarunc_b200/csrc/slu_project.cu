@@ -129,6 +129,10 @@ struct ProjParams {
     int* part_diag;                // [B*gx*2] per-block (missing ids, near-edge points)
     double* part_exact;            // [B*gx*2] per-block exact fp64 theta (min, max) over the block's candidates
     int gx;                        // blocks per scan of the point kernels
+    int dbg_atom;                  // timing experiments only (SLU_P3_ATOM): 1 = 64-bit RED.MIN on the key, 2 = no atomic
+    unsigned long long* dbg_times; // timing experiments only (SLU_P3_TIMES=1): per-block globaltimer stamps, [3][4096][8], or NULL
+    struct Cell* cell;             // [B*HW] 128-bit (range key, point index) cells of the single-pass depth test
+    int want_pix, want_winner;     // the caller asked for d_pix / d_winner (the cell pipeline skips the stores otherwise)
     // outputs
     int* pix;                      // [n_total]
     int* winner;                   // [B*HW]
@@ -678,13 +682,478 @@ __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_cons
     }
 }
 
+
+// ====================================================================================================
+// Cell pipeline (round 2; an A/B alternative selected with slu_debug_project_exact(2), NOT the default): THREE launches, one
+// pass of atomics.
+//
+//   P1 extremes  cells <- empty; per block the fp32 tangent of the elevation z / rho (monotone in theta: no arctangent)
+//                gives the block's extreme candidates, which alone are evaluated in fp64 -> exact (min, max) partials
+//                (with a fixed elevation range P1 only resets the cells)
+//   P2 points    ONE fused pass per point: fp32-prefiltered column and row (fp64 near edges, as above), then the depth
+//                test as a 128-bit compare-and-swap on the pixel's (range key, point index) cell.  The cell orders
+//                points by (float64 range, index), so the winner INCLUDING the lowest-index rule for exact ties is
+//                settled by this pass: no separate tie pass, no second gather of per-point state (theta32 / col / rkey
+//                never exist in memory).
+//   P3 resolve   per pixel: read the cell, gather the winner, write the planes.
+//
+// The first CAS of a point assumes an empty cell, so the common case (first point of its pixel) costs one L2 round
+// trip; a failed CAS returns the resident (key, index), the point retires if the resident one is better and retries
+// against the value it saw otherwise.  The cell only ever moves down the total order, whatever the interleaving: the
+// result is deterministic and bit-identical to the exact kernels (tests/test_gpu_project.py).
+//
+// Measured on B200 (16 HDL-64 scans, graph replay): 0.076-0.078 ms against 0.076 ms for the four-launch path, and 0.158
+// against 0.135 ms with a fixed range -- the pass it deletes (ties, 11 us) and the per-point state it never writes are
+// paid back by the fused kernel: ATOMG.CAS.128 costs what RED.MIN.64 costs (the same 45.7 us kernel with either, 30.3 us
+// with no atomic at all: ~15 us per 1.9 M L2 atomics whatever their width), the fused loop needs 48-64 registers (4-5 CTAs
+// per SM) and its blocks finish 12 us apart (31.8 ... 44.5 us after a common start; tools/proj_timeline.py), so the
+// slowest SMs set the time.  It stays in the library as the measured alternative (profiles/projection_r02.md).
+// ====================================================================================================
+struct alignas(16) Cell { unsigned long long idx, key; };     // one little-endian 128-bit word: (key << 64) | idx
+constexpr unsigned long long CELL_EMPTY = ~0ull;
+
+__device__ __forceinline__ void cas128(Cell* addr, unsigned long long exp_lo, unsigned long long exp_hi,
+                                       unsigned long long new_lo, unsigned long long new_hi,
+                                       unsigned long long& old_lo, unsigned long long& old_hi) {
+    asm volatile(
+        "{\n\t.reg .b128 e, n, o;\n\t"
+        "mov.b128 e, {%3, %4};\n\t"
+        "mov.b128 n, {%5, %6};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%2], e, n;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old_lo), "=l"(old_hi)
+        : "l"(addr), "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi)
+        : "memory");
+}
+
+typedef unsigned __int128 u128;
+__device__ __forceinline__ u128 cas128q(Cell* addr, u128 expect, u128 desired) {      // result stays ONE 128-bit register
+    u128 old;
+    asm volatile("atom.global.relaxed.gpu.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(expect), "q"(desired) : "memory");
+    return old;
+}
+
+// strict total order of the depth test: smaller float64 range first (same_range: r^2 keys whose square roots coincide are
+// the ties they are in the reference), then the lower point index
+__device__ __forceinline__ bool cell_before(const ProjParams& p, unsigned long long ka, unsigned long long ia,
+                                            unsigned long long kb, unsigned long long ib) {
+    if (ka == kb) return ia < ib;
+    const bool a_small = ka < kb;
+    if (same_range(p, a_small ? kb : ka, a_small ? ka : kb)) return ia < ib;
+    return a_small;
+}
+
+// retire or retry after a failed first CAS (old = what the cell held)
+__device__ __forceinline__ void depth_test_finish(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
+                                                  unsigned long long ol, unsigned long long oh) {
+    unsigned long long el = CELL_EMPTY, eh = CELL_EMPTY;
+    while (!(ol == el && oh == eh)) {
+        if (!cell_before(p, key, idx, oh, ol)) return;          // the resident point stays
+        el = ol; eh = oh;
+        cas128(a, el, eh, idx, key, ol, oh);
+    }
+}
+__device__ __forceinline__ void depth_test(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx) {
+    unsigned long long ol, oh;
+    cas128(a, CELL_EMPTY, CELL_EMPTY, idx, key, ol, oh);
+    depth_test_finish(p, a, key, idx, ol, oh);
+}
+
+// fp32 tangent of the elevation, z / sqrt(x^2 + y^2): relative error <= 5e-7 (two rounded products and a sum, rsqrt.approx
+// <= 2 ulp, one product, plus the float32 view of yaw-rotated coordinates).  NaN when the operands leave the range in
+// which that bound holds (rho^2 outside [1e-30, 1e30], |t| >= 1e9, non-finite input): such points are always candidates.
+__device__ __forceinline__ float tan_elev32(float x, float y, float z) {
+    const float s = fmaf(x, x, y * y);
+    const float t = z * rsqrtf(s);
+    const bool ok = s > 1.0e-30f && s < 1.0e30f && fabsf(t) < 1.0e9f;
+    return ok ? t : __int_as_float(0x7fc00000);
+}
+// |t~ - t| <= TAN_BAND(t~): 4x the fp32 bound above, plus an absolute floor that covers the rounding of the float64 theta
+// itself near the horizon (theta carries ~4e-16 absolute; d theta / d t = 1 / (1 + t^2))
+__device__ __forceinline__ float tan_band(float t) { return fmaf(2.0e-6f, fabsf(t), 1.0e-9f); }
+
+__device__ __forceinline__ void dbg_stamp(const ProjParams& p, int kernel, int slot) {
+    if (p.dbg_times && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.dbg_times[((long long)kernel * 4096 + blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+    }
+}
+constexpr int P1_NB = 4;                    // points a thread of P1 has in flight per iteration
+
+// float32 coordinates of a point as the prefilter sees them (float32(rotated float64 coordinate) under a yaw)
+__device__ __forceinline__ void coords32(const ProjParams& p, int b, const float4 v, float& x, float& y, float& z) {
+    x = v.x; y = v.y; z = v.z;
+    if (p.yaw) {
+        const Pt q = load_pt(p, b, v);
+        x = (float)q.x; y = (float)q.y;
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS) proj3_extremes_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b];
+    const int npts = (int)(p.offsets[b + 1] - n0);
+    const int tid0 = blockIdx.x * PT_THREADS + threadIdx.x, stride = gridDim.x * PT_THREADS;
+    dbg_stamp(p, 0, 0);
+    {
+        ulonglong2* cell = reinterpret_cast<ulonglong2*>(p.cell + (long long)b * p.HW);
+        const ulonglong2 empty = make_ulonglong2(CELL_EMPTY, CELL_EMPTY);
+        const int hw = (int)p.HW;
+        for (int i = tid0; i < hw; i += stride) cell[i] = empty;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { p.diag[2 * b] = 0; p.diag[2 * b + 1] = 0; }
+    if (p.use_range) return;
+    dbg_stamp(p, 0, 1);
+    const float4* __restrict__ pts = p.xyzi + n0;
+    // pass A: every thread keeps the smallest and second smallest (largest, second largest) fp32 tangent of its points
+    // and the index of the extreme one; points whose tangent is not a number are always candidates and are evaluated in
+    // fp64 on the spot
+    float m1 = INFINITY, m2 = INFINITY, M1 = -INFINITY, M2 = -INFINITY;
+    int i1 = -1, j1 = -1;
+    double emin = INFINITY, emax = -INFINITY;
+    for (int i = tid0; i < npts; i += stride * P1_NB) {
+        float4 v[P1_NB];
+#pragma unroll
+        for (int k = 0; k < P1_NB; ++k) {
+            const int idx = i + k * stride;
+            v[k] = idx < npts ? __ldg(pts + idx) : make_float4(1.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < P1_NB; ++k) {
+            const int idx = i + k * stride;
+            if (idx >= npts) continue;
+            float x, y, z;
+            coords32(p, b, v[k], x, y, z);
+            const float t = tan_elev32(x, y, z);
+            if (t != t) {
+                const double th = exact_theta(load_pt(p, b, v[k]));
+                if (th == th) { emin = fmin(emin, th); emax = fmax(emax, th); }
+                continue;
+            }
+            if (t < m1) { m2 = m1; m1 = t; i1 = idx; } else if (t < m2) m2 = t;
+            if (t > M1) { M2 = M1; M1 = t; j1 = idx; } else if (t > M2) M2 = t;
+        }
+    }
+    dbg_stamp(p, 0, 2);
+    __shared__ float s_min[PT_THREADS / 32], s_max[PT_THREADS / 32];
+    float tmin = m1, tmax = M1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_min[w] = tmin; s_max[w] = tmax; }
+    __syncthreads();
+    float bmin = s_min[0], bmax = s_max[0];
+    for (int i = 1; i < PT_THREADS / 32; ++i) { bmin = fminf(bmin, s_min[i]); bmax = fmaxf(bmax, s_max[i]); }
+    // The point P attaining the scan's exact minimum has t(P) <= t(Q) for every Q (theta is monotone in t = tan theta), so
+    // t~(P) - band <= t(P) <= t(Q) <= t~(Q) + band for the Q that set this block's fp32 minimum: P passes the test below in
+    // its own block.  Usually only a thread's extreme point can pass; when a thread's SECOND point passes as well, the
+    // block walks its points again and evaluates every one that passes.
+    const float thr_lo = bmin + tan_band(bmin), thr_hi = bmax - tan_band(bmax);
+    const bool c_lo = i1 >= 0 && !(m1 - tan_band(m1) > thr_lo), c_hi = j1 >= 0 && !(M1 + tan_band(M1) < thr_hi);
+    const bool more = (m2 < INFINITY && !(m2 - tan_band(m2) > thr_lo)) || (M2 > -INFINITY && !(M2 + tan_band(M2) < thr_hi));
+    if (!__syncthreads_or(more ? 1 : 0)) {
+        if (c_lo) {
+            const double th = exact_theta(load_pt(p, b, __ldg(pts + i1)));
+            if (th == th) { emin = fmin(emin, th); emax = fmax(emax, th); }
+        }
+        if (c_hi && !(c_lo && j1 == i1)) {
+            const double th = exact_theta(load_pt(p, b, __ldg(pts + j1)));
+            if (th == th) { emin = fmin(emin, th); emax = fmax(emax, th); }
+        }
+    } else {
+        for (int i = tid0; i < npts; i += stride) {
+            const float4 v = __ldg(pts + i);
+            float x, y, z;
+            coords32(p, b, v, x, y, z);
+            const float t = tan_elev32(x, y, z);
+            if (t != t) continue;                               // already evaluated in pass A
+            const float band = tan_band(t);
+            if (!(t - band > thr_lo) || !(t + band < thr_hi)) {
+                const double th = exact_theta(load_pt(p, b, v));
+                if (th == th) { emin = fmin(emin, th); emax = fmax(emax, th); }
+            }
+        }
+    }
+    __shared__ double s_emin[PT_THREADS / 32], s_emax[PT_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        emin = fmin(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+        emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_emin[w] = emin; s_emax[w] = emax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < PT_THREADS / 32; ++i) { emin = fmin(emin, s_emin[i]); emax = fmax(emax, s_emax[i]); }
+        const long long slot = (long long)b * p.gx + blockIdx.x;
+        p.part_exact[2 * slot] = emin; p.part_exact[2 * slot + 1] = emax;
+    }
+    dbg_stamp(p, 0, 3);
+}
+
+// bins of one point from its exact fp64 angles (the queue / overflow path of P2)
+// (a real call, not inlined: the fp64 arctangents would otherwise set the register budget of the whole point kernel)
+__device__ __noinline__ int exact_pixel_call(double x, double y, double z, int cnt_w, int cnt_h, double lo, double hi, int W, int H,
+                                             int use_range, int* near_cnt) {
+    // the float64 edges are rebuilt here, on the rare path, rather than held in registers across the point loop
+    Pt q; q.x = x; q.y = y; q.z = z;
+    bool near;
+    int nc = 0;
+    if (cnt_w < 0) {
+        cnt_w = count_le(make_edges(-PI, PI, W), exact_phi(q), near);
+        if (near) ++nc;
+    }
+    if (cnt_h < 0) {
+        const double th = exact_theta(q);
+        cnt_h = count_le(make_edges(lo, hi, H), th, near);
+        if (near && !use_range) near = !(th == lo || th == hi);         // the scan's own extremes sit ON the outer edges
+        if (near) ++nc;
+    }
+    *near_cnt += nc;
+    int c = W - 1 - cnt_w;                          // cnt in [0, n]: only -1 wraps (numpy's negative index)
+    if (c < 0) c += W;
+    int rr = H - 1 - cnt_h;
+    if (rr < 0) rr += H;
+    return rr * W + c;
+}
+// cnt_w / cnt_h >= 0: that bin is already certified by the prefilter and only the other angle is evaluated
+__device__ __forceinline__ int exact_pixel(const ProjParams& p, const Pt q, int cnt_w, int cnt_h, double lo, double hi, int& near_cnt) {
+    int nc = 0;
+    const int px = exact_pixel_call(q.x, q.y, q.z, cnt_w, cnt_h, lo, hi, p.W, p.H, p.use_range, &nc);
+    near_cnt += nc;
+    return px;
+}
+
+// depth key of a point: the bits of r^2 = (x^2 + y^2) + z^2 in numpy's operation order (utils.py:299 before its sqrt; the
+// tie rule of cell_before restores the order by r).  File coordinates are float32 values, whose squares are exact in
+// float64, so fl(x^2 + y^2) and fl(that + z^2) are single-rounding fused operations; yaw-rotated coordinates are not
+// float32 values and take the five separately rounded operations.  fmask = 0 (nearest wins) or 0x7fff... (farthest wins:
+// MAX - bits == MAX ^ bits).
+template <bool YAW>
+__device__ __forceinline__ unsigned long long range_key(const ProjParams& p, int b, const float4 v, unsigned long long fmask) {
+    double r2;
+    if (YAW) {
+        const Pt q = load_pt(p, b, v);
+        r2 = __dadd_rn(__dadd_rn(__dmul_rn(q.x, q.x), __dmul_rn(q.y, q.y)), __dmul_rn(q.z, q.z));
+    } else {
+        const double x = (double)v.x, y = (double)v.y, z = (double)v.z;
+        r2 = __fma_rn(z, z, __fma_rn(x, x, __dmul_rn(y, y)));
+    }
+    return ((unsigned long long)__double_as_longlong(r2) & 0x7fffffffffffffffull) ^ fmask;
+}
+
+// fast_atan2 without its operand checks: the caller guarantees finite operands with max(|x|, |y|) in [1e-15, 1e30)
+__device__ __forceinline__ float fast_atan2_nc(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float q = __fdividef(mn, mx);
+    const float t = q * q;
+    float a = fmaf(6.811646790e-03f, t, -3.360372957e-02f);
+    a = fmaf(a, t, 7.962303474e-02f);
+    a = fmaf(a, t, -1.323330193e-01f);
+    a = fmaf(a, t, 1.980780307e-01f);
+    a = fmaf(a, t, -3.331736634e-01f);
+    a = fmaf(a, t, 9.999961108e-01f);
+    float r = a * q;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return y < 0.f ? -r : r;
+}
+__device__ __forceinline__ float sqrt_approx(float s) {          // MUFU.SQRT, relative error <= 2^-23
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+}
+// fast_count_le for an angle that is known to be finite
+__device__ __forceinline__ int fast_count_le_nc(const FastEdges& f, float a32) {
+    const float t = fmaf(a32, f.inv_step, f.c0);
+    const float fl = floorf(t);
+    const float lo = t - fl;
+    const bool ok = lo > f.margin_bins && lo < 1.0f - f.margin_bins && fl >= 0.0f && fl <= f.last;
+    return ok ? (int)fl + 1 : -1;
+}
+
+// the rare half of the depth test, a real call: the compare-and-swap retry loop with its float64 square roots would
+// otherwise be inlined at every site and set the register budget of the point loop
+__device__ __noinline__ void depth_test_retry(Cell* a, unsigned long long key, unsigned long long idx,
+                                              unsigned long long ol, unsigned long long oh, int key_sq, int farthest) {
+    ProjParams q;                                   // only the two fields same_range reads
+    q.key_sq = key_sq; q.farthest = farthest;
+    depth_test_finish(q, a, key, idx, ol, oh);
+}
+__device__ __forceinline__ void depth_test_settle(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
+                                                  unsigned long long ol, unsigned long long oh) {
+    if ((ol & oh) != CELL_EMPTY) depth_test_retry(a, key, idx, ol, oh, p.key_sq, p.farthest);
+}
+
+// MINB resident CTAs per SM (the register budget); YAW: the loaders' yaw augmentation is applied; IDS: raw label ids are
+// checked against the look-up table.  The point loop is a three-stage software pipeline per thread: the point two
+// iterations ahead is being LOADED, the next point's bins and key are COMPUTED, and the current point's compare-and-swap
+// -- issued at the top of the iteration -- is only examined at the bottom, after that arithmetic, so neither the load nor
+// the atomic round trip is waited for.  (Examining the result straight away, or carrying it into the next iteration,
+// costs a full L2 round trip per point: ptxas copies a carried 128-bit result out of its register quad at once.)
+template <int NB, int MINB, bool YAW, bool IDS>      // NB: unused (kept for the launch macro)
+__global__ void __launch_bounds__(PT_THREADS, MINB) proj3_points_kernel(const __grid_constant__ ProjParams p) {
+    const int b = blockIdx.y;
+    const long long n0 = p.offsets[b];
+    const int npts = (int)(p.offsets[b + 1] - n0);
+    __shared__ int s_q[DEFER_CAP];
+    __shared__ unsigned s_qc[DEFER_CAP];            // the bin counts the prefilter DID certify (0xffff = not certified), cnt_w | cnt_h << 16
+    __shared__ int s_qn;
+    __shared__ FastEdges s_fw, s_fh;
+    __shared__ double s_lohi[2];
+    dbg_stamp(p, 1, 0);
+    {
+        double lo, hi;
+        scan_theta_range_fast(p, b, lo, hi);
+        if (threadIdx.x == 0) {                     // the float64 divisions of the edge set-up run once per block
+            s_qn = 0;
+            s_lohi[0] = lo; s_lohi[1] = hi;
+            s_fw = make_fast_edges(make_edges(-PI, PI, p.W));
+            s_fh = make_fast_edges(make_edges(lo, hi, p.H));
+            if (blockIdx.x == 0 && p.theta_out) { p.theta_out[2 * b] = lo; p.theta_out[2 * b + 1] = hi; }
+        }
+    }
+    __syncthreads();
+    dbg_stamp(p, 1, 1);
+    const FastEdges fw = s_fw, fh = s_fh;
+    int missing = 0, near_cnt = 0;
+    const float4* __restrict__ pts = p.xyzi + n0;
+    const unsigned* __restrict__ labs = p.raw_label + (IDS ? n0 : 0);
+    int* __restrict__ pix = p.pix + n0;
+    Cell* cell = p.cell + (long long)b * p.HW;
+    const int W = p.W, H = p.H;
+    const unsigned long long fmask = p.farthest ? 0x7fffffffffffffffull : 0ull;
+    const int tid0 = blockIdx.x * PT_THREADS + threadIdx.x, stride = gridDim.x * PT_THREADS;
+    const u128 EMPTY128 = ~(u128)0;
+
+    // bins of one point from fp32 angles; -1 and a queue entry when it is near an edge
+    auto classify = [&](int idx, const float4 v) -> int {
+        float x = v.x, y = v.y;
+        const float z = v.z;
+        if (YAW) {
+            const Pt q = load_pt(p, b, v);
+            x = (float)q.x; y = (float)q.y;
+        }
+        // one operand check for both arctangents; whatever fails it takes the fp64 path through the queue
+        const float s = fmaf(x, x, y * y);
+        int cnt_w = -1, cnt_h = -1;
+        if (s > 1.0e-30f && s < 1.0e30f && fabsf(z) < 1.0e30f) {
+            cnt_w = fast_count_le_nc(fw, fast_atan2_nc(y, x));
+            cnt_h = fast_count_le_nc(fh, 1.57079632679489662f - fast_atan2_nc(sqrt_approx(s), z));
+        }
+        if ((cnt_w | cnt_h) < 0) {
+            // near an edge: queue the point, the fp64 angle runs once per block on the packed queue (a queue that
+            // overflows is dropped as a whole: the block then re-scans its points for the near-edge ones, below)
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < DEFER_CAP) { s_q[slot] = idx; s_qc[slot] = ((unsigned)cnt_w & 0xffffu) | ((unsigned)cnt_h << 16); }
+            return -1;
+        }
+        int c = W - 1 - cnt_w;                                   // cnt in [0, n]: only -1 wraps (numpy's negative index)
+        if (c < 0) c += W;
+        int rr = H - 1 - cnt_h;
+        if (rr < 0) rr += H;
+        return rr * W + c;
+    };
+
+    int idx = tid0, idx_nx = tid0 + stride;
+    bool have = idx < npts;
+    float4 v = have ? __ldg(pts + idx) : make_float4(1.f, 0.f, 0.f, 0.f);
+    unsigned raw = (IDS && have) ? (__ldg(labs + idx) & 0xffffu) : 0u;
+    float4 v_nx = idx_nx < npts ? __ldg(pts + idx_nx) : make_float4(1.f, 0.f, 0.f, 0.f);
+    unsigned raw_nx = (IDS && idx_nx < npts) ? (__ldg(labs + idx_nx) & 0xffffu) : 0u;
+    int px = have ? classify(idx, v) : -1;
+    unsigned long long rk = px >= 0 ? range_key<YAW>(p, b, v, fmask) : 0ull;
+    while (have) {
+        // stage 3 of the current point: issue its depth test and its label look-up
+        u128 old = EMPTY128;
+        if (px >= 0) {
+            if (p.want_pix) pix[idx] = px;
+            if (p.dbg_atom == 0) old = cas128q(cell + px, EMPTY128, ((u128)rk << 64) | (unsigned long long)(unsigned)idx);
+            else if (p.dbg_atom == 1) atomicMin(&cell[px].key, rk);
+        }
+        int lutv = 0;
+        if (IDS) lutv = __ldg(p.lut + raw);
+        // stage 1 of the point two ahead, stage 2 of the next point
+        const bool have_nx = idx_nx < npts;
+        const float4 v2 = v_nx;
+        const unsigned raw2 = raw_nx;
+        const int idx_nn = idx_nx + stride;
+        v_nx = idx_nn < npts ? __ldg(pts + idx_nn) : make_float4(1.f, 0.f, 0.f, 0.f);
+        if (IDS) raw_nx = idx_nn < npts ? (__ldg(labs + idx_nn) & 0xffffu) : 0u;
+        const int px2 = have_nx ? classify(idx_nx, v2) : -1;
+        const unsigned long long rk2 = px2 >= 0 ? range_key<YAW>(p, b, v2, fmask) : 0ull;
+        // the current point's results are back by now
+        if (IDS) missing += lutv < 0 ? 1 : 0;                    // KeyError of the reference's remap loop
+        if (old != EMPTY128)
+            depth_test_retry(cell + px, rk, (unsigned long long)(unsigned)idx, (unsigned long long)old, (unsigned long long)(old >> 64), p.key_sq, p.farthest);
+        idx = idx_nx; idx_nx = idx_nn; px = px2; rk = rk2; raw = raw2; have = have_nx;
+    }
+    dbg_stamp(p, 1, 2);
+    __syncthreads();
+    dbg_stamp(p, 1, 3);
+    const int qn = s_qn;
+    const double lo = s_lohi[0], hi = s_lohi[1];
+    if (qn <= DEFER_CAP) {
+        for (int i = threadIdx.x; i < qn; i += PT_THREADS) {
+            const int idx = s_q[i];
+            const unsigned qc = s_qc[i];
+            const float4 v = __ldg(pts + idx);
+            // only the angle the prefilter could not certify is evaluated in fp64 (a certified bin is not near an edge)
+            const int cw = (qc & 0xffffu) == 0xffffu || W > 0xfffe ? -1 : (int)(qc & 0xffffu);
+            const int ch = (qc >> 16) == 0xffffu || H > 0xfffe ? -1 : (int)(qc >> 16);
+            const int px = exact_pixel(p, load_pt(p, b, v), cw, ch, lo, hi, near_cnt);
+            if (p.want_pix) pix[idx] = px;
+            unsigned long long ol, oh;
+            const unsigned long long rk = range_key<YAW>(p, b, v, fmask);
+            cas128(cell + px, CELL_EMPTY, CELL_EMPTY, (unsigned long long)idx, rk, ol, oh);
+            depth_test_settle(p, cell + px, rk, (unsigned long long)idx, ol, oh);
+        }
+    } else {
+        // more near-edge points than the queue holds (adversarial inputs): every thread walks its points again and
+        // settles the near-edge ones in place
+        for (int idx = tid0; idx < npts; idx += stride) {
+            const float4 v = __ldg(pts + idx);
+            float x = v.x, y = v.y;
+            if (YAW) {
+                const Pt q = load_pt(p, b, v);
+                x = (float)q.x; y = (float)q.y;
+            }
+            const float s = fmaf(x, x, y * y);
+            if (s > 1.0e-30f && s < 1.0e30f && fabsf(v.z) < 1.0e30f &&
+                fast_count_le_nc(fw, fast_atan2_nc(y, x)) >= 0 &&
+                fast_count_le_nc(fh, 1.57079632679489662f - fast_atan2_nc(sqrt_approx(s), v.z)) >= 0) continue;
+            const int px = exact_pixel(p, load_pt(p, b, v), -1, -1, lo, hi, near_cnt);
+            if (p.want_pix) pix[idx] = px;
+            unsigned long long ol, oh;
+            const unsigned long long rk = range_key<YAW>(p, b, v, fmask);
+            cas128(cell + px, CELL_EMPTY, CELL_EMPTY, (unsigned long long)idx, rk, ol, oh);
+            depth_test_settle(p, cell + px, rk, (unsigned long long)idx, ol, oh);
+        }
+    }
+    missing = __reduce_add_sync(0xffffffffu, missing);
+    near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
+    if ((threadIdx.x & 31) == 0) {
+        if (missing) atomicAdd(&p.diag[2 * b], missing);
+        if (near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
+    }
+    __syncthreads();
+    dbg_stamp(p, 1, 4);
+}
+
 // planes: 0 x, 1 y, 2 z, 3 range (fp32 norm of the fp32 xyz, dataloader_semantic_KITTI.py:83),
 //         4 intensity, 5 label (train id as float, as the reference's float32 image carries it)
+template <bool CELLS>
 __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b];
     const long long stride = (long long)gridDim.x * blockDim.x;
     int* winner = p.winner + (long long)b * p.HW;
+    const ulonglong2* cell = reinterpret_cast<const ulonglong2*>(p.cell + (long long)b * p.HW);
+    if (CELLS) dbg_stamp(p, 2, 0);
     // the gather is a chain of dependent loads (winner -> point -> raw label -> LUT): PT_BATCH pixels per thread go
     // through it together, one L2 round trip per link for the whole batch
     for (long long pb = (long long)blockIdx.x * blockDim.x + threadIdx.x; pb < p.HW; pb += stride * PT_BATCH) {
@@ -693,7 +1162,15 @@ __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const _
         unsigned raw[PT_BATCH];
         float lab[PT_BATCH];
 #pragma unroll
-        for (int k = 0; k < PT_BATCH; ++k) w[k] = (pb + k * stride < p.HW) ? winner[pb + k * stride] : 0x7fffffff;
+        for (int k = 0; k < PT_BATCH; ++k) {
+            if (CELLS) {
+                ulonglong2 c = make_ulonglong2(CELL_EMPTY, CELL_EMPTY);
+                if (pb + k * stride < p.HW) c = cell[pb + k * stride];
+                w[k] = c.y == CELL_EMPTY ? 0x7fffffff : (int)c.x;
+            } else {
+                w[k] = (pb + k * stride < p.HW) ? winner[pb + k * stride] : 0x7fffffff;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < PT_BATCH; ++k) {
             const bool has = w[k] != 0x7fffffff;
@@ -719,7 +1196,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const _
                 rng = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(q.x, q.x), __fmul_rn(q.y, q.y)), __fmul_rn(q.z, q.z)));
             }
             const long long cell = (long long)b * p.HW + px;
-            winner[px] = w[k] == 0x7fffffff ? -1 : w[k];
+            if (!CELLS || p.want_winner) winner[px] = w[k] == 0x7fffffff ? -1 : w[k];
             if (p.label_img) p.label_img[cell] = (long long)lab[k];
             if (p.img) {
                 float* o = p.img + (long long)b * 6 * p.HW + px;
@@ -727,6 +1204,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_resolve_planes_kernel(const _
             }
         }
     }
+    if (CELLS) dbg_stamp(p, 2, 1);
 }
 
 // generic form: [H,W,Cin] float32 = float(pc[winner]) per channel (utils.py:341-344)
@@ -770,7 +1248,7 @@ static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 
 constexpr int MAX_GX = 2048;         // upper bound of blocks per scan (partials are sized for it)
 struct Workspace {
-    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, theta32, part_min, part_max, part_diag, part_exact, total;
+    int64_t theta, rkey, col, key, tminmax, pix, winner, diag, theta32, part_min, part_max, part_diag, part_exact, cell, total;
 };
 static Workspace carve(int64_t n_total, int B, int64_t HW) {
     Workspace w;
@@ -784,11 +1262,14 @@ static Workspace carve(int64_t n_total, int B, int64_t HW) {
     w.winner = o;  o = align_up(o + (int64_t)B * HW * 4, 256);
     w.diag = o;    o = align_up(o + (int64_t)B * 8, 256);
     w.theta32 = o; o = align_up(o + n_total * 4, 256);
-    const int64_t gx_max = n_total / PT_THREADS + 1 < MAX_GX ? n_total / PT_THREADS + 1 : MAX_GX;
+    // blocks per scan never exceed ceil(max(points of a scan, pixels) / PT_THREADS) (the extremes kernel also resets the cells)
+    const int64_t items_max = n_total > HW ? n_total : HW;
+    const int64_t gx_max = items_max / PT_THREADS + 1 < MAX_GX ? items_max / PT_THREADS + 1 : MAX_GX;
     w.part_min = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
     w.part_max = o;  o = align_up(o + (int64_t)B * gx_max * 4, 256);
     w.part_diag = o; o = align_up(o + (int64_t)B * gx_max * 8, 256);
     w.part_exact = o; o = align_up(o + (int64_t)B * gx_max * 16, 256);
+    w.cell = o;    o = align_up(o + (int64_t)B * HW * 16, 256);
     w.total = o;
     return w;
 }
@@ -802,21 +1283,31 @@ static int g_pt_ctas_per_sm = [] { const char* e = getenv("SLU_PT_CTAS_PER_SM");
 // partial last wave 0.090-0.094 ms per 16 HDL-64 scans).  Each kernel's grid is therefore sized from ITS occupancy.
 template <typename K>
 static int resident_ctas_per_sm(K kernel) {
-    static int cached = 0;                       // one instantiation per kernel type: the value depends on the kernel only
-    if (cached == 0) {
-        int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, PT_THREADS, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
-        cached = n;
-    }
+    // cached per kernel ADDRESS (several kernels share one function type, so a per-type static would hand every one of
+    // them the occupancy of whichever was asked first)
+    static const void* seen[32];
+    static int value[32];
+    static int n_seen = 0;
     const char* e = getenv("SLU_PT_CTAS_PER_SM");
     const int forced = e ? atoi(e) : 0;
-    return forced > 0 ? forced : cached;
+    if (forced > 0) return forced;
+    const void* key = reinterpret_cast<const void*>(kernel);
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == key) return value[i];
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, PT_THREADS, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 4; }
+    if (n_seen < 32) { seen[n_seen] = key; value[n_seen] = n; ++n_seen; }
+    return n;
 }
 
+// waves of the kernels WITHOUT per-CTA set-up (ties, resolve, back-projection): short CTAs that the hardware scheduler deals
+// out as SMs free up, which evens out the 30-40 % spread in per-SM speed that a single static wave leaves as its tail
+static int g_light_waves = [] { const char* e = getenv("SLU_PT_LIGHT_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1; }();
+
 template <typename K>
-static int wave_grid_x(K kernel, long long items_max, int B, int sms) {
+static int wave_grid_x(K kernel, long long items_max, int B, int sms, int waves = 1) {
     long long gx = (items_max + PT_THREADS - 1) / PT_THREADS;
-    long long cap = ((long long)resident_ctas_per_sm(kernel) * sms) / B;      // floor: never more than one wave
+    long long cap = ((long long)resident_ctas_per_sm(kernel) * sms * waves) / B;      // floor: never more than `waves` waves
     if (cap < 1) cap = 1;
     if (gx > cap) gx = cap;
     if (gx > MAX_GX) gx = MAX_GX;
@@ -841,8 +1332,9 @@ static int point_grid_x(const long long* offsets, int B, int sms) {
 
 // A/B switch for tests and profiles/: run the exact fp64 kernels in the batched entry point too.
 // Initial value from SLU_PROJECT_EXACT=1, changed at run time by slu_debug_project_exact().
-static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && e[0] == '1') ? 1 : 0; }();
-static bool exact_only() { return g_exact_only != 0; }
+static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
+static bool exact_only() { return g_exact_only == 1; }
+static bool cell_path() { return g_exact_only == 2; }             // A/B: the three-launch cell pipeline (128-bit compare-and-swap depth test)
 static int g_no_fused = [] { const char* e = getenv("SLU_PROJECT_NO_FUSED"); return (e && e[0] == '1') ? 1 : 0; }();   // A/B: two-pass kernels with a fixed range too
 
 static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t* d_pix, int32_t* d_winner,
@@ -865,8 +1357,41 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     p.part_max = reinterpret_cast<float*>(base + w.part_max);
     p.part_diag = reinterpret_cast<int*>(base + w.part_diag);
     p.part_exact = reinterpret_cast<double*>(base + w.part_exact);
+    p.cell = reinterpret_cast<Cell*>(base + w.cell);
+    p.want_pix = d_pix != nullptr; p.want_winner = d_winner != nullptr;
     const dim3 gp(point_grid_x(p.offsets, p.B, sms), p.B);
     p.gx = (int)gp.x;
+    if (!generic && cell_path()) {
+        // cell pipeline: extremes (+ cell reset) -> fused point pass with the 128-bit depth test; the caller resolves
+        p.key_sq = 1;
+        const long long nmax = max_points(p.offsets, p.B);
+        long long items = p.use_range ? p.HW : (nmax > p.HW ? nmax : p.HW);
+        static const int dbg_times = [] { const char* e = getenv("SLU_P3_TIMES"); return e ? atoi(e) : 0; }();
+        p.dbg_times = dbg_times ? reinterpret_cast<unsigned long long*>(base + w.theta) : nullptr;   // the theta region is unused on this path
+        p.gx = wave_grid_x(proj3_extremes_kernel, items, p.B, sms);          // P2 reads gx per-block partials
+        proj3_extremes_kernel<<<dim3(p.gx, p.B), PT_THREADS, 0, st>>>(p);
+        SLU_LAUNCH_CHECK("proj3_extremes_kernel");
+        static const int variant = [] { const char* e = getenv("SLU_P3_VARIANT"); return e ? atoi(e) : 0; }();
+        static const int dbg_atom = [] { const char* e = getenv("SLU_P3_ATOM"); return e ? atoi(e) : 0; }();
+        p.dbg_atom = dbg_atom;
+#define SLU_P3_LAUNCH2(NB, MINB, YAW, IDS)                                                                                               \
+    proj3_points_kernel<NB, MINB, YAW, IDS><<<dim3(wave_grid_x(proj3_points_kernel<NB, MINB, YAW, IDS>, (nmax + NB - 1) / NB, p.B, sms), p.B), PT_THREADS, 0, st>>>(p)
+#define SLU_P3_LAUNCH(NB, MINB)                                                        \
+    do {                                                                               \
+        if (p.yaw) { if (ids) SLU_P3_LAUNCH2(NB, MINB, true, true); else SLU_P3_LAUNCH2(NB, MINB, true, false); }      \
+        else { if (ids) SLU_P3_LAUNCH2(NB, MINB, false, true); else SLU_P3_LAUNCH2(NB, MINB, false, false); }          \
+    } while (0)
+        const bool ids = p.raw_label != nullptr && p.lut != nullptr;
+        switch (variant) {
+            case 1: SLU_P3_LAUNCH(1, 4); break;
+            case 2: SLU_P3_LAUNCH(1, 6); break;
+            default: SLU_P3_LAUNCH(1, 5); break;
+        }
+#undef SLU_P3_LAUNCH2
+#undef SLU_P3_LAUNCH
+        SLU_LAUNCH_CHECK("proj3_points_kernel");
+        return 0;
+    }
     if (!generic && !exact_only()) {
         p.key_sq = 1;
         if (p.use_range && !g_no_fused) {
@@ -887,7 +1412,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
             SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
         }
         if (n_total > 0) {
-            proj_ties_kernel<<<dim3(wave_grid_x(proj_ties_kernel, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
+            proj_ties_kernel<<<dim3(wave_grid_x(proj_ties_kernel, (max_points(p.offsets, p.B) + PT_BATCH - 1) / PT_BATCH, p.B, sms, g_light_waves), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_ties_kernel");
         }
         return 0;
@@ -915,7 +1440,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
 
 extern "C" int slu_debug_project_exact(int on) {
     const int prev = slu::g_exact_only;
-    if (on >= 0) slu::g_exact_only = on ? 1 : 0;
+    if (on >= 0) slu::g_exact_only = on > 2 ? 1 : on;
     return prev;
 }
 
@@ -957,8 +1482,13 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     int rc = project_common(p, n_total, d_work, d_pix, d_winner, d_diag, false, st);
     if (rc) return rc;
     const int sms = sm_count_current_device();
-    const int gx = wave_grid_x(proj_resolve_planes_kernel, p.HW, B, sms);
-    proj_resolve_planes_kernel<<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
+    if (cell_path()) {
+        const int gx = wave_grid_x(proj_resolve_planes_kernel<true>, (p.HW + PT_BATCH - 1) / PT_BATCH, B, sms, g_light_waves);
+        proj_resolve_planes_kernel<true><<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
+    } else {
+        const int gx = wave_grid_x(proj_resolve_planes_kernel<false>, (p.HW + PT_BATCH - 1) / PT_BATCH, B, sms, g_light_waves);
+        proj_resolve_planes_kernel<false><<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
+    }
     SLU_LAUNCH_CHECK("proj_resolve_planes_kernel");
     return 0;
 }
@@ -1028,7 +1558,7 @@ extern "C" int slu_backproject(const int64_t* d_label_img, const int32_t* d_pix,
     p.B = B; p.HW = HW;
     const int sms = sm_count_current_device();
     if (sms <= 0) return fail(SLU_E_DEVICE, "no CUDA device");
-    const dim3 g(wave_grid_x(backproject_kernel, max_points(p.offsets, B), B, sms), B);
+    const dim3 g(wave_grid_x(backproject_kernel, (max_points(p.offsets, B) + PT_BATCH - 1) / PT_BATCH, B, sms, g_light_waves), B);
     backproject_kernel<<<g, PT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const long long*>(d_label_img), d_pix, p, reinterpret_cast<long long*>(d_out));
     SLU_LAUNCH_CHECK("backproject_kernel");

@@ -231,3 +231,70 @@ def test_fixed_range_fused_pass_agrees_with_exact_kernels(cuda, theta_range, H):
         pc = np.concatenate([a.astype(np.float64), build_id_lut()[(r & 0xFFFF).astype(np.int64)].astype(np.float64)[:, None]], axis=1)
         row, col, _ = oproj.projection_indices(pc, H, W, theta_range=theta_range)
         assert np.array_equal(fused["pix"][offs[b]:offs[b + 1]].cpu().numpy().astype(np.int64), row * W + col)
+
+
+def _project_in_mode(mode, *args, **kw):
+    from semanticlidarunc_b200 import _lib
+    prev = _lib.lib().slu_debug_project_exact(mode)
+    try:
+        return ops.project_batch(*args, **kw)
+    finally:
+        _lib.lib().slu_debug_project_exact(prev)
+
+
+@pytest.mark.parametrize("case", ["auto", "fixed", "farthest", "yaw", "ties", "pile_up", "tiny_and_empty"])
+def test_cell_pipeline_agrees_with_four_launch_and_exact_kernels(cuda, case):
+    """slu_debug_project_exact(2) runs the cell pipeline (extremes -> fused point pass with a 128-bit compare-and-swap
+    depth test -> resolve), (0) the default four-launch path (64-bit atomicMin + tie pass), (1) the all-fp64 kernels.
+    All three must give identical bits: pixel of every point, winner per pixel INCLUDING the lowest-index rule among
+    exactly equal ranges, image, labels, theta range and the diagnostics."""
+    H, W = 64, 2048
+    kw = {}
+    scans = [synth.synth_scan(301, "hdl64"), synth.synth_scan(302, "hdl64", n_points=33_333)]
+    if case == "fixed":
+        kw["theta_range"] = (-0.45, 0.05)                        # clips a few beams: points outside the range wrap like numpy's
+    elif case == "farthest":
+        kw["farthest_wins"] = True
+    elif case == "yaw":
+        kw["yaw_deg"] = [17.0, -123.4]
+    elif case == "ties":
+        # exact duplicates (same float64 range, same pixel, different index) and same-range points on a sphere:
+        # the lowest index must win whichever thread's compare-and-swap lands first
+        a, r = scans[0]
+        a = np.concatenate([a[:20_000], a[:20_000][::-1], a[5_000:15_000]])
+        r = np.concatenate([r[:20_000], r[:20_000][::-1], r[5_000:15_000]])
+        rng = np.random.default_rng(5)
+        d = rng.normal(size=(30_000, 3))
+        d[:, 2] *= 0.2
+        d = (d / np.linalg.norm(d, axis=1, keepdims=True) * 10.0).astype(np.float32)      # ranges equal up to fp32 rounding
+        sph = np.concatenate([d, np.zeros((30_000, 1), np.float32)], axis=1)
+        scans = [(a, r), (sph, scans[1][1][:30_000])]
+    elif case == "pile_up":
+        # 60 000 points into a patch of ~200 pixels: long compare-and-swap retry chains
+        rng = np.random.default_rng(6)
+        az = rng.uniform(0.30, 0.35, 60_000)
+        el = rng.uniform(-0.10, -0.08, 60_000)
+        rg = rng.uniform(3.0, 50.0, 60_000)
+        pts = np.stack([rg * np.cos(el) * np.cos(az), rg * np.cos(el) * np.sin(az), rg * np.sin(el), rg * 0], axis=1).astype(np.float32)
+        scans = [(pts, scans[0][1][:60_000]), scans[1]]
+    elif case == "tiny_and_empty":
+        H, W = 16, 256
+        e = (np.zeros((0, 4), np.float32), np.zeros((0,), np.uint32))
+        scans = [synth.synth_scan(303, "tiny", n_points=1), e, synth.synth_scan(304, "tiny"), synth.synth_scan(305, "tiny", n_points=7)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    dx, dr, dl = to_dev(np.concatenate([s[0] for s in scans]), np.concatenate([s[1] for s in scans]), cuda)
+    cells = _project_in_mode(2, dx, dr, offs, H, W, lut=dl, **kw)
+    four = _project_in_mode(0, dx, dr, offs, H, W, lut=dl, **kw)
+    exact = _project_in_mode(1, dx, dr, offs, H, W, lut=dl, **kw)
+    for key in ("pix", "winner", "img", "label", "theta", "diag"):
+        assert torch.equal(cells[key], four[key]), ("four-launch", key)
+        assert torch.equal(cells[key], exact[key]), ("exact", key)
+    if case == "ties":
+        w = cells["winner"][0].reshape(-1).cpu().numpy()
+        assert w.max() < 20_000                                     # every duplicate lost to its lower-index twin
+    if case in ("auto", "ties", "pile_up"):
+        for b, (a, r) in enumerate(scans):
+            o = oproj.kitti_frame(a, r, H, W, build_id_lut())
+            assert np.array_equal(cells["pix"][offs[b]:offs[b + 1]].cpu().numpy().astype(np.int64), o["pix"])
+            if case != "ties":                                      # the oracle's winner among exact ties follows argsort
+                assert np.array_equal(cells["winner"][b].cpu().numpy().reshape(-1).astype(np.int64), o["winner"])
