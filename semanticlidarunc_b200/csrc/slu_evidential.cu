@@ -17,6 +17,7 @@
 // DIFFERENCE psi(alpha_c+1) - psi(alpha0+1) (slu_special.cuh::psi_g: psi(x) = ln x + g(1/x) with a degree-7 polynomial,
 // the logarithm taken once on the ratio of the two arguments), two lg2 for the entropies: 5 MUFU per class.
 #include <math.h>
+#include <stdlib.h>
 #include "slu_common.cuh"
 #include "slu_special.cuh"
 #include "slu_packed.cuh"
@@ -406,6 +407,10 @@ __global__ void __launch_bounds__(EV2_THREADS, SLU_EV2_MINB) evidential_x2_kerne
     atomic_hist_flush(hs, p.C, p.n_bins, p.confmat, p.bins, tid, EV2_THREADS);
 }
 
+// experiment (SLU_GRID_WAVES): more, shorter CTAs dealt out by the hardware scheduler instead of one resident wave (slower here:
+// 0.076 -> 0.094 ms per 16 scans at 8 waves)
+static int grid_waves() { static const int w = [] { const char* e = getenv("SLU_GRID_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 1; }(); return w; }
+
 template <int CP>
 static int launch_ev(const EvParams& p, cudaStream_t st) {
     const int sms = sm_count_current_device();
@@ -421,7 +426,7 @@ static int launch_ev(const EvParams& p, cudaStream_t st) {
     const uintptr_t al16 = reinterpret_cast<uintptr_t>(p.labels) | reinterpret_cast<uintptr_t>(p.pred);
     if (!g_ev_no_packed && (p.HW & 1) == 0 && (al8 & 7) == 0 && (al16 & 15) == 0) {
         const long long chunks2 = ((p.n_px >> 1) + EV2_THREADS - 1) / EV2_THREADS;
-        const long long cap2 = (long long)SLU_EV2_MINB * sms;
+        const long long cap2 = (long long)SLU_EV2_MINB * sms * grid_waves();
         const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
         // GE1: a head output always gives alpha >= 1; caller-supplied concentrations are checked per thread
         if (p.outputs) {

@@ -14,6 +14,7 @@
 //                          n = -(dy x dz style cross product), n /= (||n|| + 1e-10).
 // Pure copies are bit-exact; the normals agree with cv2 to float32 rounding (cv2's SIMD paths may fuse
 // multiply-adds differently), tested at 1e-5.
+#include <stdlib.h>
 #include "slu_common.cuh"
 
 namespace slu {
@@ -206,7 +207,8 @@ static void launch_normals(const FrameParams& p, int B, int sms, cudaStream_t st
                      ((reinterpret_cast<uintptr_t>(p.xyz) | reinterpret_cast<uintptr_t>(p.normals)) & 15) == 0;
     const long long work = vec ? HWd / 4 : HWd;
     long long gx = (work + FR_THREADS - 1) / FR_THREADS;
-    const long long cap = (8LL * sms + B - 1) / B;
+    static const int ctas_per_sm = [] { const char* e = getenv("SLU_FR_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    const long long cap = ((long long)ctas_per_sm * sms + B - 1) / B;
     if (gx > cap) gx = cap;
     if (vec) frame_normals4_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);
     else frame_normals_kernel<<<dim3((unsigned)gx, B), FR_THREADS, 0, st>>>(p);

@@ -315,6 +315,11 @@ __global__ void __launch_bounds__(DL2_THREADS, SLU_DL2_MINB) dirichlet_loss_x2_k
     }
 }
 
+// SLU_GRID_WAVES (experiment): more, shorter CTAs dealt out by the hardware scheduler instead of one resident wave.  Measured on
+// 16 scans (profiles/kernel_report_r02.md): the two-term kernel gains 8 % with 8 waves (0.125 -> 0.115 ms: its CTAs do one
+// chunk each and the scheduler evens out slow SMs), the fused kernel and the evidential reduction lose 2-30 %.
+static int grid_waves(int dflt) { static const int w = [] { const char* e = getenv("SLU_GRID_WAVES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }(); return w ? w : dflt; }
+
 template <int CP>
 static int launch_loss(const LossParams& p, cudaStream_t st) {
     const int sms = sm_count_current_device();
@@ -326,7 +331,7 @@ static int launch_loss(const LossParams& p, cudaStream_t st) {
                           reinterpret_cast<uintptr_t>(p.grad_kl)) & 7) == 0;
     if (packed) {
         const long long chunks2 = ((p.n_px >> 1) + DL2_THREADS - 1) / DL2_THREADS;
-        const long long cap2 = (long long)SLU_DL2_MINB * sms;
+        const long long cap2 = (long long)SLU_DL2_MINB * sms * grid_waves(8);
         const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
         if (p.C == CP) dirichlet_loss_x2_kernel<CP, true><<<grid2, DL2_THREADS, 0, st>>>(p);
         else dirichlet_loss_x2_kernel<CP, false><<<grid2, DL2_THREADS, 0, st>>>(p);
@@ -823,7 +828,7 @@ static int launch_fused(const FusedParams& p, bool precounted, cudaStream_t st) 
     const bool packed = !g_no_packed && g_loss_variant != 2 && pair_ok;
     if (packed) {
         const long long chunks2 = ((p.n_px >> 1) + LOSS2_THREADS - 1) / LOSS2_THREADS;
-        const long long cap2 = (long long)SLU_LOSS2_MINB * sms;
+        const long long cap2 = (long long)SLU_LOSS2_MINB * sms * grid_waves(1);
         const unsigned grid2 = (unsigned)(chunks2 < cap2 ? chunks2 : cap2);
         if (p.C == CP) evidential_loss_fused_x2_kernel<CP, true><<<grid2, LOSS2_THREADS, 0, st>>>(p);
         else evidential_loss_fused_x2_kernel<CP, false><<<grid2, LOSS2_THREADS, 0, st>>>(p);

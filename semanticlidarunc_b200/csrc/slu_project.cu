@@ -320,8 +320,8 @@ __device__ __forceinline__ float fast_atan2(float y, float x) {
     return y < 0.f ? -r : r;
 }
 
-__device__ __forceinline__ double exact_phi(const Pt q) { return atan2(q.y, q.x); }
-__device__ __forceinline__ double exact_theta(const Pt q) {
+__device__ __noinline__ double exact_phi(const Pt q) { return atan2(q.y, q.x); }       // real calls: the fp64 arctangent would set the register budget of the point loops
+__device__ __noinline__ double exact_theta(const Pt q) {
     const double rho = __dsqrt_rn(__dadd_rn(__dmul_rn(q.x, q.x), __dmul_rn(q.y, q.y)));
     return __dadd_rn(-atan2(rho, q.z), HALF_PI);
 }
@@ -354,6 +354,12 @@ __device__ __forceinline__ int fast_count_le(const FastEdges& f, float a32) {
 __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
+    const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
+    // the first point of every thread is requested before anything else, so its round trip overlaps the reset below
+    const long long pt_stride = (long long)gridDim.x * blockDim.x;
+    const long long n_first = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 v_nx = n_first < n1 ? __ldg(p.xyzi + n_first) : make_float4(1.f, 0.f, 0.f, 0.f);
+    unsigned raw_nx = (check_ids && n_first < n1) ? __ldg(p.raw_label + n_first) : 0u;
     // this launch also resets the per-pixel depth-test state and the per-scan scalars
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.HW; i += (long long)gridDim.x * blockDim.x) {
         p.key[(long long)b * p.HW + i] = ~0ull;
@@ -371,14 +377,19 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     __syncthreads();
     float tmin = INFINITY, tmax = -INFINITY;
     int missing = 0, near_cnt = 0;
-    const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
     int pend_lut = 0;
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const float4 v4 = __ldg(p.xyzi + n);
+    // the point (and raw label) of the NEXT iteration is requested before the current one is worked on: with ~10 points per
+    // thread the loop otherwise pays one exposed memory round trip per point
+    for (long long n = n_first; n < n1; n += pt_stride) {
+        const float4 v4 = v_nx;
         // label-id check (the reference raises KeyError on ids outside id_map, dataloader_semantic_KITTI.py:47): the raw
         // label is loaded together with the point, its LUT gather is issued here and only tested one iteration later,
         // so neither load stalls the angle arithmetic
-        const unsigned raw = check_ids ? (__ldg(p.raw_label + n) & 0xffffu) : 0u;
+        const unsigned raw = raw_nx & 0xffffu;
+        if (n + pt_stride < n1) {
+            v_nx = __ldg(p.xyzi + n + pt_stride);
+            if (check_ids) raw_nx = __ldg(p.raw_label + n + pt_stride);
+        }
         missing += pend_lut < 0 ? 1 : 0;
         const Pt q = load_pt(p, b, v4);
         const double x = q.x, y = q.y, z = q.z;
@@ -398,11 +409,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         if (cnt_w < 0) {
             // near an edge: queue the point; the fp64 path runs once per block on the packed queue instead of
             // once per warp that happens to contain such a point
+            // (a queue that overflows is dropped as a whole: the block then walks its points again, below)
             const int slot = atomicAdd(&s_qn, 1);
-            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
-            bool near;
-            cnt_w = count_le(ew, exact_phi(q), near);
-            if (near) ++near_cnt;
+            if (slot < DEFER_CAP) s_q[slot] = (int)(n - n0);
+            continue;
         }
         int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
         if (c < 0) c += p.W;
@@ -410,14 +420,28 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     }
     missing += pend_lut < 0 ? 1 : 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
-        const long long n = n0 + s_q[i];
-        bool near;
-        const int cnt_w = count_le(ew, exact_phi(load_pt(p, b, __ldg(p.xyzi + n))), near);
-        if (near) ++near_cnt;
-        int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
-        if (c < 0) c += p.W;
-        p.col[n] = c;
+    if (s_qn <= DEFER_CAP) {
+        for (int i = threadIdx.x; i < s_qn; i += blockDim.x) {
+            const long long n = n0 + s_q[i];
+            bool near;
+            const int cnt_w = count_le(ew, exact_phi(load_pt(p, b, __ldg(p.xyzi + n))), near);
+            if (near) ++near_cnt;
+            int c = p.W - 1 - cnt_w;                    // cnt_w in [0, W]: only -1 wraps (numpy's negative index)
+            if (c < 0) c += p.W;
+            p.col[n] = c;
+        }
+    } else {
+        // more near-edge points than the queue holds (adversarial inputs): every thread settles its own in place
+        for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
+            const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
+            if (fast_count_le(fw, fast_atan2((float)q.y, (float)q.x)) >= 0) continue;
+            bool near;
+            const int cnt_w = count_le(ew, exact_phi(q), near);
+            if (near) ++near_cnt;
+            int c = p.W - 1 - cnt_w;
+            if (c < 0) c += p.W;
+            p.col[n] = c;
+        }
     }
     __shared__ float s_min[PT_THREADS / 32], s_max[PT_THREADS / 32];
     __shared__ int s_miss[PT_THREADS / 32], s_near[PT_THREADS / 32];
@@ -495,12 +519,15 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
     double lo, hi;
     scan_theta_range_fast(p, b, lo, hi);
-    const Edges eh = make_edges(lo, hi, p.H);
-    const FastEdges fh = make_fast_edges(eh);
     __shared__ int s_q[DEFER_CAP];
     __shared__ int s_qn;
-    if (threadIdx.x == 0) s_qn = 0;
+    __shared__ FastEdges s_fh;
+    if (threadIdx.x == 0) {                         // the float64 divisions of the edge set-up run once per block
+        s_qn = 0;
+        s_fh = make_fast_edges(make_edges(lo, hi, p.H));
+    }
     __syncthreads();
+    const FastEdges fh = s_fh;
     int near_cnt = 0;
     if (blockIdx.x == 0) {
         // fold the angle kernel's per-block diagnostics into the scan's counters (strided over the block's
@@ -537,12 +564,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
             int cnt_h = fast_count_le(fh, t32[k]);
             if (cnt_h < 0) {
                 const int slot = atomicAdd(&s_qn, 1);
-                if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
-                bool near;
-                const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
-                cnt_h = count_le(eh, th, near);
-                if (near && !p.use_range) near = !(th == lo || th == hi);
-                if (near) ++near_cnt;
+                if (slot < DEFER_CAP) s_q[slot] = (int)(n - n0);
+                continue;
             }
             int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
             if (r < 0) r += p.H;
@@ -552,8 +575,13 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
-        const long long n = n0 + s_q[i];
+    const Edges eh = make_edges(lo, hi, p.H);       // float64 edges: only the queued points need them
+    const bool overflow = s_qn > DEFER_CAP;         // then every thread walks its points again and settles the near-edge ones
+    const long long q_begin = overflow ? (long long)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    const long long q_end = overflow ? n1 - n0 : s_qn, q_step = overflow ? stride : blockDim.x;
+    for (long long i = q_begin; i < q_end; i += q_step) {
+        const long long n = n0 + (overflow ? i : (long long)s_q[i]);
+        if (overflow && fast_count_le(fh, p.theta32[n]) >= 0) continue;
         bool near;
         const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
         const int cnt_h = count_le(eh, th, near);
@@ -588,9 +616,17 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
     const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
     int pend_lut = 0;
     unsigned long long* key = p.key + (long long)b * p.HW;
-    for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
-        const float4 v4 = __ldg(p.xyzi + n);
-        const unsigned raw = check_ids ? (__ldg(p.raw_label + n) & 0xffffu) : 0u;
+    const long long pt_stride = (long long)gridDim.x * blockDim.x;       // next iteration's point requested ahead, as in the angle kernel
+    const long long n_first = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 v_nx = n_first < n1 ? __ldg(p.xyzi + n_first) : make_float4(1.f, 0.f, 0.f, 0.f);
+    unsigned raw_nx = (check_ids && n_first < n1) ? __ldg(p.raw_label + n_first) : 0u;
+    for (long long n = n_first; n < n1; n += pt_stride) {
+        const float4 v4 = v_nx;
+        const unsigned raw = raw_nx & 0xffffu;
+        if (n + pt_stride < n1) {
+            v_nx = __ldg(p.xyzi + n + pt_stride);
+            if (check_ids) raw_nx = __ldg(p.raw_label + n + pt_stride);
+        }
         missing += pend_lut < 0 ? 1 : 0;
         const Pt q = load_pt(p, b, v4);
         const double x = q.x, y = q.y, z = q.z;
@@ -606,10 +642,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         int cnt_h = fast_count_le(fh, th32);
         if (cnt_w < 0 || cnt_h < 0) {
             const int slot = atomicAdd(&s_qn, 1);
-            if (slot < DEFER_CAP) { s_q[slot] = (int)(n - n0); continue; }
-            bool near;
-            if (cnt_w < 0) { cnt_w = count_le(ew, exact_phi(q), near); if (near) ++near_cnt; }
-            if (cnt_h < 0) { cnt_h = count_le(eh, exact_theta(q), near); if (near) ++near_cnt; }
+            if (slot < DEFER_CAP) s_q[slot] = (int)(n - n0);
+            continue;
         }
         int c = p.W - 1 - cnt_w;
         if (c < 0) c += p.W;
@@ -621,10 +655,18 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
     }
     missing += pend_lut < 0 ? 1 : 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < min(s_qn, DEFER_CAP); i += blockDim.x) {
+    const bool overflow = s_qn > DEFER_CAP;         // then every thread walks its points again and settles the near-edge ones
+    const long long q_begin = overflow ? (long long)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    const long long q_end = overflow ? n1 - n0 : s_qn, q_step = overflow ? (long long)gridDim.x * blockDim.x : blockDim.x;
+    for (long long i = q_begin; i < q_end; i += q_step) {
         // queued points: both bins from the exact fp64 angles (a bin the prefilter had certified cannot be near an edge)
-        const long long n = n0 + s_q[i];
+        const long long n = n0 + (overflow ? i : (long long)s_q[i]);
         const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
+        if (overflow) {
+            const float x32 = (float)q.x, y32 = (float)q.y, z32 = (float)q.z;
+            if (fast_count_le(fw, fast_atan2(y32, x32)) >= 0 &&
+                fast_count_le(fh, 1.57079632679489662f - fast_atan2(sqrtf(fmaf(x32, x32, y32 * y32)), z32)) >= 0) continue;
+        }
         bool near_w, near_h;
         const int cnt_w = count_le(ew, exact_phi(q), near_w);
         const int cnt_h = count_le(eh, exact_theta(q), near_h);

@@ -72,6 +72,8 @@ for sensor, B in (("hdl64", 1), ("hdl64", 16), ("os1-128", 1), ("os1-128", 16)):
         tr = (-np.pi / 8, np.pi / 8)
         add(f"projection {sensor} B={B}, fixed theta range (CUDAL)", lambda: ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws, theta_range=tr),
             20 * n + 24 * B * H * W, B, "init + fused point pass + ties + resolve")
+    img = res["img"]
+    add(f"loader normals {sensor} B={B}", lambda: ops.frame_normals(img), 24 * B * H * W, B, "Scharr gradients of x,y,z + cross product (build_normal_xyz)")
     lab_img, pix = res["label"], res["pix"]
     add(f"back-projection {sensor} B={B}", lambda: ops.backproject(lab_img, pix, offs), 8 * n + 8 * B * H * W, B)
 
