@@ -818,7 +818,13 @@ __device__ __forceinline__ void dbg_stamp(const ProjParams& p, int kernel, int s
     if (p.dbg_times && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        p.dbg_times[((long long)kernel * 4096 + blockIdx.y * gridDim.x + blockIdx.x) * 8 + slot] = t;
+        unsigned long long* row = p.dbg_times + ((long long)kernel * 4096 + blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        row[slot] = t;
+        if (slot == 0) {                             // slot 7: which SM ran the block
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            row[7] = smid + 1;
+        }
     }
 }
 constexpr int P1_NB = 4;                    // points a thread of P1 has in flight per iteration

@@ -31,10 +31,12 @@ for rep in range(2):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); g.replay(); b.record(); torch.cuda.synchronize()
     t = ws[: 3 * 4096 * 64].view(torch.int64).reshape(3, 4096, 8).cpu().numpy()
-    t0 = t[t > 0].min()
+    t0 = t[:, :, :7][t[:, :, :7] > 0].min()            # slot 7 holds the SM id, not a time
     print("replay", rep, "event ms", round(a.elapsed_time(b), 4))
+    if os.environ.get("SLU_DUMP"):
+        np.save(os.environ["SLU_DUMP"], t)
     for k, name in enumerate(("P1 extremes", "P2 points", "P3 resolve")):
-        for s in range(8):
+        for s in range(7):
             v = t[k, :, s]; v = v[v > 0]
             if v.size:
                 v = (v - t0) / 1000.0
