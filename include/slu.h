@@ -328,7 +328,9 @@ int64_t slu_project_workspace_bytes(int64_t n_total, int B, int64_t HW);
  * fp32-prefiltered ones (bit-identical results, ~2x slower); on=2 runs the three-launch "cell" pipeline (one fused point
  * pass whose depth test is a 128-bit compare-and-swap on a (range, index) cell per pixel; bit-identical results, same
  * speed with an automatic range, slower with a fixed one; needs the larger workspace slu_project_workspace_bytes
- * already reports); on=0 restores the default; on<0 only queries.  Returns the previous setting.  Process-wide host
+ * already reports); on=3 keeps the default kernels but runs their depth test as that 128-bit compare-and-swap (no tie
+ * pass; bit-identical, slower: atomics that return a value cost more than reductions); on=0 restores the default; on<0
+ * only queries.  Returns the previous setting.  Process-wide host
  * state, not for concurrent use. */
 int slu_debug_project_exact(int on);
 /* diagnostic: out[i] = the projection prefilter's fp32 arctangent of (y[i], x[i]); NaN for zero / denormal / huge / non-finite

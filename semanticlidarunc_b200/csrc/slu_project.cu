@@ -133,6 +133,7 @@ struct ProjParams {
     unsigned long long* dbg_times; // timing experiments only (SLU_P3_TIMES=1): per-block globaltimer stamps, [3][4096][8], or NULL
     struct Cell* cell;             // [B*HW] 128-bit (range key, point index) cells of the single-pass depth test
     int want_pix, want_winner;     // the caller asked for d_pix / d_winner (the cell pipeline skips the stores otherwise)
+    int use_cells;                 // the depth test runs on the 128-bit cells (no key / winner arrays, no tie pass)
     // outputs
     int* pix;                      // [n_total]
     int* winner;                   // [B*HW]
@@ -156,11 +157,100 @@ __device__ __forceinline__ Pt load_pt(const ProjParams& p, int b, const float4 v
     return q;
 }
 
+// ---- the per-pixel depth-test cell: (range key, point index) as ONE 128-bit word, updated by compare-and-swap ----
+// A point is a winner candidate of its pixel when its range equals the pixel's best range.  With r^2 keys (key_sq) two
+// DIFFERENT keys can stand for the same float64 range (sqrt rounds at most a few neighbouring r^2 values together); the
+// reference, which sorts by r, sees a tie there, so keys within 8 ulp of the best are compared after the square root.
+__device__ __forceinline__ bool same_range(const ProjParams& p, unsigned long long rk, unsigned long long best) {
+    if (rk == best) return true;
+    if (!p.key_sq || rk - best > 8ull) return false;           // best is the minimum: rk >= best
+    const unsigned long long a = p.farthest ? 0x7fffffffffffffffull - rk : rk;
+    const unsigned long long c = p.farthest ? 0x7fffffffffffffffull - best : best;
+    return __dsqrt_rn(__longlong_as_double((long long)a)) == __dsqrt_rn(__longlong_as_double((long long)c));
+}
+
+struct alignas(16) Cell { unsigned long long idx, key; };     // one little-endian 128-bit word: (key << 64) | idx
+constexpr unsigned long long CELL_EMPTY = ~0ull;
+
+__device__ __forceinline__ void cas128(Cell* addr, unsigned long long exp_lo, unsigned long long exp_hi,
+                                       unsigned long long new_lo, unsigned long long new_hi,
+                                       unsigned long long& old_lo, unsigned long long& old_hi) {
+    asm volatile(
+        "{\n\t.reg .b128 e, n, o;\n\t"
+        "mov.b128 e, {%3, %4};\n\t"
+        "mov.b128 n, {%5, %6};\n\t"
+        "atom.global.relaxed.gpu.cas.b128 o, [%2], e, n;\n\t"
+        "mov.b128 {%0, %1}, o;\n\t}"
+        : "=l"(old_lo), "=l"(old_hi)
+        : "l"(addr), "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi)
+        : "memory");
+}
+
+typedef unsigned __int128 u128;
+__device__ __forceinline__ u128 cas128q(Cell* addr, u128 expect, u128 desired) {      // result stays ONE 128-bit register
+    u128 old;
+    asm volatile("atom.global.relaxed.gpu.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(expect), "q"(desired) : "memory");
+    return old;
+}
+
+// strict total order of the depth test: smaller float64 range first (same_range: r^2 keys whose square roots coincide are
+// the ties they are in the reference), then the lower point index
+__device__ __forceinline__ bool cell_before(const ProjParams& p, unsigned long long ka, unsigned long long ia,
+                                            unsigned long long kb, unsigned long long ib) {
+    if (ka == kb) return ia < ib;
+    const bool a_small = ka < kb;
+    if (same_range(p, a_small ? kb : ka, a_small ? ka : kb)) return ia < ib;
+    return a_small;
+}
+
+// retire or retry after a failed first CAS (old = what the cell held)
+__device__ __forceinline__ void depth_test_finish(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
+                                                  unsigned long long ol, unsigned long long oh) {
+    unsigned long long el = CELL_EMPTY, eh = CELL_EMPTY;
+    while (!(ol == el && oh == eh)) {
+        if (!cell_before(p, key, idx, oh, ol)) return;          // the resident point stays
+        el = ol; eh = oh;
+        cas128(a, el, eh, idx, key, ol, oh);
+    }
+}
+__device__ __forceinline__ void depth_test(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx) {
+    unsigned long long ol, oh;
+    cas128(a, CELL_EMPTY, CELL_EMPTY, idx, key, ol, oh);
+    depth_test_finish(p, a, key, idx, ol, oh);
+}
+
+// the rare half of the depth test, a real call: the compare-and-swap retry loop with its float64 square roots would
+// otherwise be inlined at every site and set the register budget of the point loop
+__device__ __noinline__ void depth_test_retry(Cell* a, unsigned long long key, unsigned long long idx,
+                                              unsigned long long ol, unsigned long long oh, int key_sq, int farthest) {
+    ProjParams q;                                   // only the two fields same_range reads
+    q.key_sq = key_sq; q.farthest = farthest;
+    depth_test_finish(q, a, key, idx, ol, oh);
+}
+__device__ __forceinline__ void depth_test_settle(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
+                                                  unsigned long long ol, unsigned long long oh) {
+    if ((ol & oh) != CELL_EMPTY) depth_test_retry(a, key, idx, ol, oh, p.key_sq, p.farthest);
+}
+
+// issue / settle pair used by the point kernels: several first attempts of a thread are put in flight before any is examined
+__device__ __forceinline__ u128 depth_test_issue(Cell* a, unsigned long long key, unsigned long long idx) {
+    return cas128q(a, ~(u128)0, ((u128)key << 64) | idx);
+}
+__device__ __forceinline__ void depth_test_settle(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx, u128 old) {
+    if (old != ~(u128)0) depth_test_retry(a, key, idx, (unsigned long long)old, (unsigned long long)(old >> 64), p.key_sq, p.farthest);
+}
+
 __global__ void __launch_bounds__(PT_THREADS) proj_init_kernel(const __grid_constant__ ProjParams p) {
     const long long total = (long long)p.B * p.HW;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        p.key[i] = ~0ull;
-        p.winner[i] = 0x7fffffff;
+    if (p.use_cells) {
+        ulonglong2* cell = reinterpret_cast<ulonglong2*>(p.cell);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+            cell[i] = make_ulonglong2(CELL_EMPTY, CELL_EMPTY);
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            p.key[i] = ~0ull;
+            p.winner[i] = 0x7fffffff;
+        }
     }
     if (blockIdx.x == 0) {
         for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
@@ -361,9 +451,15 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     float4 v_nx = n_first < n1 ? __ldg(p.xyzi + n_first) : make_float4(1.f, 0.f, 0.f, 0.f);
     unsigned raw_nx = (check_ids && n_first < n1) ? __ldg(p.raw_label + n_first) : 0u;
     // this launch also resets the per-pixel depth-test state and the per-scan scalars
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.HW; i += (long long)gridDim.x * blockDim.x) {
-        p.key[(long long)b * p.HW + i] = ~0ull;
-        p.winner[(long long)b * p.HW + i] = 0x7fffffff;
+    if (p.use_cells) {
+        ulonglong2* cell = reinterpret_cast<ulonglong2*>(p.cell + (long long)b * p.HW);
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.HW; i += (long long)gridDim.x * blockDim.x)
+            cell[i] = make_ulonglong2(CELL_EMPTY, CELL_EMPTY);
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.HW; i += (long long)gridDim.x * blockDim.x) {
+            p.key[(long long)b * p.HW + i] = ~0ull;
+            p.winner[(long long)b * p.HW + i] = 0x7fffffff;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.tminmax[2 * b] = ~0ull; p.tminmax[2 * b + 1] = 0ull;
@@ -514,6 +610,7 @@ __device__ __forceinline__ void scan_theta_range_fast(const ProjParams& p, int b
     lo = a; hi = c;
 }
 
+template <bool CELLS>
 __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
@@ -545,6 +642,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     // 3 * PT_BATCH memory requests in flight instead of paying one L2 round trip per point
     const long long stride = (long long)gridDim.x * blockDim.x;
     unsigned long long* key = p.key + (long long)b * p.HW;
+    Cell* cell = p.cell + (long long)b * p.HW;
     for (long long nb = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; nb < n1; nb += stride * PT_BATCH) {
         float t32[PT_BATCH];
         int col[PT_BATCH];
@@ -557,9 +655,12 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
             col[k] = in ? p.col[n] : 0;
             rk[k] = in ? p.rkey[n] : 0ull;
         }
+        int pxs[PT_BATCH];
+        u128 old[PT_BATCH];
 #pragma unroll
         for (int k = 0; k < PT_BATCH; ++k) {
             const long long n = nb + k * stride;
+            pxs[k] = -1;
             if (n >= n1) continue;
             int cnt_h = fast_count_le(fh, t32[k]);
             if (cnt_h < 0) {
@@ -570,8 +671,15 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
             int r = p.H - 1 - cnt_h;                    // cnt_h in [0, H]: only -1 wraps
             if (r < 0) r += p.H;
             const int px = r * p.W + col[k];
+            pxs[k] = px;
             p.pix[n] = px;
-            atomicMin(&key[px], rk[k]);
+            if (CELLS) old[k] = depth_test_issue(cell + px, rk[k], (unsigned long long)(n - n0));    // all first attempts of the batch in flight
+            else atomicMin(&key[px], rk[k]);
+        }
+        if (CELLS) {
+#pragma unroll
+            for (int k = 0; k < PT_BATCH; ++k)
+                if (pxs[k] >= 0) depth_test_settle(p, cell + pxs[k], rk[k], (unsigned long long)(nb + k * stride - n0), old[k]);
         }
     }
     __syncthreads();
@@ -591,7 +699,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
         if (r < 0) r += p.H;
         const int px = r * p.W + p.col[n];
         p.pix[n] = px;
-        atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
+        if (CELLS) depth_test_settle(p, cell + px, p.rkey[n], (unsigned long long)(n - n0), depth_test_issue(cell + px, p.rkey[n], (unsigned long long)(n - n0)));
+        else atomicMin(&p.key[(long long)b * p.HW + px], p.rkey[n]);
     }
     near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
     if ((threadIdx.x & 31) == 0 && near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
@@ -601,6 +710,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
 // the row edges do not depend on the scan, so column, row and the depth test run in ONE pass over the points -- no fp32
 // theta / column round trip through memory, and the 64-bit atomic stream overlaps the angle arithmetic.  The per-pixel
 // state is reset by proj_init_kernel beforehand (the depth test cannot share a launch with its own initialisation).
+template <bool CELLS>
 __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
@@ -616,6 +726,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
     const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
     int pend_lut = 0;
     unsigned long long* key = p.key + (long long)b * p.HW;
+    Cell* cell = p.cell + (long long)b * p.HW;
     const long long pt_stride = (long long)gridDim.x * blockDim.x;       // next iteration's point requested ahead, as in the angle kernel
     const long long n_first = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float4 v_nx = n_first < n1 ? __ldg(p.xyzi + n_first) : make_float4(1.f, 0.f, 0.f, 0.f);
@@ -651,7 +762,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         if (rr < 0) rr += p.H;
         const int px = rr * p.W + c;
         p.pix[n] = px;
-        atomicMin(&key[px], rk);
+        if (CELLS) depth_test_settle(p, cell + px, rk, (unsigned long long)(n - n0), depth_test_issue(cell + px, rk, (unsigned long long)(n - n0)));
+        else atomicMin(&key[px], rk);
     }
     missing += pend_lut < 0 ? 1 : 0;
     __syncthreads();
@@ -677,7 +789,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         if (rr < 0) rr += p.H;
         const int px = rr * p.W + c;
         p.pix[n] = px;
-        atomicMin(&key[px], p.rkey[n]);
+        if (CELLS) depth_test_settle(p, cell + px, p.rkey[n], (unsigned long long)(n - n0), depth_test_issue(cell + px, p.rkey[n], (unsigned long long)(n - n0)));
+        else atomicMin(&key[px], p.rkey[n]);
     }
     missing = __reduce_add_sync(0xffffffffu, missing);
     near_cnt = __reduce_add_sync(0xffffffffu, near_cnt);
@@ -685,17 +798,6 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         if (missing) atomicAdd(&p.diag[2 * b], missing);
         if (near_cnt) atomicAdd(&p.diag[2 * b + 1], near_cnt);
     }
-}
-
-// A point is a winner candidate of its pixel when its range equals the pixel's best range.  With r^2 keys (key_sq) two
-// DIFFERENT keys can stand for the same float64 range (sqrt rounds at most a few neighbouring r^2 values together); the
-// reference, which sorts by r, sees a tie there, so keys within 8 ulp of the best are compared after the square root.
-__device__ __forceinline__ bool same_range(const ProjParams& p, unsigned long long rk, unsigned long long best) {
-    if (rk == best) return true;
-    if (!p.key_sq || rk - best > 8ull) return false;           // best is the minimum: rk >= best
-    const unsigned long long a = p.farthest ? 0x7fffffffffffffffull - rk : rk;
-    const unsigned long long c = p.farthest ? 0x7fffffffffffffffull - best : best;
-    return __dsqrt_rn(__longlong_as_double((long long)a)) == __dsqrt_rn(__longlong_as_double((long long)c));
 }
 
 __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_constant__ ProjParams p) {
@@ -751,56 +853,6 @@ __global__ void __launch_bounds__(PT_THREADS) proj_ties_kernel(const __grid_cons
 // per SM) and its blocks finish 12 us apart (31.8 ... 44.5 us after a common start; tools/proj_timeline.py), so the
 // slowest SMs set the time.  It stays in the library as the measured alternative (profiles/projection_r02.md).
 // ====================================================================================================
-struct alignas(16) Cell { unsigned long long idx, key; };     // one little-endian 128-bit word: (key << 64) | idx
-constexpr unsigned long long CELL_EMPTY = ~0ull;
-
-__device__ __forceinline__ void cas128(Cell* addr, unsigned long long exp_lo, unsigned long long exp_hi,
-                                       unsigned long long new_lo, unsigned long long new_hi,
-                                       unsigned long long& old_lo, unsigned long long& old_hi) {
-    asm volatile(
-        "{\n\t.reg .b128 e, n, o;\n\t"
-        "mov.b128 e, {%3, %4};\n\t"
-        "mov.b128 n, {%5, %6};\n\t"
-        "atom.global.relaxed.gpu.cas.b128 o, [%2], e, n;\n\t"
-        "mov.b128 {%0, %1}, o;\n\t}"
-        : "=l"(old_lo), "=l"(old_hi)
-        : "l"(addr), "l"(exp_lo), "l"(exp_hi), "l"(new_lo), "l"(new_hi)
-        : "memory");
-}
-
-typedef unsigned __int128 u128;
-__device__ __forceinline__ u128 cas128q(Cell* addr, u128 expect, u128 desired) {      // result stays ONE 128-bit register
-    u128 old;
-    asm volatile("atom.global.relaxed.gpu.cas.b128 %0, [%1], %2, %3;" : "=q"(old) : "l"(addr), "q"(expect), "q"(desired) : "memory");
-    return old;
-}
-
-// strict total order of the depth test: smaller float64 range first (same_range: r^2 keys whose square roots coincide are
-// the ties they are in the reference), then the lower point index
-__device__ __forceinline__ bool cell_before(const ProjParams& p, unsigned long long ka, unsigned long long ia,
-                                            unsigned long long kb, unsigned long long ib) {
-    if (ka == kb) return ia < ib;
-    const bool a_small = ka < kb;
-    if (same_range(p, a_small ? kb : ka, a_small ? ka : kb)) return ia < ib;
-    return a_small;
-}
-
-// retire or retry after a failed first CAS (old = what the cell held)
-__device__ __forceinline__ void depth_test_finish(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
-                                                  unsigned long long ol, unsigned long long oh) {
-    unsigned long long el = CELL_EMPTY, eh = CELL_EMPTY;
-    while (!(ol == el && oh == eh)) {
-        if (!cell_before(p, key, idx, oh, ol)) return;          // the resident point stays
-        el = ol; eh = oh;
-        cas128(a, el, eh, idx, key, ol, oh);
-    }
-}
-__device__ __forceinline__ void depth_test(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx) {
-    unsigned long long ol, oh;
-    cas128(a, CELL_EMPTY, CELL_EMPTY, idx, key, ol, oh);
-    depth_test_finish(p, a, key, idx, ol, oh);
-}
-
 // fp32 tangent of the elevation, z / sqrt(x^2 + y^2): relative error <= 5e-7 (two rounded products and a sum, rsqrt.approx
 // <= 2 ulp, one product, plus the float32 view of yaw-rotated coordinates).  NaN when the operands leave the range in
 // which that bound holds (rho^2 outside [1e-30, 1e30], |t| >= 1e9, non-finite input): such points are always candidates.
@@ -1022,19 +1074,6 @@ __device__ __forceinline__ int fast_count_le_nc(const FastEdges& f, float a32) {
     const float lo = t - fl;
     const bool ok = lo > f.margin_bins && lo < 1.0f - f.margin_bins && fl >= 0.0f && fl <= f.last;
     return ok ? (int)fl + 1 : -1;
-}
-
-// the rare half of the depth test, a real call: the compare-and-swap retry loop with its float64 square roots would
-// otherwise be inlined at every site and set the register budget of the point loop
-__device__ __noinline__ void depth_test_retry(Cell* a, unsigned long long key, unsigned long long idx,
-                                              unsigned long long ol, unsigned long long oh, int key_sq, int farthest) {
-    ProjParams q;                                   // only the two fields same_range reads
-    q.key_sq = key_sq; q.farthest = farthest;
-    depth_test_finish(q, a, key, idx, ol, oh);
-}
-__device__ __forceinline__ void depth_test_settle(const ProjParams& p, Cell* a, unsigned long long key, unsigned long long idx,
-                                                  unsigned long long ol, unsigned long long oh) {
-    if ((ol & oh) != CELL_EMPTY) depth_test_retry(a, key, idx, ol, oh, p.key_sq, p.farthest);
 }
 
 // MINB resident CTAs per SM (the register budget); YAW: the loaders' yaw augmentation is applied; IDS: raw label ids are
@@ -1380,9 +1419,10 @@ static int point_grid_x(const long long* offsets, int B, int sms) {
 
 // A/B switch for tests and profiles/: run the exact fp64 kernels in the batched entry point too.
 // Initial value from SLU_PROJECT_EXACT=1, changed at run time by slu_debug_project_exact().
-static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0; }();
+static int g_exact_only = [] { const char* e = getenv("SLU_PROJECT_EXACT"); return (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 0; }();
 static bool exact_only() { return g_exact_only == 1; }
 static bool cell_path() { return g_exact_only == 2; }             // A/B: the three-launch cell pipeline (128-bit compare-and-swap depth test)
+static bool cells_in_rows_path() { return g_exact_only == 3; }    // A/B: the default kernels with the depth test as a 128-bit compare-and-swap (no tie pass)
 static int g_no_fused = [] { const char* e = getenv("SLU_PROJECT_NO_FUSED"); return (e && e[0] == '1') ? 1 : 0; }();   // A/B: two-pass kernels with a fixed range too
 
 static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t* d_pix, int32_t* d_winner,
@@ -1412,6 +1452,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     if (!generic && cell_path()) {
         // cell pipeline: extremes (+ cell reset) -> fused point pass with the 128-bit depth test; the caller resolves
         p.key_sq = 1;
+        p.use_cells = 1;
         const long long nmax = max_points(p.offsets, p.B);
         long long items = p.use_range ? p.HW : (nmax > p.HW ? nmax : p.HW);
         static const int dbg_times = [] { const char* e = getenv("SLU_P3_TIMES"); return e ? atoi(e) : 0; }();
@@ -1442,13 +1483,19 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
     }
     if (!generic && !exact_only()) {
         p.key_sq = 1;
+        // default: fire-and-forget RED.MIN.64 on the range key, then the tie pass.  Measured alternative (mode 3): a 128-bit
+        // compare-and-swap on a (range, index) cell settles the winner in the row kernel and deletes the tie pass (11 us per 16
+        // HDL-64 scans) -- but the row kernel is an atomic stream, and atomics that RETURN a value cost 36.0 us there against
+        // 15.2 us for the reductions: 0.090 ms in total against 0.072.
+        p.use_cells = cells_in_rows_path() ? 1 : 0;
         if (p.use_range && !g_no_fused) {
             // fixed elevation range: init -> one fused pass (angles + rows + depth test) -> ties
             const long long cells = (long long)p.B * p.HW;
             const long long gi = (cells + PT_THREADS - 1) / PT_THREADS;
             proj_init_kernel<<<(unsigned)(gi < 8LL * sms ? (gi < 1 ? 1 : gi) : 8LL * sms), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_init_kernel");
-            proj_fast_fused_kernel<<<dim3(wave_grid_x(proj_fast_fused_kernel, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
+            if (p.use_cells) proj_fast_fused_kernel<true><<<dim3(wave_grid_x(proj_fast_fused_kernel<true>, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
+            else proj_fast_fused_kernel<false><<<dim3(wave_grid_x(proj_fast_fused_kernel<false>, max_points(p.offsets, p.B), p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_fused_kernel");
         } else {
             // fp32-prefiltered path: angles (+ init, + exact theta extremes per block) -> rows -> ties
@@ -1456,10 +1503,11 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
             p.gx = wave_grid_x(proj_fast_angles_kernel, nmax, p.B, sms);      // the row kernel reads gx per-block partials
             proj_fast_angles_kernel<<<dim3(p.gx, p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_angles_kernel");
-            proj_fast_rows_kernel<<<dim3(wave_grid_x(proj_fast_rows_kernel, nmax, p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
+            if (p.use_cells) proj_fast_rows_kernel<true><<<dim3(wave_grid_x(proj_fast_rows_kernel<true>, nmax, p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
+            else proj_fast_rows_kernel<false><<<dim3(wave_grid_x(proj_fast_rows_kernel<false>, nmax, p.B, sms), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_fast_rows_kernel");
         }
-        if (n_total > 0) {
+        if (n_total > 0 && !p.use_cells) {
             proj_ties_kernel<<<dim3(wave_grid_x(proj_ties_kernel, (max_points(p.offsets, p.B) + PT_BATCH - 1) / PT_BATCH, p.B, sms, g_light_waves), p.B), PT_THREADS, 0, st>>>(p);
             SLU_LAUNCH_CHECK("proj_ties_kernel");
         }
@@ -1488,7 +1536,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
 
 extern "C" int slu_debug_project_exact(int on) {
     const int prev = slu::g_exact_only;
-    if (on >= 0) slu::g_exact_only = on > 2 ? 1 : on;
+    if (on >= 0) slu::g_exact_only = on > 3 ? 1 : on;
     return prev;
 }
 
@@ -1530,7 +1578,7 @@ extern "C" int slu_project_batch(const float* d_xyzi, const uint32_t* d_raw_labe
     int rc = project_common(p, n_total, d_work, d_pix, d_winner, d_diag, false, st);
     if (rc) return rc;
     const int sms = sm_count_current_device();
-    if (cell_path()) {
+    if (p.use_cells) {
         const int gx = wave_grid_x(proj_resolve_planes_kernel<true>, (p.HW + PT_BATCH - 1) / PT_BATCH, B, sms, g_light_waves);
         proj_resolve_planes_kernel<true><<<dim3((unsigned)gx, B), PT_THREADS, 0, st>>>(p);
     } else {

@@ -244,9 +244,9 @@ def _project_in_mode(mode, *args, **kw):
 
 @pytest.mark.parametrize("case", ["auto", "fixed", "farthest", "yaw", "ties", "pile_up", "tiny_and_empty"])
 def test_cell_pipeline_agrees_with_four_launch_and_exact_kernels(cuda, case):
-    """slu_debug_project_exact(2) runs the cell pipeline (extremes -> fused point pass with a 128-bit compare-and-swap
-    depth test -> resolve), (0) the default four-launch path (64-bit atomicMin + tie pass), (1) the all-fp64 kernels.
-    All three must give identical bits: pixel of every point, winner per pixel INCLUDING the lowest-index rule among
+    """slu_debug_project_exact(0) = the default (angles -> rows with a 64-bit atomicMin on the range -> tie pass -> resolve),
+    (3) the same kernels with a 128-bit compare-and-swap depth test on a (range, index) cell per pixel and no tie pass, (2) the
+    fused cell pipeline (extremes -> one point pass -> resolve), (1) the all-fp64 kernels.  All four must give identical bits: pixel of every point, winner per pixel INCLUDING the lowest-index rule among
     exactly equal ranges, image, labels, theta range and the diagnostics."""
     H, W = 64, 2048
     kw = {}
@@ -283,11 +283,13 @@ def test_cell_pipeline_agrees_with_four_launch_and_exact_kernels(cuda, case):
         scans = [synth.synth_scan(303, "tiny", n_points=1), e, synth.synth_scan(304, "tiny"), synth.synth_scan(305, "tiny", n_points=7)]
     offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
     dx, dr, dl = to_dev(np.concatenate([s[0] for s in scans]), np.concatenate([s[1] for s in scans]), cuda)
-    cells = _project_in_mode(2, dx, dr, offs, H, W, lut=dl, **kw)
-    four = _project_in_mode(0, dx, dr, offs, H, W, lut=dl, **kw)
+    cells = _project_in_mode(0, dx, dr, offs, H, W, lut=dl, **kw)
+    fused = _project_in_mode(2, dx, dr, offs, H, W, lut=dl, **kw)
+    ties = _project_in_mode(3, dx, dr, offs, H, W, lut=dl, **kw)
     exact = _project_in_mode(1, dx, dr, offs, H, W, lut=dl, **kw)
     for key in ("pix", "winner", "img", "label", "theta", "diag"):
-        assert torch.equal(cells[key], four[key]), ("four-launch", key)
+        assert torch.equal(cells[key], fused[key]), ("fused cell pipeline", key)
+        assert torch.equal(cells[key], ties[key]), ("cells in the row kernel", key)
         assert torch.equal(cells[key], exact[key]), ("exact", key)
     if case == "ties":
         w = cells["winner"][0].reshape(-1).cpu().numpy()
