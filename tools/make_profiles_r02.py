@@ -37,12 +37,15 @@ def kernel_report():
         sc = {r["stage"]: r for r in json.load(open(ps))["rows"]}
     cols = [("stage", lambda r: r["stage"]), ("ms", lambda r: r["ms"]), ("algorithmic MB", lambda r: r["algorithmic_MB"]),
             ("GB/s", lambda r: r["GBps"]), ("of measured peak", lambda r: r["frac_of_measured_peak"]),
-            ("scans/s", lambda r: r["scans_per_s"]), ("round 1 ms", lambda r: r1.get(r["stage"], {}).get("ms", "")),
+            ("scans/s", lambda r: r["scans_per_s"]), ("ms, clean flush", lambda r: r.get("ms_clean_flush", "")),
+            ("of peak, clean flush", lambda r: r.get("frac_of_measured_peak_clean_flush", "")), ("round 1 ms", lambda r: r1.get(r["stage"], {}).get("ms", "")),
             ("round 1 of peak", lambda r: r1.get(r["stage"], {}).get("frac_of_measured_peak", "")),
             ("one-pixel-per-thread kernels, this build", lambda r: sc.get(r["stage"], {}).get("ms", "")), ("note", lambda r: r.get("note", ""))]
     with open(os.path.join(P, "kernel_report_r02.md"), "w") as f:
         f.write("# GPU-side time per stage, round 2 (tools/kernel_report.py)\n\nEvery stage captured into a CUDA graph once and replayed "
-                "between CUDA events, median of 20, L2 flushed (256 MB write) before each replay; one B200.\n"
+                "between CUDA events, median of 20, L2 flushed (256 MB write) before each replay; one B200.  The `clean flush` columns repeat the "
+                "measurement with the write followed by a 256 MB READ of another buffer: the write alone leaves the L2 full of dirty lines of the flush "
+                "buffer, whose write-back (up to 126 MB = 19 us at the copy peak) is then charged to the timed kernel.\n"
                 f"Algorithmic bytes per SURVEY.md 8d; peak = {d['peak_GBps']} GB/s (measured copy, MEASURED_PEAKS.json).  "
                 "The last numeric column is the same build with `SLU_NO_PACKED=1` (the round-1 style one-pixel-per-thread kernels).\n\n")
         f.write(table(d["rows"], cols) + "\n")
