@@ -452,8 +452,9 @@ def leg_config4(cx: Ctx):
 def leg_config5(cx: Ctx):
     """configs[4]: the training-step data path, the global batch of 16 HDL-64 scans dealt to the ranks (STRONG scaling).
     Per rank: projection (4 launches) -> loader tensors incl. normals (2) -> fused evidential loss forward + backward from
-    the head output [B_local, C+1, 64, 2048]; the ranks exchange ONE float64 (the valid-pixel count), launched on a side
-    stream as soon as the labels exist.  Every rank asserts that its gradient equals, bit for bit, the matching slice of
+    the head output [B_local, C+1, 64, 2048]; the ranks exchange ONE number (the valid-pixel count), launched on a side
+    stream as soon as the labels exist -- by the count kernel itself over NVLink peer memory (csrc/slu_peer.cu) when all
+    ranks share a node, by an NCCL all-reduce otherwise (`count_transport` says which).  Every rank asserts that its gradient equals, bit for bit, the matching slice of
     the single-process full-batch gradient.  Timed eager (through the Python API) and as one CUDA graph."""
     from semanticlidarunc_b200 import ops, synth
     from semanticlidarunc_b200.dataset.definitions import build_id_lut
@@ -534,6 +535,7 @@ def leg_config5(cx: Ctx):
            "graph_ms_per_step": None if graph_stats is None else stats(graph_stats),
            "graph_scans_per_s": None if graph_stats is None else round(GB / float(np.median(graph_stats)) * 1e3, 1),
            "graph_grad_equals_eager": graph_equal,
+           "count_transport": crit.count_transport(dev),
            "shard_grad_equals_full_batch_slice_bitwise": all_equal, "loss_sum_of_shares_rel_err": loss_rel,
            "full_batch_loss": float(full4[0]),
            "loss_kernel": {"ms_local_shard": round(t_loss, 5), "bytes_per_px": 176,

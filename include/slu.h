@@ -177,6 +177,37 @@ int slu_evidential_loss_fused(const float* d_outputs, const int64_t* d_target, c
 int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t n_px,
                     const int64_t* h_ignore, int n_ignore, double* d_count, slu_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The exchange of the batch-sharded training step over NVLink / NVSwitch peer memory (BASELINE.json
+ * configs[4]): slu_count_valid fused with the all-reduce of its result.  No reference counterpart (the reference is a
+ * single process; its dormant all_reduce is src/utils/agg.py:75-83).
+ *
+ *   slu_peer_mailbox_create   allocates this rank's 4 KB mailbox on the current device (zeroed) and returns its device
+ *                             pointer and the 64 bytes of its CUDA IPC handle; the caller passes the handle bytes to the
+ *                             other ranks' processes (one all-gather at set-up)
+ *   slu_peer_mailbox_open     maps another rank's mailbox (same node) into this process; _close unmaps it
+ *   slu_peer_mailbox_destroy  frees the own mailbox (after every peer has closed it)
+ *   slu_count_valid_exchange  ONE kernel: counts the valid pixels of (d_target, mask) as slu_count_valid does; its last CTA
+ *                             stores (step << 32 | count) into slot [rank] of every rank's mailbox, waits until all
+ *                             `world` words of this step have arrived in its own mailbox and writes their sum -- an
+ *                             integer, so bit-identical on every rank -- to d_count[0] (float64, OVERWRITTEN).
+ *                             h_boxes [world]: HOST array of device pointers, h_boxes[r] = rank r's mailbox as mapped in
+ *                             this process (h_boxes[rank] = the own one).  Every rank of the group must make the same
+ *                             sequence of calls; the step number lives in the mailbox, so the launch can be captured
+ *                             in a CUDA graph and replayed.  n_px < 2^32, world <= 16, n_ignore <= 8.  A peer that does
+ *                             not show up within timeout_s (<= 0: 2 s) makes d_count NaN instead of hanging
+ *                             (slu_peer_mailbox_timeouts counts such events; it synchronises).
+ */
+int slu_peer_mailbox_create(void** d_box_out, uint8_t* handle64_out);
+int slu_peer_mailbox_open(const uint8_t* handle64, void** d_box_out);
+int slu_peer_mailbox_close(void* d_box);
+int slu_peer_mailbox_destroy(void* d_box);
+int slu_peer_mailbox_timeouts(const void* d_box, uint32_t* h_out);
+int slu_count_valid_exchange(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t n_px,
+                             const int64_t* h_ignore, int n_ignore,
+                             void* const* h_boxes, int rank, int world, double timeout_s,
+                             double* d_count, slu_stream_t stream);
+
 /* Training-step form of slu_evidential_loss_fused: no host arithmetic and no memset between steps.
  *   d_count  [1] float64  number of valid pixels the masked mean runs over.  precounted == 0: the call counts the valid
  *            pixels of (d_target, mask) into it (it must hold 0 on entry and is reset to 0 by the kernel);

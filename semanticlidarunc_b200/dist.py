@@ -88,3 +88,90 @@ def bind_to_gpu_numa_node(index: int):
         return len(cpus)
     except Exception:
         return 0
+
+
+class PeerCounter:
+    """Mailboxes for `ops.count_valid_exchange`: the valid-pixel count of the batch-sharded training step summed over the
+    ranks by the count kernel itself, through NVLink / NVSwitch peer stores instead of an NCCL all-reduce (tens of
+    microseconds of collective latency between two kernels that take a few microseconds each).
+
+    Set-up is plumbing: every rank allocates a 4 KB mailbox in libslu (cudaMalloc), the 64-byte CUDA IPC handles go round
+    with ONE all_gather over the process group, and every rank maps the others' mailboxes.  Works for ranks on one node
+    (one process per GPU); `PeerCounter.create` returns None when that is not the case or the driver refuses the
+    mapping, and the caller keeps the NCCL path."""
+
+    def __init__(self, boxes, rank, world, timeout_s=2.0):
+        import ctypes as C
+        self._boxes = list(boxes)                       # device pointers (ints); boxes[rank] is the own mailbox
+        self.rank, self.world, self.timeout_s = int(rank), int(world), float(timeout_s)
+        self.boxes_array = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self._boxes])
+        self._closed = False
+
+    @classmethod
+    def create(cls, group=None, device=None, timeout_s: float = 2.0):
+        import ctypes as C
+        import socket
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        g = None if group is True else group
+        world_size, rank = dist.get_world_size(g), dist.get_rank(g)
+        if world_size < 2 or world_size > 16 or not torch.cuda.is_available():
+            return None
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        own, handle, err = C.c_void_p(), (C.c_uint8 * 64)(), ""
+        with torch.cuda.device(dev):
+            try:
+                _lib.check(_lib.lib().slu_peer_mailbox_create(C.byref(own), handle), "slu_peer_mailbox_create")
+            except Exception as e:                      # no IPC support here: every rank must still take part below
+                err = str(e)
+            mine = {"host": socket.gethostname(), "handle": bytes(handle), "err": err}
+            everyone = [None] * world_size
+            dist.all_gather_object(everyone, mine, group=g)
+            ok = all(not e["err"] for e in everyone) and len({e["host"] for e in everyone}) == 1
+            boxes, opened = [None] * world_size, []
+            if ok:
+                for r, e in enumerate(everyone):
+                    if r == rank:
+                        boxes[r] = own.value
+                        continue
+                    p = C.c_void_p()
+                    buf = (C.c_uint8 * 64).from_buffer_copy(e["handle"])
+                    if _lib.lib().slu_peer_mailbox_open(buf, C.byref(p)) != 0:
+                        ok = False
+                        break
+                    boxes[r] = p.value
+                    opened.append(p.value)
+            # all or nothing: a rank that could not map a peer makes every rank fall back
+            flags = [None] * world_size
+            dist.all_gather_object(flags, bool(ok), group=g)
+            if not all(flags):
+                for p in opened:
+                    _lib.lib().slu_peer_mailbox_close(C.c_void_p(p))
+                if own.value:
+                    _lib.lib().slu_peer_mailbox_destroy(own)
+                return None
+        return cls(boxes, rank, world_size, timeout_s)
+
+    def timeouts(self) -> int:
+        """exchanges of THIS rank that gave up waiting for a peer (synchronises the device)"""
+        import ctypes as C
+        from . import _lib
+        n = C.c_uint32(0)
+        _lib.check(_lib.lib().slu_peer_mailbox_timeouts(C.c_void_p(self._boxes[self.rank]), C.byref(n)), "slu_peer_mailbox_timeouts")
+        return int(n.value)
+
+    def close(self, group=None):
+        """Unmap the peers' mailboxes, then (after a barrier: nobody may still be mapped) free the own one."""
+        import ctypes as C
+        from . import _lib
+        if self._closed:
+            return
+        self._closed = True
+        torch.cuda.synchronize()
+        for r, b in enumerate(self._boxes):
+            if r != self.rank and b:
+                _lib.lib().slu_peer_mailbox_close(C.c_void_p(b))
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=None if group is True else group)
+        _lib.lib().slu_peer_mailbox_destroy(C.c_void_p(self._boxes[self.rank]))

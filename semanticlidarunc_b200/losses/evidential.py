@@ -17,7 +17,10 @@ Three ways in, same kernel (slu_evidential_loss_step; the loss values are writte
 Batch-sharded training (BASELINE.json configs[4], `group=`): the only thing ranks exchange is the valid-pixel count.
 `prefetch_count(target)` launches the count kernel and its all-reduce on a SIDE stream as soon as the labels exist
 (they do not depend on the network), so the collective overlaps whatever the main stream does next (loader kernels,
-the backbone's forward) instead of sitting between the count and the loss kernel.
+the backbone's forward) instead of sitting between the count and the loss kernel.  With `peer_exchange=True` (default)
+and all ranks on one node, count and all-reduce are ONE kernel: its last CTA publishes the local count in every rank's
+mailbox over NVLink peer stores and sums what the others published (`dist.PeerCounter`, csrc/slu_peer.cu); NCCL stays
+the fallback (other topologies, `peer_exchange=False`).
 """
 from __future__ import annotations
 
@@ -74,11 +77,13 @@ class EvidentialLoss(nn.Module):
     stays the DDP wrapper's job (use sum, not mean)."""
 
     def __init__(self, w_mse: float = 1.0, w_kl: float = 0.05, ignore_index=None, temperature: float = 1.0, eps: float = 1e-8,
-                 group=None):
+                 group=None, peer_exchange: bool = True):
         super().__init__()
         self.w_mse, self.w_kl = float(w_mse), float(w_kl)
         self.ignore_index, self.temperature, self.eps = ignore_index, float(temperature), float(eps)
         self.group = group
+        self.peer_exchange = bool(peer_exchange)
+        self._peers = {}             # per device: dist.PeerCounter, or None once the set-up has failed (NCCL from then on)
         self._bufs = {}              # per device: count float64[1], state float64[3]
         self._side = {}              # per device: side stream of the count prefetch
         self._prefetched = None      # (event, count buffer) of a pending prefetch_count()
@@ -103,6 +108,33 @@ class EvidentialLoss(nn.Module):
             target = target[:, 0]
         return target if target.dtype == torch.int64 else target.long()
 
+    def _peer_counter(self, dev):
+        """the NVLink mailboxes of this device (collective set-up on first use), or None -> NCCL"""
+        if not self.peer_exchange:
+            return None
+        if dev not in self._peers:
+            from ..dist import PeerCounter
+            self._peers[dev] = PeerCounter.create(self.group, device=dev)
+        return self._peers[dev]
+
+    def count_transport(self, dev=None) -> str:
+        """"peer-memory" or "nccl": how the valid-pixel count is summed over the ranks on `dev` ("none": not sharded)"""
+        if _group_of(self.group)[1] == 1:
+            return "none"
+        dev = torch.device("cuda", torch.cuda.current_device()) if dev is None else torch.device(dev)
+        return "peer-memory" if self._peer_counter(dev) is not None else "nccl"
+
+    def _global_count(self, target, count, ids, keep, g):
+        """count <- valid pixels of `target` over all ranks, enqueued on the current stream"""
+        peers = self._peer_counter(target.device)
+        if peers is not None:
+            ops.count_valid_exchange(target, count, peers, ignore=ids, keep_mask=keep)     # one kernel: count + exchange
+            return
+        import torch.distributed as dist
+        count.zero_()
+        ops.count_valid(target, count, ignore=ids, keep_mask=keep)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
+
     # ---- the sharded count, off the critical path ------------------------------------------------------------------
     @torch.no_grad()
     def prefetch_count(self, target: torch.Tensor):
@@ -112,20 +144,18 @@ class EvidentialLoss(nn.Module):
         g, world = _group_of(self.group)
         if world == 1:
             return
-        import torch.distributed as dist
         target = self._target3(target)
         dev = target.device
         count, _ = self._work_buffers(dev)
         ids, keep = self._mask(target)
+        self._peer_counter(dev)                      # collective set-up happens here, outside any stream capture
         main = torch.cuda.current_stream(dev)
         if dev not in self._side:
             self._side[dev] = torch.cuda.Stream(device=dev)
         side = self._side[dev]
         side.wait_stream(main)                       # the labels are produced on the main stream
         with torch.cuda.stream(side):
-            count.zero_()
-            ops.count_valid(target, count, ignore=ids, keep_mask=keep)
-            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
+            self._global_count(target, count, ids, keep, g)
             ev = torch.cuda.Event()
             ev.record(side)
         target.record_stream(side)
@@ -142,11 +172,8 @@ class EvidentialLoss(nn.Module):
             if self._prefetched is not None and self._prefetched[1] == dev:
                 torch.cuda.current_stream(dev).wait_event(self._prefetched[0])
                 self._prefetched = None
-            else:                                    # in line: count kernel -> all-reduce -> loss kernel
-                import torch.distributed as dist
-                count.zero_()
-                ops.count_valid(target, count, ignore=ids, keep_mask=keep)
-                dist.all_reduce(count, op=dist.ReduceOp.SUM, group=g)
+            else:                                    # in line: count kernel (+ exchange) -> loss kernel
+                self._global_count(target, count, ids, keep, g)
         return ops.evidential_loss_step(outputs, target, count, state, w_mse=self.w_mse, w_kl=self.w_kl, ignore=ids,
                                         keep_mask=keep, temperature=self.temperature, eps_alpha=self.eps, eps_mse=self.eps,
                                         eps_kl=self.eps, precounted=precounted, want_grad=want_grad, loss4=loss4, grad=grad)

@@ -359,6 +359,23 @@ def count_valid(target: torch.Tensor, count: torch.Tensor, *, ignore=(), keep_ma
 
 
 @_lib.device_guard
+def count_valid_exchange(target: torch.Tensor, count: torch.Tensor, peers, *, ignore=(), keep_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """count float64[1] <- the number of valid pixels of `target` summed over ALL ranks of `peers` (a dist.PeerCounter):
+    slu_count_valid fused with the all-reduce of its result over NVLink peer memory, one kernel, capturable in a CUDA
+    graph.  Every rank of the group must call it the same number of times."""
+    _lib.require_cuda()
+    target = _lib.as_buffer(target, torch.int64, "target")
+    if keep_mask is not None:
+        keep_mask = _lib.as_buffer(keep_mask, torch.bool, "keep_mask")
+    ign = [int(v) for v in ignore]
+    h_ign = (_lib.C.c_int64 * max(1, len(ign)))(*ign) if ign else None
+    _lib.check(_lib.lib().slu_count_valid_exchange(_lib.ptr(target), _lib.ptr(keep_mask), target.numel(), h_ign, len(ign),
+                                                   peers.boxes_array, peers.rank, peers.world, float(peers.timeout_s),
+                                                   _lib.ptr(count), _lib.stream_ptr()), "slu_count_valid_exchange")
+    return count
+
+
+@_lib.device_guard
 def special_functions(x: torch.Tensor) -> torch.Tensor:
     """[n,3] = lgamma, digamma, trigamma of x > 0 as the loss kernels evaluate them (slu_diag_special)."""
     _lib.require_cuda()

@@ -93,6 +93,43 @@ def timed(fn, n=20):
     return ts
 
 
+# ---- the count exchange over NVLink peer memory against an NCCL all-reduce of the same counts: 40 random label maps of
+#      different sizes, eager, then 20 replays of a captured exchange (the step number lives in device memory)
+transport = crit.count_transport(dev)
+peer_ok, peer_timeouts = None, None
+if world > 1 and transport == "peer-memory":
+    peers = crit._peer_counter(dev)
+    peer_ok = True
+    gen = torch.Generator().manual_seed(900 + rank)
+    cnt = torch.zeros(1, dtype=torch.float64, device=dev)
+    for k in range(40):
+        n = 1000 + 37 * k * (rank + 1)
+        tg = torch.randint(0, 5, (n,), generator=gen).to(dev)
+        ops.count_valid_exchange(tg, cnt, peers, ignore=(0, 3))
+        ref = ((tg != 0) & (tg != 3)).sum().double().reshape(1)
+        dist.all_reduce(ref)
+        peer_ok = peer_ok and bool(cnt.item() == ref.item())
+    tg = torch.randint(0, 5, (50_000,), generator=gen).to(dev)
+    ref = (tg != 0).sum().double().reshape(1)
+    dist.all_reduce(ref)
+    torch.cuda.synchronize()
+    gx = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gx):
+        ops.count_valid_exchange(tg, cnt, peers, ignore=(0,))
+    for k in range(20):
+        cnt.fill_(-1.0)
+        gx.replay()
+        peer_ok = peer_ok and bool(cnt.item() == ref.item())
+    peer_timeouts = peers.timeouts()
+    # and the whole step with the NCCL exchange instead: the same gradient, bit for bit
+    crit_nccl = EvidentialLoss(1.0, 0.05, ignore_index=0, group=True, peer_exchange=False)
+    g_peer = outs.grad.clone()
+    step(xyzi, raw, offs, outs, crit_nccl, ws)
+    peer_ok = peer_ok and bool(torch.equal(outs.grad, g_peer)) and crit_nccl.count_transport(dev) == "nccl"
+    pk = torch.tensor([1.0 if peer_ok else 0.0], device=dev)
+    dist.all_reduce(pk, op=dist.ReduceOp.MIN)
+    peer_ok = bool(pk.item() == 1.0)
+
 for _ in range(3):
     step(xyzi, raw, offs, outs, crit, ws)
 times = timed(lambda: step(xyzi, raw, offs, outs, crit, ws))
@@ -130,8 +167,9 @@ if rank == 0:
                       "ms_per_step_cuda_graph": None if graph_ms is None else round(graph_ms, 4),
                       "scans_per_s_cuda_graph": None if graph_ms is None else round(GB / graph_ms * 1e3, 1), "graph_grad_equals_eager": graph_grad_equal,
                       "shard_grad_equals_full_batch_bitwise": bool(ok.item() == 1.0), "loss_sum_of_shares_rel_err": loss_rel,
-                      "full_batch_loss": float(full_loss)}))
-rc = 0 if (ok.item() == 1.0 and loss_rel < 1e-6) else 1
+                      "full_batch_loss": float(full_loss), "count_transport": transport,
+                      "peer_exchange_equals_nccl": peer_ok, "peer_exchange_timeouts": peer_timeouts}))
+rc = 0 if (ok.item() == 1.0 and loss_rel < 1e-6 and peer_ok is not False) else 1
 sys.stdout.flush()
 barrier()
 # a captured graph that holds an NCCL collective keeps the communicator busy at teardown (destroy_process_group waits
