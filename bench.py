@@ -442,6 +442,7 @@ def leg_config4(cx: Ctx):
             "scaling": "strong", "chunks_per_rank": len(mine), "ms_per_sweep": stats(times), "scans_per_s": round(N_SCANS / ms * 1e3),
             "aggregate_gbs": round(nbytes / ms / 1e6, 1), "frac_of_peak_per_gpu": round(nbytes / ms / 1e6 / cx.peak / cx.world, 4),
             "counts_sha256_16": digest, "n1_counts_sha256_16": digest_n1, "equals_single_process_counts": equal,
+            "count_transport": sdist.count_transport(),
             "confmat_sum": int(gcm.sum()), "mIoU": round(float((tp / den.clamp_min(1))[1:].mean()), 6), "ece": round(ece, 6),
             "int32_maps": {"ms_per_sweep": stats(times32), "scans_per_s": round(N_SCANS / ms32 * 1e3),
                            "frac_of_peak_per_gpu_12B_px": round(12 * N_SCANS * H * W / ms32 / 1e6 / cx.peak / cx.world, 4),

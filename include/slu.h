@@ -182,7 +182,7 @@ int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t
  * configs[4]): slu_count_valid fused with the all-reduce of its result.  No reference counterpart (the reference is a
  * single process; its dormant all_reduce is src/utils/agg.py:75-83).
  *
- *   slu_peer_mailbox_create   allocates this rank's 4 KB mailbox on the current device (zeroed) and returns its device
+ *   slu_peer_mailbox_create   allocates this rank's mailbox (264 KB) on the current device (zeroed) and returns its device
  *                             pointer and the 64 bytes of its CUDA IPC handle; the caller passes the handle bytes to the
  *                             other ranks' processes (one all-gather at set-up)
  *   slu_peer_mailbox_open     maps another rank's mailbox (same node) into this process; _close unmaps it
@@ -197,6 +197,12 @@ int slu_count_valid(const int64_t* d_target, const uint8_t* d_keep_mask, int64_t
  *                             in a CUDA graph and replayed.  n_px < 2^32, world <= 16, n_ignore <= 8.  A peer that does
  *                             not show up within timeout_s (<= 0: 2 s) makes d_count NaN instead of hanging
  *                             (slu_peer_mailbox_timeouts counts such events; it synchronises).
+ *   slu_peer_allreduce_i64    ONE single-CTA kernel: d_out[0 .. n_a+n_b) = sum over the ranks of the int64 vector
+ *                             (d_a[0..n_a), d_b[0..n_b)) -- the end-of-sweep combination of the confusion matrix and the
+ *                             reliability bins (n_a + n_b <= 512, d_b may be NULL).  Payload stores into every
+ *                             rank's mailbox, a system-scope fence, a release store of the step number, an acquire wait
+ *                             for the peers' step numbers, sums in rank order: integers, identical bits on every rank.
+ *                             Inputs are left untouched.  A missing peer (timeout_s) fills d_out with INT64_MIN.
  */
 int slu_peer_mailbox_create(void** d_box_out, uint8_t* handle64_out);
 int slu_peer_mailbox_open(const uint8_t* handle64, void** d_box_out);
@@ -207,6 +213,9 @@ int slu_count_valid_exchange(const int64_t* d_target, const uint8_t* d_keep_mask
                              const int64_t* h_ignore, int n_ignore,
                              void* const* h_boxes, int rank, int world, double timeout_s,
                              double* d_count, slu_stream_t stream);
+int slu_peer_allreduce_i64(const int64_t* d_a, int n_a, const int64_t* d_b, int n_b,
+                           void* const* h_boxes, int rank, int world, double timeout_s,
+                           int64_t* d_out, slu_stream_t stream);
 
 /* Training-step form of slu_evidential_loss_fused: no host arithmetic and no memset between steps.
  *   d_count  [1] float64  number of valid pixels the masked mean runs over.  precounted == 0: the call counts the valid

@@ -47,6 +47,7 @@ SIGNATURES = {
     "slu_peer_mailbox_destroy": (_i, [_p]),
     "slu_peer_mailbox_timeouts": (_i, [_p, C.POINTER(C.c_uint32)]),
     "slu_count_valid_exchange": (_i, [_p, _p, _i64, _p, _i, _p, _i, _i, _d, _p, _p]),
+    "slu_peer_allreduce_i64": (_i, [_p, _i, _p, _i, _p, _i, _i, _d, _p, _p]),
     "slu_dirichlet_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _f, _p, _p, _p]),
     "slu_evidence_term": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _p, _i, _p, _p, _p]),
     "slu_logit_regularizer": (_i, [_p, _p, _p, _i, _i, _i64, _p, _i, _i, _f, _p, _p, _p]),

@@ -3,6 +3,8 @@
 // float64 that exchange is 30-60 us of latency between the count kernel and the loss kernel at 8 ranks -- as long as the
 // rest of a 2-scan step.  Here the count kernel does the exchange itself over NVLink / NVSwitch peer memory:
 //
+//   peer_allreduce_i64_kernel  the same mailboxes carry the one all-reduce of an evaluation sweep (confusion matrix +
+//                           reliability bins, C*C + 3*n_bins int64 <= 512): payload stores, fence, release flag, acquire.
 //   count_exchange_kernel   every CTA counts valid pixels of its part of the label map; the LAST CTA to arrive (ticket
 //                           counter) packs (step number << 32 | local count) into one 64-bit word, stores that word into
 //                           slot [parity][my rank] of EVERY rank's mailbox (plain 8-byte peer stores: atomic on the wire,
@@ -26,14 +28,21 @@ constexpr int PEER_MAX_WORLD = 16;
 constexpr int PEER_THREADS = 256;
 constexpr int PEER_MAX_IGNORE = 8;
 
-// one rank's mailbox (device memory of that rank, mapped into every peer): 4 KB
+constexpr int PEER_VEC_MAX = 512;                   // longest int64 vector of slu_peer_allreduce_i64 (C*C + 3*n_bins = 445 at C=20, 15 bins)
+
+// one rank's mailbox (device memory of that rank, mapped into every peer)
 struct PeerMailbox {
     unsigned long long slot[2][PEER_MAX_WORLD];     // [parity][source rank]: step << 32 | count
     unsigned long long step;                        // this rank's step counter (local use only)
     unsigned long long acc;                         // local count accumulator of the running launch
     unsigned int ticket;                            // CTA arrival counter of the running launch
     unsigned int timeouts;                          // number of exchanges that gave up waiting
+    // small-vector all-reduce (slu_peer_allreduce_i64): payload first, then the flag that publishes it
+    unsigned long long vstep;
+    unsigned long long vflag[2][PEER_MAX_WORLD];    // [parity][source rank]: step number of the payload in vec[parity][rank]
+    long long vec[2][PEER_MAX_WORLD][PEER_VEC_MAX];
 };
+constexpr size_t PEER_MAILBOX_BYTES = (sizeof(PeerMailbox) + 4095) / 4096 * 4096;
 
 struct PeerParams {
     const long long* target;
@@ -128,6 +137,60 @@ __global__ void __launch_bounds__(PEER_THREADS) count_exchange_kernel(const __gr
     }
 }
 
+struct PeerVecParams {
+    const long long* a;                             // first part of the vector (e.g. the confusion matrix)
+    const long long* b;                             // second part (e.g. the reliability bins) or NULL
+    int n_a, n_b;
+    long long* out;                                 // [n_a + n_b] sums over the ranks
+    PeerMailbox* box[PEER_MAX_WORLD];
+    int rank, world;
+    unsigned long long spin_ns;
+};
+
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One CTA: every rank stores its vector into slot [rank] of every rank's mailbox (8-byte peer stores, one element per
+// thread and peer), fences, publishes the step number with a release store, waits (acquire) for the `world` flags of this
+// step in its own mailbox and sums the payloads in rank order -- integers, so every rank gets the same bits.
+__global__ void __launch_bounds__(PEER_VEC_MAX) peer_allreduce_i64_kernel(const __grid_constant__ PeerVecParams p) {
+    PeerMailbox* mine = p.box[p.rank];
+    __shared__ unsigned long long s_step;
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) { s_step = mine->vstep + 1; mine->vstep = s_step; s_ok = 1; }
+    __syncthreads();
+    const unsigned long long step = s_step;
+    const int par = (int)(step & 1ull), n = p.n_a + p.n_b, i = threadIdx.x;
+    if (i < n) {
+        const long long v = i < p.n_a ? p.a[i] : p.b[i - p.n_a];
+        for (int r = 0; r < p.world; ++r) st_sys_u64(reinterpret_cast<unsigned long long*>(&p.box[r]->vec[par][p.rank][i]), (unsigned long long)v);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (i < p.world) {
+        st_release_sys_u64(&p.box[i]->vflag[par][p.rank], step);
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys_u64(&mine->vflag[par][i]) != step) {
+            if (globaltimer_ns() - t0 > p.spin_ns) { atomicExch(&s_ok, 0); break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (i < n) {
+        long long sum = 0;
+        for (int r = 0; r < p.world; ++r) sum += (long long)ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&mine->vec[par][r][i]));
+        p.out[i] = s_ok ? sum : (long long)0x8000000000000000ull;        // a missing peer poisons the result instead of hanging
+    }
+    if (i == 0 && !s_ok) atomicAdd(&mine->timeouts, 1u);
+}
+
 }  // namespace slu
 
 extern "C" int slu_peer_mailbox_create(void** d_box_out, uint8_t* handle64_out) {
@@ -135,8 +198,8 @@ extern "C" int slu_peer_mailbox_create(void** d_box_out, uint8_t* handle64_out) 
     if (!d_box_out || !handle64_out) return fail(SLU_E_ARG, "slu_peer_mailbox_create: NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     void* p = nullptr;
-    SLU_CUDA(cudaMalloc(&p, 4096));
-    cudaError_t e = cudaMemset(p, 0, 4096);
+    SLU_CUDA(cudaMalloc(&p, PEER_MAILBOX_BYTES));
+    cudaError_t e = cudaMemset(p, 0, PEER_MAILBOX_BYTES);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
@@ -203,5 +266,26 @@ extern "C" int slu_peer_mailbox_timeouts(const void* d_box, uint32_t* h_out) {
     using namespace slu;
     if (!d_box || !h_out) return fail(SLU_E_ARG, "slu_peer_mailbox_timeouts: NULL argument");
     SLU_CUDA(cudaMemcpy(h_out, &static_cast<const PeerMailbox*>(d_box)->timeouts, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int slu_peer_allreduce_i64(const int64_t* d_a, int n_a, const int64_t* d_b, int n_b,
+                                      void* const* h_boxes, int rank, int world, double timeout_s,
+                                      int64_t* d_out, slu_stream_t stream) {
+    using namespace slu;
+    if (!d_a || !d_out || !h_boxes) return fail(SLU_E_ARG, "slu_peer_allreduce_i64: NULL argument");
+    if (n_a < 1 || n_b < 0 || (n_b > 0 && !d_b) || n_a + n_b > PEER_VEC_MAX) return fail(SLU_E_RANGE, "vector of %d + %d elements unsupported (<= %d)", n_a, n_b, PEER_VEC_MAX);
+    if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world) return fail(SLU_E_RANGE, "rank %d / world %d unsupported (world <= %d)", rank, world, PEER_MAX_WORLD);
+    PeerVecParams p{};
+    p.a = reinterpret_cast<const long long*>(d_a); p.b = reinterpret_cast<const long long*>(d_b);
+    p.n_a = n_a; p.n_b = n_b; p.out = reinterpret_cast<long long*>(d_out);
+    for (int r = 0; r < world; ++r) {
+        if (!h_boxes[r]) return fail(SLU_E_ARG, "mailbox of rank %d is NULL", r);
+        p.box[r] = static_cast<PeerMailbox*>(h_boxes[r]);
+    }
+    p.rank = rank; p.world = world;
+    p.spin_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 2.0) * 1e9);
+    peer_allreduce_i64_kernel<<<1, PEER_VEC_MAX, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    SLU_LAUNCH_CHECK("peer_allreduce_i64_kernel");
     return 0;
 }

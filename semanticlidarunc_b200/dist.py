@@ -39,9 +39,43 @@ def pack_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None) 
     return torch.cat(parts).to(torch.int64)
 
 
+_PEERS = {}                      # (id of the group, device index) -> PeerCounter, or None once the set-up has failed there
+
+
+def peer_counter(group=None, device=None):
+    """The NVLink mailboxes of (group, device): created on first use (a collective: every rank of the group must get
+    here, as it must for the all-reduce this replaces), None when the ranks do not share a node, the driver refuses the
+    IPC mapping, or SLU_NO_PEER_EXCHANGE=1 -- the callers then use the process group's all-reduce."""
+    if os.environ.get("SLU_NO_PEER_EXCHANGE", "0") == "1" or not torch.cuda.is_available():
+        return None
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    g = None if group is True else group
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (id(g) if g is not None else 0, dev.index)
+    if key not in _PEERS:
+        _PEERS[key] = PeerCounter.create(g, device=dev)
+    return _PEERS[key]
+
+
+def count_transport(group=None, device=None) -> str:
+    """"peer-memory", "nccl" (the process group's all-reduce) or "none" (one rank): how the small exchanges travel"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(None if group is True else group) == 1:
+        return "none"
+    return "peer-memory" if peer_counter(group, device) is not None else "nccl"
+
+
 def allreduce_packed(buf: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum a packed int64 counter buffer over all ranks, in place (no-op without a process group)."""
+    """Sum a packed int64 counter buffer over all ranks, in place (no-op without a process group).  CUDA buffers of up to
+    512 elements go through one single-CTA kernel over NVLink peer memory (ops.peer_allreduce_i64) when the ranks share a
+    node; everything else through the process group (NCCL / gloo)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if buf.is_cuda and buf.dtype == torch.int64 and buf.is_contiguous() and buf.numel() <= 512:
+            peers = peer_counter(group, buf.device)
+            if peers is not None:
+                from . import ops
+                buf.copy_(ops.peer_allreduce_i64(buf, None, peers))
+                return buf
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf
 
@@ -49,8 +83,16 @@ def allreduce_packed(buf: torch.Tensor, group=None) -> torch.Tensor:
 def reduced_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = None, group=None):
     """(confmat, ece_bins) summed over all ranks with a single all-reduce of a packed COPY.  The arguments are
     left untouched, so live accumulators can keep accumulating and be reduced again later."""
-    buf = allreduce_packed(pack_counts(confmat, ece_bins), group=group)
     n = confmat.numel()
+    if (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and confmat.is_cuda and
+            confmat.dtype == torch.int64 and confmat.is_contiguous() and (ece_bins is None or (ece_bins.dtype == torch.int64 and ece_bins.is_contiguous())) and
+            n + (0 if ece_bins is None else ece_bins.numel()) <= 512):
+        peers = peer_counter(group, confmat.device)
+        if peers is not None:                        # one kernel reads both accumulators in place and writes the packed sums
+            from . import ops
+            buf = ops.peer_allreduce_i64(confmat, ece_bins, peers)
+            return buf[:n].view_as(confmat), (None if ece_bins is None else buf[n:].view_as(ece_bins))
+    buf = allreduce_packed(pack_counts(confmat, ece_bins), group=group)
     return buf[:n].view_as(confmat), (None if ece_bins is None else buf[n:].view_as(ece_bins))
 
 
@@ -62,8 +104,7 @@ def allreduce_counts(confmat: torch.Tensor, ece_bins: Optional[torch.Tensor] = N
     `reduced_counts`, which reduces a copy."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    buf = pack_counts(confmat, ece_bins)
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    buf = allreduce_packed(pack_counts(confmat, ece_bins), group=group)
     n = confmat.numel()
     confmat.copy_(buf[:n].view_as(confmat))
     if ece_bins is not None:

@@ -113,8 +113,8 @@ class EvidentialLoss(nn.Module):
         if not self.peer_exchange:
             return None
         if dev not in self._peers:
-            from ..dist import PeerCounter
-            self._peers[dev] = PeerCounter.create(self.group, device=dev)
+            from ..dist import peer_counter
+            self._peers[dev] = peer_counter(self.group, dev)        # one set of mailboxes per (group, device), shared with dist.*
         return self._peers[dev]
 
     def count_transport(self, dev=None) -> str:

@@ -375,6 +375,26 @@ def count_valid_exchange(target: torch.Tensor, count: torch.Tensor, peers, *, ig
     return count
 
 
+PEER_VEC_MAX = 512
+
+
+@_lib.device_guard
+def peer_allreduce_i64(a: torch.Tensor, b: Optional[torch.Tensor], peers, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[0 .. a.numel() + b.numel()) = the int64 vector (a, b) summed over ALL ranks of `peers` (a dist.PeerCounter) by one
+    single-CTA kernel over NVLink peer memory (slu_peer_allreduce_i64); a and b are left untouched.  At most 512 elements."""
+    _lib.require_cuda()
+    a = _lib.as_buffer(a, torch.int64, "a").reshape(-1)
+    n_b = 0
+    if b is not None:
+        b = _lib.as_buffer(b, torch.int64, "b").reshape(-1)
+        n_b = b.numel()
+    if out is None:
+        out = torch.empty(a.numel() + n_b, dtype=torch.int64, device=a.device)
+    _lib.check(_lib.lib().slu_peer_allreduce_i64(_lib.ptr(a), a.numel(), _lib.ptr(b), n_b, peers.boxes_array, peers.rank, peers.world,
+                                                 float(peers.timeout_s), _lib.ptr(out), _lib.stream_ptr()), "slu_peer_allreduce_i64")
+    return out
+
+
 @_lib.device_guard
 def special_functions(x: torch.Tensor) -> torch.Tensor:
     """[n,3] = lgamma, digamma, trigamma of x > 0 as the loss kernels evaluate them (slu_diag_special)."""

@@ -120,6 +120,32 @@ if world > 1 and transport == "peer-memory":
         cnt.fill_(-1.0)
         gx.replay()
         peer_ok = peer_ok and bool(cnt.item() == ref.item())
+    # the small-vector all-reduce on the same mailboxes (confusion matrix + reliability bins of a sweep): random int64 vectors
+    # of every split (a | b), against NCCL; then graph replays
+    from semanticlidarunc_b200 import dist as sdist
+    for k in range(30):
+        n_a = 1 + (53 * k) % 400
+        n_b = 0 if k % 3 == 0 else (7 * k) % (512 - n_a) + 1
+        va = torch.randint(-2**40, 2**40, (n_a,), generator=gen).to(dev)
+        vb = torch.randint(0, 2**50, (n_b,), generator=gen).to(dev) if n_b else None
+        got = ops.peer_allreduce_i64(va, vb, peers)
+        ref = torch.cat([va, vb]) if n_b else va.clone()
+        dist.all_reduce(ref)
+        peer_ok = peer_ok and bool(torch.equal(got, ref))
+    cm = torch.randint(0, 10**9, (20, 20), generator=gen).to(dev)
+    bn = torch.randint(0, 10**9, (45,), generator=gen).to(dev)
+    ref = torch.cat([cm.reshape(-1), bn]); dist.all_reduce(ref)
+    rc_, rb_ = sdist.reduced_counts(cm, bn)                          # the public path: must pick the peer kernel here
+    peer_ok = peer_ok and bool(torch.equal(rc_.reshape(-1), ref[:400]) and torch.equal(rb_, ref[400:])) and sdist.count_transport() == "peer-memory"
+    outv = torch.empty(445, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    gv = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gv):
+        ops.peer_allreduce_i64(cm, bn, peers, out=outv)
+    for k in range(20):
+        outv.fill_(-7)
+        gv.replay()
+        peer_ok = peer_ok and bool(torch.equal(outv, ref))
     peer_timeouts = peers.timeouts()
     # and the whole step with the NCCL exchange instead: the same gradient, bit for bit
     crit_nccl = EvidentialLoss(1.0, 0.05, ignore_index=0, group=True, peer_exchange=False)
