@@ -56,6 +56,12 @@ def _worker(rank, world, port, q):
     hist = torch.full((2, 16), rank + 1, dtype=torch.int64)
     sdist.allreduce_counts(hist)
     assert int(hist.sum()) == 3 * 32
+    # without a GPU there are no NVLink mailboxes: the exchanges fall back to the process group, and the non-destructive
+    # reduction (a packed copy) leaves the live accumulators alone
+    assert sdist.peer_counter() is None and sdist.count_transport() == "nccl"
+    live = torch.full((3,), rank + 1, dtype=torch.int64)
+    total, _ = sdist.reduced_counts(live)
+    assert total.tolist() == [3, 3, 3] and live.tolist() == [rank + 1] * 3
     q.put((rank, cm.numpy(), bins.numpy()))
     dist.barrier()
     dist.destroy_process_group()
