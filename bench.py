@@ -452,7 +452,7 @@ def leg_config4(cx: Ctx):
 # ------------------------------------------------------------------------------------------------ config 5
 def leg_config5(cx: Ctx):
     """configs[4]: the training-step data path, the global batch of 16 HDL-64 scans dealt to the ranks (STRONG scaling).
-    Per rank: projection (4 launches) -> loader tensors incl. normals (2) -> fused evidential loss forward + backward from
+    Per rank: projection (4 launches) -> loader tensors (views of the projection's planes + the normals kernel, 1) -> fused evidential loss forward + backward from
     the head output [B_local, C+1, 64, 2048]; the ranks exchange ONE number (the valid-pixel count), launched on a side
     stream as soon as the labels exist -- by the count kernel itself over NVLink peer memory (csrc/slu_peer.cu) when all
     ranks share a node, by an NCCL all-reduce otherwise (`count_transport` says which).  Every rank asserts that its gradient equals, bit for bit, the matching slice of
@@ -476,7 +476,7 @@ def leg_config5(cx: Ctx):
         proj = ops.project_batch(xyzi, raw, offs, H, W, lut=lut, workspace=ws[0])
         ws[0] = proj["workspace"]
         crit.prefetch_count(proj["label"])                 # count + its all-reduce on a side stream, off the critical path
-        fr = ops.frame_tensors(proj["img"])                # range / reflectivity / xyz / normals / semantics
+        fr = ops.frame_tensors(proj["img"], label=proj["label"])   # range / reflectivity / xyz / semantics as views of the projection's planes, normals computed
         loss4, grad = crit.forward_backward(outs, proj["label"])
         return loss4, grad, fr
 

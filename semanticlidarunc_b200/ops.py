@@ -629,11 +629,15 @@ def organized_planes(xyzi: torch.Tensor, raw_label: Optional[torch.Tensor], H: i
 
 @_lib.device_guard
 def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float = 0.25, want_normals: bool = True,
-                  drop_empty_rows: bool = False) -> dict:
+                  drop_empty_rows: bool = False, label: Optional[torch.Tensor] = None) -> dict:
     """Loader glue on the device (slu_frame_tensors): img [B,6,H,W] planes -> the loaders' five tensors,
     stacked over B: range [B,1,h,w], reflectivity [B,1,h,w], xyz [B,3,h,w], normals [B,3,h,w], semantics
     [B,1,h,w] int64.  out_hw=(h,w) resizes with cv2's INTER_NEAREST rule; flip: per-scan booleans;
-    drop_empty_rows removes image rows without any return first (WADS) and adds "rows_kept" [B] int32."""
+    drop_empty_rows removes image rows without any return first (WADS) and adds "rows_kept" [B] int32.
+
+    label: the int64 label map [B,H,W] project_batch returned next to img.  With it, and nothing to resize, flip or
+    drop, no plane is copied: range / reflectivity / xyz are VIEWS of img's planes (values, shapes and dtypes as above;
+    contiguous per scan, batch stride 6*H*W), semantics a view of label, and only the normals kernel is launched."""
     _lib.require_cuda()
     img = _lib.as_buffer(img, torch.float32, "img")
     if img.dim() != 4 or img.size(1) != 6:
@@ -641,6 +645,12 @@ def frame_tensors(img: torch.Tensor, out_hw=None, flip=None, norm_factor: float 
     B, _, Hs, Ws = img.shape
     Hd, Wd = (Hs, Ws) if out_hw is None else (int(out_hw[0]), int(out_hw[1]))
     dev = img.device
+    if label is not None and (Hd, Wd) == (Hs, Ws) and flip is None and not drop_empty_rows:
+        if label.dtype != torch.int64 or tuple(label.shape) != (B, Hs, Ws) or label.device != dev:
+            raise ValueError("label must be the int64 [B,H,W] map that belongs to img")
+        return {"range": img[:, 3:4], "reflectivity": img[:, 4:5], "xyz": img[:, 0:3],
+                "normals": frame_normals(img, norm_factor) if want_normals else None,
+                "semantics": label.unsqueeze(1)}
     h_flip = None
     if flip is not None:
         f = np.ascontiguousarray(np.broadcast_to(np.asarray(flip, dtype=np.uint8), (B,)))

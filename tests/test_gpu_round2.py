@@ -494,3 +494,24 @@ def test_config1_full_size_single_scan_vs_oracle(cuda):
     ece = ops.ece_from_bins(bins)[0]
     ece_ref = om.ece_from_counts(n_ref, c_ref, s_ref)[0]
     assert abs(ece - ece_ref) <= 1e-5 * abs(ece_ref)
+
+
+def test_frame_tensors_views_equal_the_copies(cuda):
+    """ops.frame_tensors(img, label=...) hands out range / reflectivity / xyz / semantics as views of the projection's planes
+    (no resample copy when nothing is resized, flipped or dropped): same values, shapes and dtypes as the copying path,
+    contiguous per scan; any resize / flip / row dropping takes the copying kernel as before."""
+    scans = [synth.synth_scan(70 + i, "hdl64", n_points=30_000 + 1000 * i) for i in range(3)]
+    offs = np.concatenate([[0], np.cumsum([s[0].shape[0] for s in scans])])
+    xyzi = torch.from_numpy(np.concatenate([s[0] for s in scans])).to(cuda)
+    raw = torch.from_numpy(np.concatenate([s[1] for s in scans]).view(np.int32)).to(cuda)
+    lut = torch.from_numpy(build_id_lut()).to(cuda)
+    proj = ops.project_batch(xyzi, raw, offs, 64, 2048, lut=lut)
+    a = ops.frame_tensors(proj["img"])
+    b = ops.frame_tensors(proj["img"], label=proj["label"])
+    for k in ("range", "reflectivity", "xyz", "normals", "semantics"):
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+    assert b["xyz"].data_ptr() == proj["img"].data_ptr() and b["semantics"].data_ptr() == proj["label"].data_ptr()      # views, not copies
+    assert b["xyz"][1].is_contiguous() and b["range"][2].is_contiguous()
+    c = ops.frame_tensors(proj["img"], label=proj["label"], flip=[True, False, True])                               # flip: the copying kernel
+    d = ops.frame_tensors(proj["img"], flip=[True, False, True])
+    assert c["xyz"].data_ptr() != proj["img"].data_ptr() and all(torch.equal(c[k], d[k]) for k in c)
