@@ -141,15 +141,19 @@ class PeerCounter:
     (one process per GPU); `PeerCounter.create` returns None when that is not the case or the driver refuses the
     mapping, and the caller keeps the NCCL path."""
 
-    def __init__(self, boxes, rank, world, timeout_s=2.0):
+    def __init__(self, boxes, rank, world, timeout_s=None):
         import ctypes as C
         self._boxes = list(boxes)                       # device pointers (ints); boxes[rank] is the own mailbox
+        # how long a kernel waits for its peers before it poisons its result (NaN / INT64_MIN) instead of hanging: long enough for
+        # ordinary skew between ranks (a slow data loader, a first-iteration compile), short enough to surface a dead rank
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("SLU_PEER_TIMEOUT_S", "30"))
         self.rank, self.world, self.timeout_s = int(rank), int(world), float(timeout_s)
         self.boxes_array = (C.c_void_p * self.world)(*[C.c_void_p(b) for b in self._boxes])
         self._closed = False
 
     @classmethod
-    def create(cls, group=None, device=None, timeout_s: float = 2.0):
+    def create(cls, group=None, device=None, timeout_s=None):
         import ctypes as C
         import socket
         from . import _lib
