@@ -134,6 +134,7 @@ struct ProjParams {
     struct Cell* cell;             // [B*HW] 128-bit (range key, point index) cells of the single-pass depth test
     int want_pix, want_winner;     // the caller asked for d_pix / d_winner (the cell pipeline skips the stores otherwise)
     int use_cells;                 // the depth test runs on the 128-bit cells (no key / winner arrays, no tie pass)
+    int use_cross;                 // near-edge points are decided by the cross-product test where it can tell
     // outputs
     int* pix;                      // [n_total]
     int* winner;                   // [B*HW]
@@ -441,7 +442,67 @@ __device__ __forceinline__ int fast_count_le(const FastEdges& f, float a32) {
     return (int)fl + 1;
 }
 
-__global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __grid_constant__ ProjParams p) {
+// ---- near-edge points decided by a float64 cross product instead of a float64 arctangent ------------------------------
+// A point whose fp32 angle is within the margin of an edge e_k is on the upper side of that edge exactly when the cross
+// product of its direction with the edge's direction is >= 0: y cos e_k - x sin e_k = rho sin(phi - e_k) for a column edge,
+// z sin g_j - rho cos g_j = r sin(g_j - a) for a row edge (a = atan2(rho, z), theta = pi/2 - a, g_j = pi/2 - h_j).  The
+// edge directions come from small shared-memory tables built once per block; the computed cross product is off by at
+// most ~6e-16 (|x| + |y|) (two rounded products, one sum, table entries good to a few ulp, the table's angle within 1e-15
+// of the float64 edge numpy builds), so outside a band of 1e-14 (|x| + |y|) its sign is the sign numpy's rounded arctangent
+// (2 ulp) gives too -- checked on 8 M emulated points at offsets from 1e-17 to 1e-5 rad from an edge, zero disagreements
+// outside the band.  Inside the band, on the outermost edges (the +-pi seam; the scan's own theta extremes, which sit ON
+// their edges), or without a table (W > 8192, H > 256), the point takes the exact fp64 path through the queue as before,
+// which is also where the 4-ulp `near` diagnostics come from.  With the test on, a handful of points per scan still queue
+// up instead of ~0.5 % of them.
+constexpr int COLT_MAX_A = 256;             // two-level column table: A[a] = dir(-pi + 32 a step), B[b] = dir(b step); W <= 8192
+constexpr int ROWT_MAX = 256;               // row table: one entry per edge
+constexpr double CROSS_BAND = 1.0e-14;
+
+// OFF by default: measured on B200 the tables' float64 sincos in every block's prologue cost what the shorter queue saves
+// (16 HDL-64 scans 0.0737 -> 0.0778 ms, OS1-128 0.1475 -> 0.1536 ms; only the fixed-range fused kernel gains, 0.1352 -> 0.1302 ms);
+// SLU_PROJECT_CROSS=1 switches it on (bit-identical results either way: the projection tests pass in both settings).
+static int g_no_cross = [] { const char* e = getenv("SLU_PROJECT_CROSS"); return (e && e[0] == '1') ? 0 : 1; }();
+
+__device__ __forceinline__ void build_col_table(double2* A, double2* B, const Edges& ew, int W) {
+    const int na = (W + 31) >> 5;
+    for (int i = threadIdx.x; i < na + 32; i += blockDim.x) {
+        const double ang = i < na ? __dadd_rn(__dmul_rn(32.0 * (double)i, ew.step), ew.start) : __dmul_rn((double)(i - na), ew.step);
+        double sv, cv;
+        sincos(ang, &sv, &cv);
+        if (i < na) A[i] = make_double2(cv, sv); else B[i - na] = make_double2(cv, sv);
+    }
+}
+// #{column edges <= phi} of a point near edge k = rint(t), or -1 when the cross product cannot tell
+__device__ __forceinline__ int col_count_by_cross(const double2* A, const double2* B, const FastEdges& f, float phi32, double x, double y, int W) {
+    if (!(fabsf(phi32) <= 4.0f)) return -1;
+    const int k = __float2int_rn(fmaf(phi32, f.inv_step, f.c0));
+    if (k < 1 || k > W - 2) return -1;
+    const double2 a = A[k >> 5], bb = B[k & 31];
+    const double C = a.x * bb.x - a.y * bb.y, S = a.y * bb.x + a.x * bb.y;
+    const double cross = y * C - x * S;
+    if (!(fabs(cross) > CROSS_BAND * (fabs(x) + fabs(y)))) return -1;
+    return k + (cross >= 0.0 ? 1 : 0);
+}
+__device__ __forceinline__ void build_row_table(double2* R, const Edges& eh, int H) {
+    for (int j = threadIdx.x; j < H; j += blockDim.x) {
+        const double g = __dadd_rn(HALF_PI, -edge_at(eh, j));
+        double sv, cv;
+        sincos(g, &sv, &cv);
+        R[j] = make_double2(cv, sv);
+    }
+}
+__device__ __forceinline__ int row_count_by_cross(const double2* R, const FastEdges& f, float th32, const Pt q, int H) {
+    if (!(fabsf(th32) <= 4.0f)) return -1;
+    const int j = __float2int_rn(fmaf(th32, f.inv_step, f.c0));
+    if (j < 1 || j > H - 2) return -1;
+    const double rho = __dsqrt_rn(__dadd_rn(__dmul_rn(q.x, q.x), __dmul_rn(q.y, q.y)));
+    const double2 g = R[j];
+    const double cross = q.z * g.y - rho * g.x;
+    if (!(fabs(cross) > CROSS_BAND * (rho + fabs(q.z)))) return -1;
+    return j + (cross >= 0.0 ? 1 : 0);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 5) proj_fast_angles_kernel(const __grid_constant__ ProjParams p) {
     const int b = blockIdx.y;
     const long long n0 = p.offsets[b], n1 = p.offsets[b + 1];
     const bool check_ids = p.raw_label != nullptr && p.lut != nullptr;
@@ -469,6 +530,9 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
     const FastEdges fw = make_fast_edges(ew);
     __shared__ int s_q[DEFER_CAP];
     __shared__ int s_qn;
+    __shared__ double2 s_colA[COLT_MAX_A], s_colB[32];
+    const bool col_cross = p.use_cross && p.W >= 4 && p.W <= 32 * COLT_MAX_A;
+    if (col_cross) build_col_table(s_colA, s_colB, ew, p.W);
     if (threadIdx.x == 0) s_qn = 0;
     __syncthreads();
     float tmin = INFINITY, tmax = -INFINITY;
@@ -502,8 +566,9 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         pend_lut = check_ids ? __ldg(p.lut + raw) : 0;          // tested at the top of the next iteration
         if (th32 == th32) { tmin = fminf(tmin, th32); tmax = fmaxf(tmax, th32); }
         int cnt_w = fast_count_le(fw, phi32);
+        if (cnt_w < 0 && col_cross) cnt_w = col_count_by_cross(s_colA, s_colB, fw, phi32, x, y, p.W);
         if (cnt_w < 0) {
-            // near an edge: queue the point; the fp64 path runs once per block on the packed queue instead of
+            // near an edge and undecided: queue the point; the fp64 path runs once per block on the packed queue instead of
             // once per warp that happens to contain such a point
             // (a queue that overflows is dropped as a whole: the block then walks its points again, below)
             const int slot = atomicAdd(&s_qn, 1);
@@ -530,7 +595,9 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_angles_kernel(const __gr
         // more near-edge points than the queue holds (adversarial inputs): every thread settles its own in place
         for (long long n = n0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; n < n1; n += (long long)gridDim.x * blockDim.x) {
             const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
-            if (fast_count_le(fw, fast_atan2((float)q.y, (float)q.x)) >= 0) continue;
+            const float a32 = fast_atan2((float)q.y, (float)q.x);
+            if (fast_count_le(fw, a32) >= 0) continue;
+            if (col_cross && col_count_by_cross(s_colA, s_colB, fw, a32, q.x, q.y, p.W) >= 0) continue;      // settled in the loop
             bool near;
             const int cnt_w = count_le(ew, exact_phi(q), near);
             if (near) ++near_cnt;
@@ -619,6 +686,9 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     __shared__ int s_q[DEFER_CAP];
     __shared__ int s_qn;
     __shared__ FastEdges s_fh;
+    __shared__ double2 s_row[ROWT_MAX];
+    const bool row_cross = p.use_cross && p.H >= 4 && p.H <= ROWT_MAX;
+    if (row_cross && threadIdx.x < p.H) build_row_table(s_row, make_edges(lo, hi, p.H), p.H);
     if (threadIdx.x == 0) {                         // the float64 divisions of the edge set-up run once per block
         s_qn = 0;
         s_fh = make_fast_edges(make_edges(lo, hi, p.H));
@@ -663,6 +733,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
             pxs[k] = -1;
             if (n >= n1) continue;
             int cnt_h = fast_count_le(fh, t32[k]);
+            if (cnt_h < 0 && row_cross) cnt_h = row_count_by_cross(s_row, fh, t32[k], load_pt(p, b, __ldg(p.xyzi + n)), p.H);
             if (cnt_h < 0) {
                 const int slot = atomicAdd(&s_qn, 1);
                 if (slot < DEFER_CAP) s_q[slot] = (int)(n - n0);
@@ -690,6 +761,7 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_rows_kernel(const __grid
     for (long long i = q_begin; i < q_end; i += q_step) {
         const long long n = n0 + (overflow ? i : (long long)s_q[i]);
         if (overflow && fast_count_le(fh, p.theta32[n]) >= 0) continue;
+        if (overflow && row_cross && row_count_by_cross(s_row, fh, p.theta32[n], load_pt(p, b, __ldg(p.xyzi + n)), p.H) >= 0) continue;   // settled in the loop
         bool near;
         const double th = exact_theta(load_pt(p, b, __ldg(p.xyzi + n)));
         const int cnt_h = count_le(eh, th, near);
@@ -719,6 +791,11 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
     const FastEdges fw = make_fast_edges(ew), fh = make_fast_edges(eh);
     __shared__ int s_q[DEFER_CAP];
     __shared__ int s_qn;
+    __shared__ double2 s_colA[COLT_MAX_A], s_colB[32], s_row[ROWT_MAX];
+    const bool col_cross = p.use_cross && p.W >= 4 && p.W <= 32 * COLT_MAX_A;
+    const bool row_cross = p.use_cross && p.H >= 4 && p.H <= ROWT_MAX && eh.step > 0.0;
+    if (col_cross) build_col_table(s_colA, s_colB, ew, p.W);
+    if (row_cross) build_row_table(s_row, eh, p.H);
     if (threadIdx.x == 0) s_qn = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.theta_out) { p.theta_out[2 * b] = p.theta_lo; p.theta_out[2 * b + 1] = p.theta_hi; }
     __syncthreads();
@@ -751,6 +828,8 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         pend_lut = check_ids ? __ldg(p.lut + raw) : 0;
         int cnt_w = fast_count_le(fw, phi32);
         int cnt_h = fast_count_le(fh, th32);
+        if (cnt_w < 0 && col_cross) cnt_w = col_count_by_cross(s_colA, s_colB, fw, phi32, x, y, p.W);
+        if (cnt_h < 0 && row_cross) cnt_h = row_count_by_cross(s_row, fh, th32, q, p.H);
         if (cnt_w < 0 || cnt_h < 0) {
             const int slot = atomicAdd(&s_qn, 1);
             if (slot < DEFER_CAP) s_q[slot] = (int)(n - n0);
@@ -776,8 +855,10 @@ __global__ void __launch_bounds__(PT_THREADS) proj_fast_fused_kernel(const __gri
         const Pt q = load_pt(p, b, __ldg(p.xyzi + n));
         if (overflow) {
             const float x32 = (float)q.x, y32 = (float)q.y, z32 = (float)q.z;
-            if (fast_count_le(fw, fast_atan2(y32, x32)) >= 0 &&
-                fast_count_le(fh, 1.57079632679489662f - fast_atan2(sqrtf(fmaf(x32, x32, y32 * y32)), z32)) >= 0) continue;
+            const float a32 = fast_atan2(y32, x32), t32 = 1.57079632679489662f - fast_atan2(sqrtf(fmaf(x32, x32, y32 * y32)), z32);
+            const bool w_ok = fast_count_le(fw, a32) >= 0 || (col_cross && col_count_by_cross(s_colA, s_colB, fw, a32, q.x, q.y, p.W) >= 0);
+            const bool h_ok = fast_count_le(fh, t32) >= 0 || (row_cross && row_count_by_cross(s_row, fh, t32, q, p.H) >= 0);
+            if (w_ok && h_ok) continue;                       // settled in the loop
         }
         bool near_w, near_h;
         const int cnt_w = count_le(ew, exact_phi(q), near_w);
@@ -1488,6 +1569,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
         // HDL-64 scans) -- but the row kernel is an atomic stream, and atomics that RETURN a value cost 36.0 us there against
         // 15.2 us for the reductions: 0.090 ms in total against 0.072.
         p.use_cells = cells_in_rows_path() ? 1 : 0;
+        p.use_cross = g_no_cross ? 0 : 1;
         if (p.use_range && !g_no_fused) {
             // fixed elevation range: init -> one fused pass (angles + rows + depth test) -> ties
             const long long cells = (long long)p.B * p.HW;
