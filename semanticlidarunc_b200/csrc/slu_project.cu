@@ -458,10 +458,11 @@ constexpr int COLT_MAX_A = 256;             // two-level column table: A[a] = di
 constexpr int ROWT_MAX = 256;               // row table: one entry per edge
 constexpr double CROSS_BAND = 1.0e-14;
 
-// OFF by default: measured on B200 the tables' float64 sincos in every block's prologue cost what the shorter queue saves
-// (16 HDL-64 scans 0.0737 -> 0.0778 ms, OS1-128 0.1475 -> 0.1536 ms; only the fixed-range fused kernel gains, 0.1352 -> 0.1302 ms);
-// SLU_PROJECT_CROSS=1 switches it on (bit-identical results either way: the projection tests pass in both settings).
-static int g_no_cross = [] { const char* e = getenv("SLU_PROJECT_CROSS"); return (e && e[0] == '1') ? 0 : 1; }();
+// Default: ON in the fixed-range fused kernel only.  Measured on B200: the tables' float64 sincos in every block's prologue
+// cost what the shorter queue saves in the two-pass kernels (16 HDL-64 scans 0.0737 -> 0.0778 ms, OS1-128 0.1475 -> 0.1536 ms),
+// while the fused kernel, whose queue carries BOTH angles, gains (0.1352 -> 0.1302 ms).  SLU_PROJECT_CROSS=1 switches it on
+// everywhere, =0 off everywhere (bit-identical results in every setting: the projection tests pass with it on and off).
+static int g_cross_mode = [] { const char* e = getenv("SLU_PROJECT_CROSS"); return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : 2; }();   // 2 = fused kernel only
 
 __device__ __forceinline__ void build_col_table(double2* A, double2* B, const Edges& ew, int W) {
     const int na = (W + 31) >> 5;
@@ -1569,7 +1570,7 @@ static int project_common(ProjParams& p, int64_t n_total, void* d_work, int32_t*
         // HDL-64 scans) -- but the row kernel is an atomic stream, and atomics that RETURN a value cost 36.0 us there against
         // 15.2 us for the reductions: 0.090 ms in total against 0.072.
         p.use_cells = cells_in_rows_path() ? 1 : 0;
-        p.use_cross = g_no_cross ? 0 : 1;
+        p.use_cross = g_cross_mode == 1 || (g_cross_mode == 2 && p.use_range && !g_no_fused) ? 1 : 0;
         if (p.use_range && !g_no_fused) {
             // fixed elevation range: init -> one fused pass (angles + rows + depth test) -> ties
             const long long cells = (long long)p.B * p.HW;
